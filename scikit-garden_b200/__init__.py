@@ -1,0 +1,23 @@
+"""scikit-garden_b200: the quantile-forest predict path of scikit-garden, B200-native.
+
+Import as ``skgarden_b200`` (the shim ``skgarden_b200.py`` at the repo root maps the
+name to this directory).  Public surface = the reference's for this path
+(skgarden/quantile/__init__.py:1-10, forests only):
+
+    RandomForestQuantileRegressor, ExtraTreesQuantileRegressor
+
+plus the lower-level pieces the estimators are made of: ``flatten_forest`` /
+``FlatForest`` (host layout), ``DeviceForest`` (HBM-resident forest + kernel calls).
+"""
+from .ensemble import ExtraTreesQuantileRegressor, RandomForestQuantileRegressor
+from .flatten import FlatForest, bootstrap_counts, flatten_forest
+
+__all__ = ["RandomForestQuantileRegressor", "ExtraTreesQuantileRegressor", "FlatForest",
+           "flatten_forest", "bootstrap_counts", "DeviceForest"]
+
+
+def __getattr__(name):          # DeviceForest pulls in torch; load it on first use
+    if name == "DeviceForest":
+        from .device_forest import DeviceForest
+        return DeviceForest
+    raise AttributeError(name)

@@ -1,0 +1,151 @@
+// Host-side forest flattener (no CUDA calls): one fitted scikit-learn tree ->
+// 8-byte packed nodes in depth-first preorder + the leaf -> in-bag member lists that
+// replace the dense (T,N) y_train_leaves_ / y_weights_ arrays of the reference
+// (skgarden/quantile/ensemble.py:83-101).  Layout documented in include/qforest_b200.h.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "qf_internal.h"
+
+namespace {
+
+// Largest float32 <= t.  sklearn compares the float32 feature with the float64
+// threshold in double (sklearn:tree/_tree.pyx:989); for float32 x,
+//   (double)x <= t   <=>   x <= floor_f32(t)
+// so the device can compare in float32 and still decide exactly like sklearn.
+inline float floor_to_f32(double t) {
+    float f = static_cast<float>(t);            // round to nearest
+    if (static_cast<double>(f) > t) f = std::nextafterf(f, -INFINITY);
+    return f;
+}
+
+inline uint32_t f32_bits(float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, sizeof(u));
+    return u;
+}
+
+}  // namespace
+
+extern "C" int64_t qf_count_inbag(int64_t n_train, const int64_t* counts) {
+    if (counts == nullptr) return n_train;
+    int64_t m = 0;
+    for (int64_t j = 0; j < n_train; ++j) m += counts[j] > 0;
+    return m;
+}
+
+extern "C" int qf_pack_tree(int64_t n_nodes, const int64_t* left, const int64_t* right,
+                            const int64_t* feature, const double* threshold,
+                            int32_t feature_bits, int64_t n_train, const int64_t* train_leaves,
+                            const int64_t* counts, const int64_t* sorter, uint64_t member_base,
+                            uint64_t* nodes_out, int32_t* node_id_out, uint64_t* members_out,
+                            int64_t* n_inbag_out, int32_t* max_leaf_members_out,
+                            int32_t* max_depth_out, double* sum_sq_leaf_members_out) {
+    if (n_nodes <= 0 || !left || !right || !feature || !threshold || !train_leaves || !sorter ||
+        !nodes_out || !node_id_out || !members_out || n_train <= 0)
+        return qf::fail(QF_ERR_INVALID, "qf_pack_tree: null or empty argument");
+    if (feature_bits < 1 || feature_bits > 24)
+        return qf::fail(QF_ERR_INVALID, "qf_pack_tree: feature_bits must be in [1,24]");
+    if (n_nodes >= (int64_t(1) << 31) || n_train >= (int64_t(1) << 31))
+        return qf::fail(QF_ERR_LIMIT, "qf_pack_tree: more than 2^31 nodes or training rows");
+    const uint32_t max_off = (1u << (31 - feature_bits)) - 1u;
+
+    // pass 1: depth-first preorder numbering (left subtree first).  sklearn's
+    // depth-first builder already numbers this way; the best-first builder
+    // (max_leaf_nodes) does not, so always renumber and keep the map.
+    std::vector<int32_t> pos_of(n_nodes, -1);
+    std::vector<int64_t> stack;
+    std::vector<int32_t> depth_stack;
+    stack.reserve(128);
+    depth_stack.reserve(128);
+    stack.push_back(0);
+    depth_stack.push_back(0);
+    int32_t next = 0, max_depth = 0;
+    while (!stack.empty()) {
+        const int64_t nd = stack.back();
+        const int32_t d = depth_stack.back();
+        stack.pop_back();
+        depth_stack.pop_back();
+        if (nd < 0 || nd >= n_nodes || pos_of[nd] != -1)
+            return qf::fail(QF_ERR_INVALID, "qf_pack_tree: children arrays do not form a tree");
+        pos_of[nd] = next;
+        node_id_out[next] = static_cast<int32_t>(nd);
+        ++next;
+        if (d > max_depth) max_depth = d;
+        if (left[nd] != -1) {              // sklearn: leaf <=> children_left == -1 (_tree.pyx:978)
+            stack.push_back(right[nd]);
+            depth_stack.push_back(d + 1);
+            stack.push_back(left[nd]);     // popped first -> left child gets position + 1
+            depth_stack.push_back(d + 1);
+        }
+    }
+    if (next != n_nodes)
+        return qf::fail(QF_ERR_INVALID, "qf_pack_tree: unreachable nodes in tree");
+
+    // pass 2: per-leaf in-bag statistics (ensemble.py:94-99: weights = count / sum of counts)
+    std::vector<int64_t> leaf_count_sum(n_nodes, 0);
+    std::vector<uint32_t> leaf_members(n_nodes, 0);
+    int64_t n_inbag = 0;
+    for (int64_t j = 0; j < n_train; ++j) {
+        const int64_t c = counts ? counts[j] : 1;
+        if (c <= 0) continue;                              // out-of-bag: -1 / weight 0 in the reference
+        const int64_t lf = train_leaves[j];
+        if (lf < 0 || lf >= n_nodes || left[lf] != -1)
+            return qf::fail(QF_ERR_INVALID, "qf_pack_tree: train_leaves entry is not a leaf id");
+        leaf_count_sum[lf] += c;
+        leaf_members[lf] += 1;
+        ++n_inbag;
+    }
+    if (member_base + static_cast<uint64_t>(n_inbag) > 0xFFFFFFFFull)
+        return qf::fail(QF_ERR_LIMIT, "qf_pack_tree: more than 2^32-1 member entries in the forest");
+
+    // pass 3: packed nodes; leaves get their member range in packed (preorder) order
+    std::vector<uint32_t> cursor(n_nodes, 0);              // indexed by sklearn id
+    uint64_t running = member_base;
+    uint32_t max_members = 0;
+    double sum_sq = 0.0;
+    for (int64_t p = 0; p < n_nodes; ++p) {
+        const int64_t nd = node_id_out[p];
+        if (left[nd] == -1) {
+            const uint32_t m = leaf_members[nd];
+            cursor[nd] = static_cast<uint32_t>(running);
+            nodes_out[p] = (static_cast<uint64_t>(0x80000000u | m) << 32) | static_cast<uint32_t>(running);
+            running += m;
+            if (m > max_members) max_members = m;
+            sum_sq += static_cast<double>(m) * static_cast<double>(m);
+        } else {
+            if (pos_of[left[nd]] != p + 1)
+                return qf::fail(QF_ERR_INVALID, "qf_pack_tree: internal numbering error");
+            const int64_t off = static_cast<int64_t>(pos_of[right[nd]]) - p;
+            const int64_t f = feature[nd];
+            if (off < 2 || static_cast<uint64_t>(off) > max_off)
+                return qf::fail(QF_ERR_LIMIT, "qf_pack_tree: right-child offset does not fit 31-feature_bits bits");
+            if (f < 0 || f >= (int64_t(1) << feature_bits))
+                return qf::fail(QF_ERR_INVALID, "qf_pack_tree: feature index does not fit feature_bits");
+            const uint32_t hi = (static_cast<uint32_t>(off) << feature_bits) | static_cast<uint32_t>(f);
+            nodes_out[p] = (static_cast<uint64_t>(hi) << 32) | f32_bits(floor_to_f32(threshold[nd]));
+        }
+    }
+
+    // pass 4: members in rank order -> every leaf's list ends up sorted by rank
+    for (int64_t k = 0; k < n_train; ++k) {
+        const int64_t j = sorter[k];
+        if (j < 0 || j >= n_train)
+            return qf::fail(QF_ERR_INVALID, "qf_pack_tree: sorter is not a permutation");
+        const int64_t c = counts ? counts[j] : 1;
+        if (c <= 0) continue;
+        const int64_t lf = train_leaves[j];
+        // ensemble.py:98-99: int64 / int64 -> float64, stored into the float32 y_weights_
+        const float w = static_cast<float>(static_cast<double>(c) / static_cast<double>(leaf_count_sum[lf]));
+        const uint64_t slot = cursor[lf]++ - member_base;
+        members_out[slot] = (static_cast<uint64_t>(f32_bits(w)) << 32) | static_cast<uint32_t>(k);
+    }
+
+    if (n_inbag_out) *n_inbag_out = n_inbag;
+    if (max_leaf_members_out) *max_leaf_members_out = static_cast<int32_t>(max_members);
+    if (max_depth_out) *max_depth_out = max_depth;
+    if (sum_sq_leaf_members_out) *sum_sq_leaf_members_out = sum_sq;
+    return QF_OK;
+}

@@ -1,0 +1,551 @@
+// C ABI (include/qforest_b200.h): forest residency in HBM, launch orchestration, and the
+// host-buffer end-to-end path.  All compute is in the kernels of apply_kernel.cuh and
+// quantile_kernel.cuh; there is no CPU fallback anywhere in this file.
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "apply_kernel.cuh"
+#include "qf_internal.h"
+#include "quantile_kernel.cuh"
+
+namespace qf {
+
+std::string& last_error_slot() {
+    static thread_local std::string slot;
+    return slot;
+}
+
+}  // namespace qf
+
+namespace {
+
+constexpr int64_t kAlign = 256;
+inline int64_t align_up(int64_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+struct HostPipe {                 // per-slot buffers of the host-buffer path
+    cudaStream_t stream = nullptr;
+    float* x = nullptr;
+    double* out = nullptr;
+    void* ws = nullptr;
+    int64_t x_bytes = 0, out_bytes = 0, ws_bytes = 0;
+};
+
+}  // namespace
+
+struct qf_forest {
+    int device = 0;
+    int T = 0, F = 0, fbits = 0;
+    int64_t N = 0, n_nodes = 0, n_members = 0, max_row_members = 0;
+    uint2* d_nodes = nullptr;
+    uint32_t* d_roots = nullptr;
+    int32_t* d_node_ids = nullptr;
+    uint2* d_members = nullptr;
+    float* d_y_sorted = nullptr;
+    double* d_values = nullptr;
+    int64_t device_bytes = 0;
+    int sm_count = 148;
+    // options
+    int apply_row_warps = 0;      // 0 = auto
+    int apply_ilp = 4;
+    int64_t rows_per_chunk = 131072;
+    int cta_capacity = 4096;      // members per row held in shared memory (power of two)
+    int dense_ctas = 0;           // 0 = auto
+    // counters
+    int launches = 0;
+    HostPipe pipe[2];
+    // per-kernel CUDA-event timing of the most recent call (option "profile")
+    int profile = 0;
+    std::vector<cudaEvent_t> event_pool;
+    size_t events_used = 0;
+    struct Span { int kind; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+};
+
+namespace {
+
+enum { SPAN_APPLY = 0, SPAN_QUANTILE = 1, SPAN_OTHER = 2 };
+
+// RAII: records an event pair around a launch when profiling is on
+struct SpanTimer {
+    qf_forest* f;
+    cudaStream_t st;
+    cudaEvent_t b = nullptr;
+    SpanTimer(qf_forest* f_, int kind, cudaStream_t st_) : f(f_), st(st_) {
+        if (!f->profile) return;
+        cudaEvent_t ev[2];
+        for (cudaEvent_t& e : ev) {
+            if (f->events_used == f->event_pool.size()) {
+                cudaEvent_t n;
+                if (cudaEventCreate(&n) != cudaSuccess) return;
+                f->event_pool.push_back(n);
+            }
+            e = f->event_pool[f->events_used++];
+        }
+        cudaEventRecord(ev[0], st);
+        b = ev[1];
+        f->spans.push_back({kind, ev[0], ev[1]});
+    }
+    ~SpanTimer() {
+        if (b) cudaEventRecord(b, st);
+    }
+};
+
+void reset_call_counters(qf_forest* f) {
+    f->launches = 0;
+    f->events_used = 0;
+    f->spans.clear();
+}
+
+struct Plan {                      // workspace carve-up for one chunk of rows
+    int64_t chunk_rows;
+    int cap;                       // shared-memory member capacity of the CTA kernel
+    bool dense_needed;
+    int dense_ctas;
+    int64_t off_seg, off_count, off_rows, off_dense, total;
+};
+
+int next_pow2(int64_t v) {
+    int p = 2;
+    while (p < v && p < (1 << 30)) p <<= 1;
+    return p;
+}
+
+Plan make_plan(const qf_forest* f, int64_t n_rows) {
+    Plan pl;
+    pl.chunk_rows = std::max<int64_t>(1, std::min<int64_t>(n_rows, f->rows_per_chunk));
+    pl.cap = std::min(next_pow2(std::max<int64_t>(f->max_row_members, 2)), f->cta_capacity);
+    pl.dense_needed = f->max_row_members > pl.cap;
+    pl.dense_ctas = 0;
+    if (pl.dense_needed) {
+        // bound the scratch to ~2 GiB
+        const int64_t per = qf::dense_scratch_bytes(f->N);
+        int64_t g = f->dense_ctas > 0 ? f->dense_ctas : f->sm_count;
+        g = std::min<int64_t>(g, std::max<int64_t>(1, (int64_t(2) << 30) / per));
+        pl.dense_ctas = static_cast<int>(std::min<int64_t>(g, pl.chunk_rows));
+    }
+    int64_t o = 0;
+    pl.off_seg = o;   o += align_up(pl.chunk_rows * f->T * 8);
+    pl.off_count = o; o += kAlign;
+    pl.off_rows = o;  o += align_up(pl.chunk_rows * 4);
+    pl.off_dense = o; o += pl.dense_needed ? qf::dense_scratch_bytes(f->N) * pl.dense_ctas : 0;
+    pl.total = o;
+    return pl;
+}
+
+int pick_row_warps(const qf_forest* f) {
+    if (f->apply_row_warps > 0) return f->apply_row_warps;
+    // keep the transposed row tile (F * 32*row_warps * 4 B) around 16 KB per CTA
+    int rw = 8;
+    while (rw > 1 && static_cast<int64_t>(f->F) * 32 * rw * 4 > 16384) rw >>= 1;
+    return rw;
+}
+
+template <int EMIT>
+int launch_apply(qf_forest* f, const float* X, int64_t n, int64_t ldx, void* out, cudaStream_t st) {
+    qf::ApplyParams ap;
+    ap.nodes = f->d_nodes;
+    ap.roots = f->d_roots;
+    ap.X = X;
+    ap.ldx = ldx;
+    ap.n = n;
+    ap.T = f->T;
+    ap.F = f->F;
+    ap.fbits = f->fbits;
+    ap.row_warps = pick_row_warps(f);
+    const int rows_per_cta = 32 * ap.row_warps;
+    const size_t smem = static_cast<size_t>(f->F) * rows_per_cta * sizeof(float);
+    if (smem > 200 * 1024)
+        return qf::fail(QF_ERR_LIMIT, "apply: n_features too large for the shared-memory row tile");
+    const int64_t grid = (n + rows_per_cta - 1) / rows_per_cta;
+    auto run = [&](auto kernel) -> int {
+        if (smem > 48 * 1024)
+            QF_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(smem)));
+        {
+            SpanTimer span(f, SPAN_APPLY, st);
+            kernel<<<static_cast<unsigned>(grid), qf::kApplyThreads, smem, st>>>(ap, out);
+        }
+        QF_CUDA_TRY(cudaGetLastError());
+        ++f->launches;
+        return QF_OK;
+    };
+    switch (f->apply_ilp) {
+        case 1: return run(qf::apply_kernel<1, EMIT>);
+        case 2: return run(qf::apply_kernel<2, EMIT>);
+        case 8: return run(qf::apply_kernel<8, EMIT>);
+        default: return run(qf::apply_kernel<4, EMIT>);
+    }
+}
+
+int check_forest_call(const qf_forest* f, const void* X, int64_t n, int64_t ldx, const void* out,
+                      const char* who) {
+    if (!f) return qf::fail(QF_ERR_INVALID, std::string(who) + ": null forest");
+    if (n < 0 || (n > 0 && (!X || !out)))
+        return qf::fail(QF_ERR_INVALID, std::string(who) + ": null buffer or negative row count");
+    if (ldx < f->F) return qf::fail(QF_ERR_INVALID, std::string(who) + ": ldx < n_features");
+    return QF_OK;
+}
+
+// `pl` is the caller's carve-up of `ws` (made once for the largest chunk, so that the
+// zeroed dense scratch stays where the kernels expect it for every chunk).
+int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, const double* q_host,
+                        int nq, double* out, int mode, const Plan& pl, void* ws, int64_t ws_bytes,
+                        cudaStream_t st) {
+    (void)mode;  // QF_MODE_FAST currently runs the exact kernels (a superset of its contract)
+    if (ws_bytes < pl.total || (!ws && pl.total > 0))
+        return qf::fail(QF_ERR_WORKSPACE, "predict_quantiles: workspace too small");
+    unsigned char* base = static_cast<unsigned char*>(ws);
+    uint2* seg = reinterpret_cast<uint2*>(base + pl.off_seg);
+    int* over_count = reinterpret_cast<int*>(base + pl.off_count);
+    int* over_rows = reinterpret_cast<int*>(base + pl.off_rows);
+
+    const int threads = pl.cap <= 256 ? 64 : 256;
+    const size_t smem = static_cast<size_t>(pl.cap) * 16 + static_cast<size_t>(f->T) * 8 + 16;
+    if (smem > 220 * 1024)
+        return qf::fail(QF_ERR_LIMIT, "predict_quantiles: n_estimators too large for shared memory");
+    if (threads == 64)
+        QF_CUDA_TRY(cudaFuncSetAttribute(qf::quantile_cta_kernel<64>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    else
+        QF_CUDA_TRY(cudaFuncSetAttribute(qf::quantile_cta_kernel<256>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+
+    for (int64_t r0 = 0; r0 < n; r0 += pl.chunk_rows) {
+        const int64_t rows = std::min(pl.chunk_rows, n - r0);
+        int rc = launch_apply<qf::APPLY_EMIT_SEGMENT>(f, X + r0 * ldx, rows, ldx, seg, st);
+        if (rc != QF_OK) return rc;
+        for (int q0 = 0; q0 < nq; q0 += qf::kMaxQuantilesPerLaunch) {
+            const int qn = std::min(qf::kMaxQuantilesPerLaunch, nq - q0);
+            qf::QuantileList ql;
+            std::memset(&ql, 0, sizeof(ql));
+            for (int i = 0; i < qn; ++i) ql.q[i] = q_host[q0 + i];
+            qf::QuantileParams qp;
+            qp.seg = seg;
+            qp.members = f->d_members;
+            qp.y_sorted = f->d_y_sorted;
+            qp.out = out + r0 * nq + q0;
+            qp.n = rows;
+            qp.ldo = nq;
+            qp.T = f->T;
+            qp.Q = qn;
+            qp.cap = pl.cap;
+            qp.overflow_count = over_count;
+            qp.overflow_rows = over_rows;
+            if (pl.dense_needed) QF_CUDA_TRY(cudaMemsetAsync(over_count, 0, sizeof(int), st));
+            {
+                SpanTimer span(f, SPAN_QUANTILE, st);
+                if (threads == 64)
+                    qf::quantile_cta_kernel<64><<<static_cast<unsigned>(rows), 64, smem, st>>>(qp, ql);
+                else
+                    qf::quantile_cta_kernel<256><<<static_cast<unsigned>(rows), 256, smem, st>>>(qp, ql);
+            }
+            QF_CUDA_TRY(cudaGetLastError());
+            ++f->launches;
+            if (pl.dense_needed) {
+                SpanTimer span(f, SPAN_QUANTILE, st);
+                qf::quantile_dense_kernel<256><<<pl.dense_ctas, 256, 0, st>>>(
+                    qp, ql, base + pl.off_dense, f->N);
+                QF_CUDA_TRY(cudaGetLastError());
+                ++f->launches;
+            }
+        }
+    }
+    return QF_OK;
+}
+
+// the dense scratch must start zeroed (the kernel restores it after every row)
+int zero_dense_scratch(const qf_forest* f, const Plan& pl, void* ws, cudaStream_t st) {
+    if (!pl.dense_needed) return QF_OK;
+    QF_CUDA_TRY(cudaMemsetAsync(static_cast<unsigned char*>(ws) + pl.off_dense, 0,
+                                qf::dense_scratch_bytes(f->N) * pl.dense_ctas, st));
+    return QF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qf_abi_version(void) { return QF_ABI_VERSION; }
+
+const char* qf_last_error(void) { return qf::last_error_slot().c_str(); }
+
+int qf_forest_create(const qf_forest_desc* d, qf_forest** out) {
+    if (!d || !out) return qf::fail(QF_ERR_INVALID, "qf_forest_create: null argument");
+    *out = nullptr;
+    if (d->n_trees <= 0 || d->n_features <= 0 || d->n_train <= 0 || d->n_nodes <= 0 ||
+        d->n_members <= 0 || !d->nodes || !d->tree_offsets || !d->members || !d->y_sorted)
+        return qf::fail(QF_ERR_INVALID, "qf_forest_create: empty forest or null array");
+    if (d->feature_bits < 1 || d->feature_bits > 24 || (int64_t(1) << d->feature_bits) < d->n_features)
+        return qf::fail(QF_ERR_INVALID, "qf_forest_create: feature_bits does not cover n_features");
+    if (d->n_nodes >= (int64_t(1) << 31) || d->n_members > 0xFFFFFFFFll || d->n_train >= (int64_t(1) << 31))
+        return qf::fail(QF_ERR_LIMIT, "qf_forest_create: forest exceeds the 32-bit packed layout");
+    int count = 0;
+    QF_CUDA_TRY(cudaGetDeviceCount(&count));
+    if (d->device < 0 || d->device >= count)
+        return qf::fail(QF_ERR_CUDA, "qf_forest_create: no such CUDA device");
+    DeviceGuard guard(d->device);
+    if (!guard.ok) return qf::fail(QF_ERR_CUDA, "qf_forest_create: cudaSetDevice failed");
+    cudaDeviceProp prop;
+    QF_CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
+    if (prop.major != 10)
+        return qf::fail(QF_ERR_CUDA, "qf_forest_create: device is not sm_100 (this library has sm_100a code only)");
+
+    qf_forest* f = new qf_forest();
+    f->device = d->device;
+    f->T = d->n_trees;
+    f->F = d->n_features;
+    f->fbits = d->feature_bits;
+    f->N = d->n_train;
+    f->n_nodes = d->n_nodes;
+    f->n_members = d->n_members;
+    f->max_row_members = d->max_row_members > 0 ? d->max_row_members : d->n_members;
+    f->sm_count = prop.multiProcessorCount;
+
+    std::vector<uint32_t> roots(d->n_trees);
+    for (int t = 0; t < d->n_trees; ++t) roots[t] = static_cast<uint32_t>(d->tree_offsets[t]);
+
+    auto upload = [&](void** dst, const void* src, int64_t bytes) -> int {
+        QF_CUDA_TRY(cudaMalloc(dst, static_cast<size_t>(bytes)));
+        // cudaMemcpyDefault: the source may be host memory or (UVA) device memory, e.g. a
+        // buffer that was just broadcast to this rank over NCCL
+        QF_CUDA_TRY(cudaMemcpy(*dst, src, static_cast<size_t>(bytes), cudaMemcpyDefault));
+        f->device_bytes += bytes;
+        return QF_OK;
+    };
+    int rc = upload(reinterpret_cast<void**>(&f->d_nodes), d->nodes, d->n_nodes * 8);
+    if (rc == QF_OK) rc = upload(reinterpret_cast<void**>(&f->d_roots), roots.data(), d->n_trees * 4);
+    if (rc == QF_OK && d->node_ids)
+        rc = upload(reinterpret_cast<void**>(&f->d_node_ids), d->node_ids, d->n_nodes * 4);
+    if (rc == QF_OK) rc = upload(reinterpret_cast<void**>(&f->d_members), d->members, d->n_members * 8);
+    if (rc == QF_OK) rc = upload(reinterpret_cast<void**>(&f->d_y_sorted), d->y_sorted, d->n_train * 4);
+    if (rc == QF_OK && d->leaf_values)
+        rc = upload(reinterpret_cast<void**>(&f->d_values), d->leaf_values, d->n_nodes * 8);
+    if (rc != QF_OK) {
+        const std::string keep = qf::last_error_slot();
+        qf_forest_destroy(f);
+        return qf::fail(rc, keep);
+    }
+    *out = f;
+    return QF_OK;
+}
+
+void qf_forest_destroy(qf_forest* f) {
+    if (!f) return;
+    DeviceGuard guard(f->device);
+    cudaFree(f->d_nodes);
+    cudaFree(f->d_roots);
+    cudaFree(f->d_node_ids);
+    cudaFree(f->d_members);
+    cudaFree(f->d_y_sorted);
+    cudaFree(f->d_values);
+    for (cudaEvent_t e : f->event_pool) cudaEventDestroy(e);
+    for (HostPipe& hp : f->pipe) {
+        cudaFree(hp.x);
+        cudaFree(hp.out);
+        cudaFree(hp.ws);
+        if (hp.stream) cudaStreamDestroy(hp.stream);
+    }
+    delete f;
+}
+
+int64_t qf_forest_device_bytes(const qf_forest* f) { return f ? f->device_bytes : 0; }
+
+int64_t qf_forest_workspace_bytes(const qf_forest* f, int64_t n_rows, int32_t n_quantiles) {
+    (void)n_quantiles;
+    if (!f || n_rows < 0) return 0;
+    return make_plan(f, n_rows).total;
+}
+
+int qf_forest_last_launches(const qf_forest* f) { return f ? f->launches : 0; }
+
+int qf_forest_last_timings(qf_forest* f, double* apply_ms, double* quantile_ms) {
+    if (!f) return qf::fail(QF_ERR_INVALID, "qf_forest_last_timings: null forest");
+    DeviceGuard guard(f->device);
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (const qf_forest::Span& s : f->spans) {
+        QF_CUDA_TRY(cudaEventSynchronize(s.b));
+        float ms = 0.0f;
+        QF_CUDA_TRY(cudaEventElapsedTime(&ms, s.a, s.b));
+        acc[s.kind] += ms;
+    }
+    if (apply_ms) *apply_ms = acc[SPAN_APPLY];
+    if (quantile_ms) *quantile_ms = acc[SPAN_QUANTILE];
+    return QF_OK;
+}
+
+int qf_forest_set_option(qf_forest* f, const char* key, int64_t value) {
+    if (!f || !key) return qf::fail(QF_ERR_INVALID, "qf_forest_set_option: null argument");
+    const std::string k(key);
+    if (k == "apply_row_warps") {
+        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8)
+            return qf::fail(QF_ERR_INVALID, "apply_row_warps must be 0 (auto), 1, 2, 4 or 8");
+        f->apply_row_warps = static_cast<int>(value);
+    } else if (k == "apply_ilp") {
+        if (value != 1 && value != 2 && value != 4 && value != 8)
+            return qf::fail(QF_ERR_INVALID, "apply_ilp must be 1, 2, 4 or 8");
+        f->apply_ilp = static_cast<int>(value);
+    } else if (k == "rows_per_chunk") {
+        if (value < 1) return qf::fail(QF_ERR_INVALID, "rows_per_chunk must be >= 1");
+        f->rows_per_chunk = value;
+    } else if (k == "cta_capacity") {
+        if (value < 2 || value > 8192 || (value & (value - 1)))
+            return qf::fail(QF_ERR_INVALID, "cta_capacity must be a power of two in [2, 8192]");
+        f->cta_capacity = static_cast<int>(value);
+    } else if (k == "profile") {
+        f->profile = value != 0;
+    } else if (k == "dense_ctas") {
+        if (value < 0) return qf::fail(QF_ERR_INVALID, "dense_ctas must be >= 0");
+        f->dense_ctas = static_cast<int>(value);
+    } else {
+        return qf::fail(QF_ERR_INVALID, "qf_forest_set_option: unknown key " + k);
+    }
+    return QF_OK;
+}
+
+int qf_forest_apply(qf_forest* f, const float* X, int64_t n, int64_t ldx, int64_t* leaves,
+                    void* ws, int64_t ws_bytes, void* stream) {
+    int rc = check_forest_call(f, X, n, ldx, leaves, "qf_forest_apply");
+    if (rc != QF_OK) return rc;
+    reset_call_counters(f);
+    if (n == 0) return QF_OK;
+    DeviceGuard guard(f->device);
+    const Plan pl = make_plan(f, n);
+    if (ws_bytes < pl.total || !ws) return qf::fail(QF_ERR_WORKSPACE, "qf_forest_apply: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int32_t* idx = reinterpret_cast<int32_t*>(static_cast<unsigned char*>(ws) + pl.off_seg);
+    for (int64_t r0 = 0; r0 < n; r0 += pl.chunk_rows) {
+        const int64_t rows = std::min(pl.chunk_rows, n - r0);
+        rc = launch_apply<qf::APPLY_EMIT_NODE>(f, X + r0 * ldx, rows, ldx, idx, st);
+        if (rc != QF_OK) return rc;
+        const int64_t total = rows * f->T;
+        const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, f->sm_count * 16));
+        qf::node_to_sklearn_id_kernel<<<blocks, 256, 0, st>>>(idx, total, f->T, f->d_roots, f->d_node_ids,
+                                                             leaves + r0 * f->T);
+        QF_CUDA_TRY(cudaGetLastError());
+        ++f->launches;
+    }
+    return QF_OK;
+}
+
+int qf_forest_predict_mean(qf_forest* f, const float* X, int64_t n, int64_t ldx, double* out,
+                           void* ws, int64_t ws_bytes, void* stream) {
+    int rc = check_forest_call(f, X, n, ldx, out, "qf_forest_predict_mean");
+    if (rc != QF_OK) return rc;
+    if (!f->d_values) return qf::fail(QF_ERR_INVALID, "qf_forest_predict_mean: forest was created without leaf_values");
+    reset_call_counters(f);
+    if (n == 0) return QF_OK;
+    DeviceGuard guard(f->device);
+    const Plan pl = make_plan(f, n);
+    if (ws_bytes < pl.total || !ws) return qf::fail(QF_ERR_WORKSPACE, "qf_forest_predict_mean: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int32_t* idx = reinterpret_cast<int32_t*>(static_cast<unsigned char*>(ws) + pl.off_seg);
+    for (int64_t r0 = 0; r0 < n; r0 += pl.chunk_rows) {
+        const int64_t rows = std::min(pl.chunk_rows, n - r0);
+        rc = launch_apply<qf::APPLY_EMIT_NODE>(f, X + r0 * ldx, rows, ldx, idx, st);
+        if (rc != QF_OK) return rc;
+        qf::mean_kernel<<<static_cast<unsigned>((rows + 127) / 128), 128, 0, st>>>(idx, rows, f->T, f->d_values,
+                                                                                   out + r0);
+        QF_CUDA_TRY(cudaGetLastError());
+        ++f->launches;
+    }
+    return QF_OK;
+}
+
+int qf_forest_predict_quantiles(qf_forest* f, const float* X, int64_t n, int64_t ldx,
+                                const double* q_host, int32_t nq, double* out, int32_t mode,
+                                void* ws, int64_t ws_bytes, void* stream) {
+    int rc = check_forest_call(f, X, n, ldx, out, "qf_forest_predict_quantiles");
+    if (rc != QF_OK) return rc;
+    if (nq <= 0 || !q_host) return qf::fail(QF_ERR_INVALID, "qf_forest_predict_quantiles: no quantiles");
+    for (int i = 0; i < nq; ++i)
+        if (!(q_host[i] >= 0.0 && q_host[i] <= 100.0))          // utils.py:42-44
+            return qf::fail(QF_ERR_INVALID, "q should be in-between 0 and 100");
+    if (mode != QF_MODE_EXACT && mode != QF_MODE_FAST)
+        return qf::fail(QF_ERR_INVALID, "qf_forest_predict_quantiles: unknown mode");
+    reset_call_counters(f);
+    if (n == 0) return QF_OK;
+    DeviceGuard guard(f->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Plan pl = make_plan(f, n);
+    if (ws_bytes < pl.total || !ws)
+        return qf::fail(QF_ERR_WORKSPACE, "qf_forest_predict_quantiles: workspace too small");
+    rc = zero_dense_scratch(f, pl, ws, st);
+    if (rc != QF_OK) return rc;
+    return quantiles_on_stream(f, X, n, ldx, q_host, nq, out, mode, pl, ws, ws_bytes, st);
+}
+
+int qf_forest_predict_quantiles_host(qf_forest* f, const float* X_host, int64_t n, int64_t ldx,
+                                     const double* q_host, int32_t nq, double* out_host, int32_t mode,
+                                     int64_t chunk_rows) {
+    int rc = check_forest_call(f, X_host, n, ldx, out_host, "qf_forest_predict_quantiles_host");
+    if (rc != QF_OK) return rc;
+    if (nq <= 0 || !q_host) return qf::fail(QF_ERR_INVALID, "qf_forest_predict_quantiles_host: no quantiles");
+    for (int i = 0; i < nq; ++i)
+        if (!(q_host[i] >= 0.0 && q_host[i] <= 100.0))
+            return qf::fail(QF_ERR_INVALID, "q should be in-between 0 and 100");
+    reset_call_counters(f);
+    if (n == 0) return QF_OK;
+    DeviceGuard guard(f->device);
+    if (chunk_rows <= 0) chunk_rows = f->rows_per_chunk;
+    chunk_rows = std::min(chunk_rows, n);
+    const Plan pl = make_plan(f, chunk_rows);
+    const int64_t x_bytes = chunk_rows * f->F * 4, out_bytes = chunk_rows * nq * 8;
+    const int slots = n > chunk_rows ? 2 : 1;
+    for (int s = 0; s < slots; ++s) {
+        HostPipe& hp = f->pipe[s];
+        if (!hp.stream) QF_CUDA_TRY(cudaStreamCreateWithFlags(&hp.stream, cudaStreamNonBlocking));
+        if (hp.x_bytes < x_bytes) {
+            cudaFree(hp.x); hp.x = nullptr; hp.x_bytes = 0;
+            QF_CUDA_TRY(cudaMalloc(&hp.x, x_bytes)); hp.x_bytes = x_bytes;
+        }
+        if (hp.out_bytes < out_bytes) {
+            cudaFree(hp.out); hp.out = nullptr; hp.out_bytes = 0;
+            QF_CUDA_TRY(cudaMalloc(&hp.out, out_bytes)); hp.out_bytes = out_bytes;
+        }
+        if (hp.ws_bytes < pl.total) {
+            cudaFree(hp.ws); hp.ws = nullptr; hp.ws_bytes = 0;
+            QF_CUDA_TRY(cudaMalloc(&hp.ws, pl.total)); hp.ws_bytes = pl.total;
+        }
+        rc = zero_dense_scratch(f, pl, hp.ws, hp.stream);
+        if (rc != QF_OK) return rc;
+    }
+    int total_launches = 0;
+    int slot = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += chunk_rows, slot ^= 1) {
+        const int64_t rows = std::min(chunk_rows, n - r0);
+        HostPipe& hp = f->pipe[slots == 2 ? slot : 0];
+        // rows of X are compacted to F columns on the device (ldx may exceed F on the host)
+        if (ldx == f->F) {
+            QF_CUDA_TRY(cudaMemcpyAsync(hp.x, X_host + r0 * ldx, rows * f->F * 4, cudaMemcpyHostToDevice, hp.stream));
+        } else {
+            QF_CUDA_TRY(cudaMemcpy2DAsync(hp.x, f->F * 4, X_host + r0 * ldx, ldx * 4, f->F * 4, rows,
+                                          cudaMemcpyHostToDevice, hp.stream));
+        }
+        f->launches = 0;
+        rc = quantiles_on_stream(f, hp.x, rows, f->F, q_host, nq, hp.out, mode, pl, hp.ws, hp.ws_bytes, hp.stream);
+        if (rc != QF_OK) return rc;
+        total_launches += f->launches;
+        QF_CUDA_TRY(cudaMemcpyAsync(out_host + r0 * nq, hp.out, rows * nq * 8, cudaMemcpyDeviceToHost, hp.stream));
+    }
+    for (int s = 0; s < slots; ++s) QF_CUDA_TRY(cudaStreamSynchronize(f->pipe[s].stream));
+    f->launches = total_launches;
+    return QF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,376 @@
+// K2 -- fused leaf co-membership weighting + weighted percentile for sm_100a.
+//
+// Replaces, per test row, the dense (T,N) mask + masked sum of
+// skgarden/quantile/ensemble.py:137-140 and weighted_percentile
+// (skgarden/quantile/utils.py:46-81) by a pass over only the non-zero weights:
+//   gather the (rank, weight) members of the row's T leaves  ->  order by rank, merging
+//   the contributions of a sample that several trees share  ->  running sum  ->  select /
+//   interpolate every requested percentile.
+//
+// Arithmetic contract (QF_MODE_EXACT, bit-identical to the reference under numpy >= 2):
+//   W_j  = ((0 + w_t1[j]) + w_t2[j]) + ...   float32, trees in increasing order  (ensemble.py:140)
+//   C_k  = float32 running sum of W in rank order                                (utils.py:68)
+//   p_k  = (100f / C_last) * (C_k - W_k / 2)                                     (utils.py:72)
+//   i    = numpy searchsorted(p, q, 'left') with the compare done in float64     (utils.py:73)
+//   out  = a_first / a_last at the ends, else a_s + ((float)q - p_s)/(p_{s+1} - p_s) * (a_{s+1} - a_s)
+//          with separately rounded float32 operations                           (utils.py:74-81)
+// All float32 operations use the _rn intrinsics so that nvcc never contracts them to FMA.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace qf {
+
+constexpr int kMaxQuantilesPerLaunch = 128;
+
+struct QuantileList {
+    double q[kMaxQuantilesPerLaunch];
+};
+
+struct QuantileParams {
+    const uint2* __restrict__ seg;        // [n][T] (member start, member count) from K1
+    const uint2* __restrict__ members;    // (rank, float bits of weight)
+    const float* __restrict__ y_sorted;   // [N]  y_train_.astype(f32)[sorter]
+    double* __restrict__ out;             // [n][ldo]
+    int64_t n;
+    int64_t ldo;                          // row stride of out (total number of quantiles)
+    int T;
+    int Q;                                // quantiles in this launch (<= kMaxQuantilesPerLaunch)
+    int cap;                              // smem capacity in members (power of two)
+    int* overflow_count;                  // rows whose gather exceeds cap go to the dense path
+    int* overflow_rows;
+};
+
+// p_k of utils.py:72 from (C_k, W_k); s = 100f / total.
+__device__ __forceinline__ float plotting_position(float s, float C, float W) {
+    return __fmul_rn(s, __fsub_rn(C, __fmul_rn(W, 0.5f)));
+}
+
+// utils.py:73-81 for one q.  rankOf(k), weightOf(k), cumOf(k) give entry k of the merged,
+// rank-ordered list; m >= 1 entries.
+template <typename RankOf, typename WeightOf, typename CumOf>
+__device__ __forceinline__ double select_percentile(double q, int m, float s, RankOf rankOf,
+                                                    WeightOf weightOf, CumOf cumOf,
+                                                    const float* __restrict__ y_sorted) {
+    // numpy's binary search, side='left', float32 element promoted to float64 for the compare
+    int lo = 0, hi = m;
+    while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        const float pm = plotting_position(s, cumOf(mid), weightOf(mid));
+        if (static_cast<double>(pm) < q) lo = mid + 1; else hi = mid;
+    }
+    const int start = lo - 1;
+    if (start == m - 1) return static_cast<double>(__ldg(y_sorted + rankOf(m - 1)));   // utils.py:74-75
+    if (start == -1) return static_cast<double>(__ldg(y_sorted + rankOf(0)));          // utils.py:76-77
+    const float p0 = plotting_position(s, cumOf(start), weightOf(start));
+    const float p1 = plotting_position(s, cumOf(start + 1), weightOf(start + 1));
+    const float a0 = __ldg(y_sorted + rankOf(start));
+    const float a1 = __ldg(y_sorted + rankOf(start + 1));
+    const float frac = __fdiv_rn(__fsub_rn(static_cast<float>(q), p0), __fsub_rn(p1, p0));  // utils.py:80
+    return static_cast<double>(__fadd_rn(a0, __fmul_rn(frac, __fsub_rn(a1, a0))));          // utils.py:81
+}
+
+// ---------------------------------------------------------------------------------------
+// CTA-per-row kernel: the row's members live in shared memory.
+//   smem: u64 keys[cap] | f32 wts[cap] | f32 cum[cap] | u32 offs[T+1] | u32 starts[T]
+// ---------------------------------------------------------------------------------------
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+quantile_cta_kernel(const QuantileParams p, const __grid_constant__ QuantileList ql) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+    float* wts = reinterpret_cast<float*>(keys + p.cap);
+    float* cum = wts + p.cap;
+    uint32_t* offs = reinterpret_cast<uint32_t*>(cum + p.cap);
+    uint32_t* starts = offs + (p.T + 1);
+    __shared__ int s_m;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int64_t row = blockIdx.x;
+    const uint2* __restrict__ seg = p.seg + row * p.T;
+
+    // 1. member counts of the row's leaves -> exclusive offsets (tree order)
+    for (int t = tid; t < p.T; t += THREADS) {
+        const uint2 s = seg[t];
+        starts[t] = s.x;
+        offs[t + 1] = s.y;
+    }
+    if (tid == 0) offs[0] = 0;
+    __syncthreads();
+    if (tid < 32) {
+        uint32_t carry = 0;
+        for (int base = 0; base < p.T; base += 32) {
+            const int t = base + lane;
+            uint32_t v = (t < p.T) ? offs[t + 1] : 0u;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, v, d);
+                if (lane >= d) v += u;
+            }
+            v += carry;
+            if (t < p.T) offs[t + 1] = v;
+            carry = __shfl_sync(0xffffffffu, v, 31);
+        }
+    }
+    __syncthreads();
+    const uint32_t P = offs[p.T];
+    if (P > static_cast<uint32_t>(p.cap)) {             // too many members for shared memory
+        if (tid == 0) p.overflow_rows[atomicAdd(p.overflow_count, 1)] = static_cast<int>(row);
+        return;
+    }
+    double* __restrict__ out = p.out + row * p.ldo;
+    if (P == 0) {                                       // cannot happen for a fitted forest
+        for (int qi = tid; qi < p.Q; qi += THREADS) out[qi] = __longlong_as_double(0x7ff8000000000000LL);
+        return;
+    }
+
+    // 2. gather: 8 lanes per leaf, key = (rank << 32) | position-in-tree-order
+    {
+        const int group = tid >> 3, sub = tid & 7;
+        for (int t = group; t < p.T; t += THREADS / 8) {
+            const uint32_t o = offs[t], len = offs[t + 1] - o;
+            const uint2* __restrict__ src = p.members + starts[t];
+            for (uint32_t i = sub; i < len; i += 8) {
+                const uint2 e = __ldg(src + i);
+                const uint32_t pos = o + i;
+                keys[pos] = (static_cast<unsigned long long>(e.x) << 32) | pos;
+                wts[pos] = __uint_as_float(e.y);
+            }
+        }
+    }
+    uint32_t P2 = 2;
+    while (P2 < P) P2 <<= 1;
+    for (uint32_t i = P + tid; i < P2; i += THREADS) keys[i] = ~0ull;
+    __syncthreads();
+
+    // 3. bitonic sort by (rank, position): equal ranks stay in tree order
+    for (uint32_t k = 2; k <= P2; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = tid; i < (P2 >> 1); i += THREADS) {
+                const uint32_t lo = i & (j - 1);
+                const uint32_t a = ((i - lo) << 1) + lo;
+                const uint32_t b = a + j;
+                const unsigned long long ka = keys[a], kb = keys[b];
+                const bool up = (a & k) == 0;
+                if ((ka > kb) == up) { keys[a] = kb; keys[b] = ka; }
+            }
+            __syncthreads();
+        }
+    }
+
+    // 4. warp 0: merge equal ranks (float32, tree order) and running sum (float32, rank
+    //    order).  Every lane replays the same sequential arithmetic on values broadcast by
+    //    shuffles, so there is no memory latency inside the dependent chain.
+    if (tid < 32) {
+        int m = 0;
+        uint32_t cur_rank = 0xffffffffu;
+        float W = 0.0f, C = 0.0f;
+        for (uint32_t base = 0; base < P; base += 32) {
+            const uint32_t k = base + lane;
+            uint32_t rk = 0xffffffffu;
+            float wk = 0.0f;
+            if (k < P) {
+                const unsigned long long key = keys[k];
+                rk = static_cast<uint32_t>(key >> 32);
+                wk = wts[static_cast<uint32_t>(key)];
+            }
+            __syncwarp();                                // all reads of this batch done before writes below
+            const int cnt = min(32u, P - base);
+            for (int i = 0; i < cnt; ++i) {
+                const uint32_t ri = __shfl_sync(0xffffffffu, rk, i);
+                const float wi = __shfl_sync(0xffffffffu, wk, i);
+                if (ri == cur_rank) {
+                    W = __fadd_rn(W, wi);               // ensemble.py:140, next tree
+                } else {
+                    if (cur_rank != 0xffffffffu && W != 0.0f) {     // utils.py:55-57
+                        C = __fadd_rn(C, W);            // utils.py:68
+                        if (lane == 0) {
+                            keys[m] = (static_cast<unsigned long long>(__float_as_uint(W)) << 32) | cur_rank;
+                            cum[m] = C;
+                        }
+                        ++m;
+                    }
+                    cur_rank = ri;
+                    W = wi;
+                }
+            }
+        }
+        if (W != 0.0f) {
+            C = __fadd_rn(C, W);
+            if (lane == 0) {
+                keys[m] = (static_cast<unsigned long long>(__float_as_uint(W)) << 32) | cur_rank;
+                cum[m] = C;
+            }
+            ++m;
+        }
+        if (lane == 0) s_m = m;
+    }
+    __syncthreads();
+
+    // 5. every requested percentile
+    const int m = s_m;
+    if (m == 0) {
+        for (int qi = tid; qi < p.Q; qi += THREADS) out[qi] = __longlong_as_double(0x7ff8000000000000LL);
+        return;
+    }
+    const float s = __fdiv_rn(100.0f, cum[m - 1]);      // utils.py:69,72
+    auto rankOf = [&](int k) { return static_cast<uint32_t>(keys[k]); };
+    auto weightOf = [&](int k) { return __uint_as_float(static_cast<uint32_t>(keys[k] >> 32)); };
+    auto cumOf = [&](int k) { return cum[k]; };
+    for (int qi = tid; qi < p.Q; qi += THREADS)
+        out[qi] = select_percentile(ql.q[qi], m, s, rankOf, weightOf, cumOf, p.y_sorted);
+}
+
+// ---------------------------------------------------------------------------------------
+// Dense fallback for rows whose member set does not fit shared memory (shallow trees /
+// large min_samples_leaf): accumulate the weights into a rank-indexed float32 vector in
+// global scratch, exactly like the reference's masked sum but touching only members.
+// Per CTA scratch: f32 dense[N] (kept zero between rows) | u32 bitmap[ceil(N/32)] (kept
+// zero) | u32 c_rank[N] | f32 c_w[N] | f32 c_cum[N].
+// ---------------------------------------------------------------------------------------
+struct DenseScratch {
+    float* dense;
+    uint32_t* bitmap;
+    uint32_t* c_rank;
+    float* c_w;
+    float* c_cum;
+};
+
+__host__ __device__ inline int64_t dense_scratch_bytes(int64_t N) {
+    const int64_t words = (N + 31) / 32;
+    int64_t b = (4 * N + 4 * words + 12 * N);
+    return (b + 255) / 256 * 256;
+}
+
+__device__ inline DenseScratch dense_scratch_at(unsigned char* base, int64_t N, int cta) {
+    unsigned char* ptr = base + dense_scratch_bytes(N) * cta;
+    const int64_t words = (N + 31) / 32;
+    DenseScratch s;
+    s.dense = reinterpret_cast<float*>(ptr);
+    s.bitmap = reinterpret_cast<uint32_t*>(s.dense + N);
+    s.c_rank = s.bitmap + words;
+    s.c_w = reinterpret_cast<float*>(s.c_rank + N);
+    s.c_cum = s.c_w + N;
+    return s;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+quantile_dense_kernel(const QuantileParams p, const __grid_constant__ QuantileList ql,
+                      unsigned char* scratch_base, int64_t N) {
+    __shared__ uint32_t warp_sums[THREADS / 32];
+    __shared__ uint32_t s_base;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const DenseScratch sc = dense_scratch_at(scratch_base, N, blockIdx.x);
+    const int64_t words = (N + 31) / 32;
+    const int n_over = *p.overflow_count;
+
+    for (int oi = blockIdx.x; oi < n_over; oi += gridDim.x) {
+        const int64_t row = p.overflow_rows[oi];
+        const uint2* __restrict__ seg = p.seg + row * p.T;
+
+        // A. trees in order; inside one leaf every sample appears once, so the plain
+        //    read-modify-write below is race free and the per-sample sum is in tree order.
+        for (int t = 0; t < p.T; ++t) {
+            const uint2 s = seg[t];
+            const uint2* __restrict__ src = p.members + s.x;
+            for (uint32_t i = tid; i < s.y; i += THREADS) {
+                const uint2 e = __ldg(src + i);
+                sc.dense[e.x] = __fadd_rn(sc.dense[e.x], __uint_as_float(e.y));   // ensemble.py:140
+                atomicOr(sc.bitmap + (e.x >> 5), 1u << (e.x & 31));
+            }
+            __syncthreads();
+        }
+
+        // B. compact the touched ranks in rank order (and restore the scratch to zero)
+        if (tid == 0) s_base = 0;
+        __syncthreads();
+        for (int64_t w0 = 0; w0 < words; w0 += THREADS) {
+            const int64_t w = w0 + tid;
+            uint32_t bits = (w < words) ? sc.bitmap[w] : 0u;
+            const uint32_t c = __popc(bits);
+            uint32_t v = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, v, d);
+                if (lane >= d) v += u;
+            }
+            if (lane == 31) warp_sums[warp] = v;
+            __syncthreads();
+            uint32_t before = 0, total = 0;
+#pragma unroll
+            for (int i = 0; i < THREADS / 32; ++i) {
+                const uint32_t ws = warp_sums[i];
+                if (i < warp) before += ws;
+                total += ws;
+            }
+            uint32_t o = s_base + before + v - c;
+            if (bits) {
+                sc.bitmap[w] = 0u;
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const uint32_t r = static_cast<uint32_t>(w * 32 + b);
+                    sc.c_rank[o] = r;
+                    sc.c_w[o] = sc.dense[r];
+                    sc.dense[r] = 0.0f;
+                    ++o;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) s_base += total;
+            __syncthreads();
+        }
+        const int m_all = static_cast<int>(s_base);
+
+        // C. warp 0: float32 running sum in rank order (utils.py:68), dropping zero weights
+        //    (utils.py:55-57); sequential arithmetic replayed by all lanes on shuffled values.
+        __shared__ int s_m;
+        if (tid < 32) {
+            int m = 0;
+            float C = 0.0f;
+            for (int base = 0; base < m_all; base += 32) {
+                const int k = base + lane;
+                const float wk = (k < m_all) ? sc.c_w[k] : 0.0f;
+                const uint32_t rk = (k < m_all) ? sc.c_rank[k] : 0u;
+                const int cnt = min(32, m_all - base);
+                float my_c = 0.0f;
+                int my_slot = -1;
+                for (int i = 0; i < cnt; ++i) {
+                    const float wi = __shfl_sync(0xffffffffu, wk, i);
+                    if (wi != 0.0f) {
+                        C = __fadd_rn(C, wi);
+                        if (lane == i) { my_c = C; my_slot = m; }
+                        ++m;
+                    }
+                }
+                __syncwarp();
+                // slots are <= k, and every read of this batch happened above
+                if (my_slot >= 0) { sc.c_rank[my_slot] = rk; sc.c_w[my_slot] = wk; sc.c_cum[my_slot] = my_c; }
+                __syncwarp();
+            }
+            if (lane == 0) s_m = m;
+        }
+        __syncthreads();
+
+        // D. percentiles
+        const int m = s_m;
+        double* __restrict__ out = p.out + row * p.ldo;
+        if (m == 0) {
+            for (int qi = tid; qi < p.Q; qi += THREADS) out[qi] = __longlong_as_double(0x7ff8000000000000LL);
+        } else {
+            const float s = __fdiv_rn(100.0f, sc.c_cum[m - 1]);
+            auto rankOf = [&](int k) { return sc.c_rank[k]; };
+            auto weightOf = [&](int k) { return sc.c_w[k]; };
+            auto cumOf = [&](int k) { return sc.c_cum[k]; };
+            for (int qi = tid; qi < p.Q; qi += THREADS)
+                out[qi] = select_percentile(ql.q[qi], m, s, rankOf, weightOf, cumOf, p.y_sorted);
+        }
+        __syncthreads();                                 // scratch reused by the next row
+    }
+}
+
+}  // namespace qf

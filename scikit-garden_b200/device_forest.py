@@ -1,0 +1,177 @@
+"""The forest resident in HBM + the calls that run the CUDA path on it.
+
+Thin Python over the C ABI (include/qforest_b200.h).  torch is plumbing only: it owns
+the device tensors for X / outputs / workspace and the stream; every kernel is ours.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _native
+from .flatten import FlatForest
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class DeviceForest:
+    """A flattened forest uploaded to one GPU (replicated per GPU when row-sharding)."""
+
+    def __init__(self, flat: FlatForest, device: int = 0, with_leaf_values: bool = True):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise RuntimeError("DeviceForest needs a CUDA device (sm_100); there is no CPU fallback")
+        self._lib = _native.lib()
+        self.flat_meta = dict(n_trees=flat.n_trees, n_features=flat.n_features, n_train=flat.n_train,
+                              n_nodes=flat.n_nodes, n_members=flat.n_members,
+                              max_row_members=flat.max_row_members,
+                              expected_row_members=flat.expected_row_members)
+        self.device = int(device)
+        self.n_trees = flat.n_trees
+        self.n_features = flat.n_features
+        desc = _native.ForestDesc()
+        desc.device = self.device
+        desc.n_trees = flat.n_trees
+        desc.n_features = flat.n_features
+        desc.feature_bits = flat.feature_bits
+        desc.n_train = flat.n_train
+        desc.n_nodes = flat.n_nodes
+        desc.n_members = flat.n_members
+        keep = [np.ascontiguousarray(flat.nodes), np.ascontiguousarray(flat.tree_offsets),
+                None if flat.node_ids is None else np.ascontiguousarray(flat.node_ids),
+                np.ascontiguousarray(flat.members), np.ascontiguousarray(flat.y_sorted),
+                np.ascontiguousarray(flat.leaf_values) if with_leaf_values else None]
+        desc.nodes = keep[0].ctypes.data
+        desc.tree_offsets = keep[1].ctypes.data
+        desc.node_ids = None if keep[2] is None else keep[2].ctypes.data
+        desc.members = keep[3].ctypes.data
+        desc.y_sorted = keep[4].ctypes.data
+        desc.leaf_values = None if keep[5] is None else keep[5].ctypes.data
+        desc.max_row_members = flat.max_row_members
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream().synchronize()      # make sure the primary context exists
+        handle = C.c_void_p()
+        _native.check(self._lib.qf_forest_create(C.byref(desc), C.byref(handle)))
+        self._h = handle
+        self._ws = None
+
+    # -- lifetime ---------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.qf_forest_destroy(self._h)
+            self._h = None
+            self._ws = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self._lib.qf_forest_device_bytes(self._h))
+
+    def set_option(self, key: str, value: int) -> None:
+        _native.check(self._lib.qf_forest_set_option(self._h, key.encode(), int(value)))
+        self._ws = None
+
+    @property
+    def last_launches(self) -> int:
+        return int(self._lib.qf_forest_last_launches(self._h))
+
+    def last_timings(self):
+        """(apply_ms, quantile_ms) of the most recent call; needs set_option("profile", 1)."""
+        a, q = C.c_double(0.0), C.c_double(0.0)
+        _native.check(self._lib.qf_forest_last_timings(self._h, C.byref(a), C.byref(q)))
+        return a.value, q.value
+
+    # -- helpers ----------------------------------------------------------------------
+    def _workspace(self, n_rows: int, n_q: int):
+        torch = _torch()
+        need = int(self._lib.qf_forest_workspace_bytes(self._h, n_rows, n_q))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device="cuda:%d" % self.device)
+        return self._ws, need
+
+    def _check_X(self, X):
+        torch = _torch()
+        if not (isinstance(X, torch.Tensor) and X.is_cuda and X.dtype == torch.float32 and X.dim() == 2):
+            raise TypeError("X must be a 2-D float32 CUDA tensor")
+        if X.device.index != self.device:
+            raise ValueError("X is on cuda:%s, forest on cuda:%d" % (X.device.index, self.device))
+        if X.shape[1] != self.n_features:
+            raise ValueError("X has %d features, forest expects %d" % (X.shape[1], self.n_features))
+        if X.stride(1) != 1:
+            X = X.contiguous()
+        return X
+
+    def _stream(self):
+        torch = _torch()
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # -- device-resident calls ----------------------------------------------------------
+    def apply(self, X):
+        """(n, T) int64 CUDA tensor of scikit-learn leaf ids (forest.py:583-604)."""
+        torch = _torch()
+        X = self._check_X(X)
+        n = X.shape[0]
+        out = torch.empty((n, self.n_trees), dtype=torch.int64, device=X.device)
+        ws, _ = self._workspace(n, 1)
+        _native.check(self._lib.qf_forest_apply(
+            self._h, C.c_void_p(X.data_ptr()), n, X.stride(0), C.c_void_p(out.data_ptr()),
+            C.c_void_p(ws.data_ptr()), ws.numel(), self._stream()))
+        return out
+
+    def predict_quantiles(self, X, quantiles: Sequence[float], mode: int = _native.QF_MODE_EXACT, out=None):
+        """(n, Q) float64 CUDA tensor (ensemble.py:104-143 for Q percentiles at once)."""
+        torch = _torch()
+        X = self._check_X(X)
+        n = X.shape[0]
+        q = np.ascontiguousarray(quantiles, dtype=np.float64).ravel()
+        if out is None:
+            out = torch.empty((n, q.shape[0]), dtype=torch.float64, device=X.device)
+        ws, _ = self._workspace(n, q.shape[0])
+        _native.check(self._lib.qf_forest_predict_quantiles(
+            self._h, C.c_void_p(X.data_ptr()), n, X.stride(0), q.ctypes.data_as(C.c_void_p),
+            q.shape[0], C.c_void_p(out.data_ptr()), int(mode),
+            C.c_void_p(ws.data_ptr()), ws.numel(), self._stream()))
+        return out
+
+    def predict_mean(self, X):
+        """(n,) float64 CUDA tensor (forest.py:1093-1131)."""
+        torch = _torch()
+        X = self._check_X(X)
+        n = X.shape[0]
+        out = torch.empty((n,), dtype=torch.float64, device=X.device)
+        ws, _ = self._workspace(n, 1)
+        _native.check(self._lib.qf_forest_predict_mean(
+            self._h, C.c_void_p(X.data_ptr()), n, X.stride(0), C.c_void_p(out.data_ptr()),
+            C.c_void_p(ws.data_ptr()), ws.numel(), self._stream()))
+        return out
+
+    # -- host-buffer end-to-end call ------------------------------------------------------
+    def predict_quantiles_host(self, X_host: np.ndarray, quantiles: Sequence[float],
+                               out_host: Optional[np.ndarray] = None,
+                               mode: int = _native.QF_MODE_EXACT, chunk_rows: int = 0) -> np.ndarray:
+        """Host float32 (n,F) in, host float64 (n,Q) out; H2D, kernels and D2H run inside
+        the C call, double-buffered.  Pass pinned arrays for full PCIe bandwidth."""
+        if X_host.dtype != np.float32 or X_host.ndim != 2 or X_host.strides[1] != 4:
+            raise TypeError("X_host must be a 2-D float32 array with contiguous rows")
+        if X_host.shape[1] != self.n_features:
+            raise ValueError("X has %d features, forest expects %d" % (X_host.shape[1], self.n_features))
+        q = np.ascontiguousarray(quantiles, dtype=np.float64).ravel()
+        n = X_host.shape[0]
+        if out_host is None:
+            out_host = np.empty((n, q.shape[0]), dtype=np.float64)
+        _native.check(self._lib.qf_forest_predict_quantiles_host(
+            self._h, C.c_void_p(X_host.ctypes.data), n, X_host.strides[0] // 4,
+            q.ctypes.data_as(C.c_void_p), q.shape[0], C.c_void_p(out_host.ctypes.data),
+            int(mode), int(chunk_rows)))
+        return out_host

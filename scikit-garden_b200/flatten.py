@@ -1,0 +1,191 @@
+"""Host-side forest flattener: fitted scikit-learn trees -> the HBM layout.
+
+Replaces the fit bookkeeping of the reference (skgarden/quantile/ensemble.py:83-101: the
+dense (T,N) ``y_train_leaves_`` / ``y_weights_`` arrays, built by an O(T*L*N) loop) and
+scikit-learn's 64-byte AoS node records (sklearn/tree/_tree.pxd:15-25) by
+
+* 8-byte packed nodes in depth-first preorder, trees back to back,
+* per-tree leaf -> in-bag member lists (CSR) whose entries are
+  (rank in ``np.argsort(y_train_)``, float32 weight), sorted by rank inside a leaf,
+* ``y_sorted = y_train_.astype(float32)[sorter]`` (skgarden/quantile/utils.py:46,52).
+
+The packing itself is native code (``qf_pack_tree`` in csrc/pack_forest.cpp, called
+through the C ABI, one tree per thread); this module only orchestrates it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from concurrent.futures import ThreadPoolExecutor
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _native
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def bootstrap_counts(random_state, n_samples: int) -> np.ndarray:
+    """In-bag multiplicities of one tree, regenerated from the tree's seed exactly as
+    the reference does (ensemble.py:16-38, :88-94; same call scikit-learn's
+    ``_generate_sample_indices`` makes when fitting with ``sample_weight=None``)."""
+    rs = np.random.RandomState(random_state)
+    idx = rs.randint(0, n_samples, n_samples)
+    return np.bincount(idx, minlength=n_samples).astype(np.int64)
+
+
+@dataclass
+class FlatForest:
+    """The flattened forest in host memory (what ``qf_forest_create`` uploads)."""
+    n_trees: int
+    n_features: int
+    feature_bits: int
+    n_train: int
+    nodes: np.ndarray            # uint64 [n_nodes]
+    tree_offsets: np.ndarray     # int64  [T+1]
+    node_ids: Optional[np.ndarray]   # int32 [n_nodes]; None when identical to packed order
+    members: np.ndarray          # uint64 [n_members]
+    member_offsets: np.ndarray   # int64  [T+1]
+    y_sorted: np.ndarray         # float32 [N]
+    leaf_values: np.ndarray      # float64 [n_nodes]
+    max_row_members: int         # sum over trees of the largest leaf (upper bound per row)
+    expected_row_members: float  # sum over trees of E[leaf size] for a training-like row
+    max_depth: int
+    sorter: np.ndarray = field(repr=False, default=None)   # int64 [N] np.argsort(y_train_)
+
+    @property
+    def n_nodes(self) -> int:
+        return int(self.nodes.shape[0])
+
+    @property
+    def n_members(self) -> int:
+        return int(self.members.shape[0])
+
+    def nbytes(self) -> int:
+        return int(self.nodes.nbytes + self.members.nbytes + self.y_sorted.nbytes +
+                   self.leaf_values.nbytes + (0 if self.node_ids is None else self.node_ids.nbytes))
+
+    # -- on-disk format: a plain .npz of the arrays above
+    def save(self, path: str) -> None:
+        np.savez(path, n_trees=self.n_trees, n_features=self.n_features,
+                 feature_bits=self.feature_bits, n_train=self.n_train, nodes=self.nodes,
+                 tree_offsets=self.tree_offsets,
+                 node_ids=np.zeros(0, np.int32) if self.node_ids is None else self.node_ids,
+                 members=self.members, member_offsets=self.member_offsets,
+                 y_sorted=self.y_sorted, leaf_values=self.leaf_values,
+                 max_row_members=self.max_row_members,
+                 expected_row_members=self.expected_row_members, max_depth=self.max_depth,
+                 sorter=self.sorter)
+
+    @classmethod
+    def load(cls, path: str) -> "FlatForest":
+        z = np.load(path)
+        node_ids = z["node_ids"]
+        return cls(int(z["n_trees"]), int(z["n_features"]), int(z["feature_bits"]),
+                   int(z["n_train"]), z["nodes"], z["tree_offsets"],
+                   None if node_ids.size == 0 else node_ids, z["members"],
+                   z["member_offsets"], z["y_sorted"], z["leaf_values"],
+                   int(z["max_row_members"]), float(z["expected_row_members"]),
+                   int(z["max_depth"]), z["sorter"])
+
+
+def _tree_arrays(tree):
+    """children_left/right, feature (int64), threshold (f64), value (f64 per node)."""
+    t = getattr(tree, "tree_", tree)
+    left = np.ascontiguousarray(t.children_left, dtype=np.int64)
+    right = np.ascontiguousarray(t.children_right, dtype=np.int64)
+    feat = np.ascontiguousarray(t.feature, dtype=np.int64)
+    thr = np.ascontiguousarray(t.threshold, dtype=np.float64)
+    val = np.asarray(t.value, dtype=np.float64)
+    val = np.ascontiguousarray(val.reshape(val.shape[0], -1)[:, 0])
+    return left, right, feat, thr, val
+
+
+def flatten_forest(trees: Sequence, train_leaves, counts, y_train, n_features: int,
+                   sorter: Optional[np.ndarray] = None, n_jobs: Optional[int] = None) -> FlatForest:
+    """Flatten ``trees`` (fitted sklearn estimators, ``Tree`` objects, or anything with
+    children_left/right, feature, threshold, value).
+
+    train_leaves : (T, N) int array or sequence of N-vectors: ``tree_.apply(X_train)``
+                   per tree (tree.py:101), or a callable ``t -> N-vector``.
+    counts       : sequence of per-tree in-bag multiplicity vectors (ensemble.py:88-94),
+                   entries may be None (= every sample once, bootstrap=False), or None.
+    y_train      : (N,) training targets as given to fit (ensemble.py:83).
+    sorter       : np.argsort(y_train) computed by the caller; computed here if None.
+                   It is never recomputed on the device (ties are ordered by numpy).
+    """
+    L = _native.lib()
+    T = len(trees)
+    if T == 0:
+        raise ValueError("empty forest")
+    y_train = np.asarray(y_train)
+    N = int(y_train.shape[0])
+    if sorter is None:
+        sorter = np.argsort(y_train)                      # ensemble.py:133
+    sorter = np.ascontiguousarray(sorter, dtype=np.int64)
+    y_sorted = np.ascontiguousarray(np.asarray(y_train, dtype=np.float32)[sorter])   # utils.py:46,52
+    feature_bits = max(1, int(n_features - 1).bit_length())
+
+    arrays = [_tree_arrays(t) for t in trees]
+    node_counts = np.array([a[0].shape[0] for a in arrays], dtype=np.int64)
+    tree_offsets = np.concatenate([[0], np.cumsum(node_counts)]).astype(np.int64)
+
+    def counts_of(t):
+        if counts is None or counts[t] is None:
+            return None
+        return np.ascontiguousarray(counts[t], dtype=np.int64)
+
+    inbag = np.array([N if counts_of(t) is None else int(np.count_nonzero(counts_of(t) > 0))
+                      for t in range(T)], dtype=np.int64)
+    member_offsets = np.concatenate([[0], np.cumsum(inbag)]).astype(np.int64)
+
+    nodes = np.empty(int(tree_offsets[-1]), dtype=np.uint64)
+    node_ids = np.empty(int(tree_offsets[-1]), dtype=np.int32)
+    members = np.empty(int(member_offsets[-1]), dtype=np.uint64)
+    leaf_values = np.empty(int(tree_offsets[-1]), dtype=np.float64)
+    stats = np.zeros((T, 3), dtype=np.float64)            # max_leaf_members, depth, sum_sq
+
+    def pack(t):
+        left, right, feat, thr, val = arrays[t]
+        lv = train_leaves(t) if callable(train_leaves) else train_leaves[t]
+        lv = np.ascontiguousarray(lv, dtype=np.int64)
+        if lv.shape[0] != N:
+            raise ValueError("train_leaves[%d] has %d entries, expected %d" % (t, lv.shape[0], N))
+        cnt = counts_of(t)
+        n0, n1 = int(tree_offsets[t]), int(tree_offsets[t + 1])
+        m0, m1 = int(member_offsets[t]), int(member_offsets[t + 1])
+        n_inbag, max_members, depth = C.c_int64(0), C.c_int32(0), C.c_int32(0)
+        sum_sq = C.c_double(0.0)
+        nodes_t, ids_t, members_t = nodes[n0:n1], node_ids[n0:n1], members[m0:m1]
+        rc = L.qf_pack_tree(n1 - n0, _ptr(left), _ptr(right), _ptr(feat), _ptr(thr), feature_bits,
+                            N, _ptr(lv), _ptr(cnt), _ptr(sorter), m0,
+                            _ptr(nodes_t), _ptr(ids_t), _ptr(members_t) if m1 > m0 else None,
+                            C.byref(n_inbag), C.byref(max_members), C.byref(depth), C.byref(sum_sq))
+        if rc != 0:
+            raise _native.QFError(rc, "tree %d: %s" % (t, _native.last_error()))
+        if n_inbag.value != m1 - m0:
+            raise RuntimeError("tree %d: in-bag count mismatch" % t)
+        leaf_values[n0:n1] = val[ids_t]
+        stats[t] = (max_members.value, depth.value, sum_sq.value)
+
+    workers = n_jobs if n_jobs and n_jobs > 0 else min(T, os.cpu_count() or 1)
+    if workers > 1:
+        with ThreadPoolExecutor(workers) as ex:
+            list(ex.map(pack, range(T)))
+    else:
+        for t in range(T):
+            pack(t)
+
+    identity = bool(np.array_equal(
+        node_ids, np.concatenate([np.arange(c, dtype=np.int32) for c in node_counts])))
+    return FlatForest(
+        n_trees=T, n_features=int(n_features), feature_bits=feature_bits, n_train=N,
+        nodes=nodes, tree_offsets=tree_offsets, node_ids=None if identity else node_ids,
+        members=members, member_offsets=member_offsets, y_sorted=y_sorted,
+        leaf_values=leaf_values, max_row_members=int(stats[:, 0].sum()),
+        expected_row_members=float((stats[:, 2] / np.maximum(inbag, 1)).sum()),
+        max_depth=int(stats[:, 1].max()), sorter=sorter)

@@ -1,0 +1,84 @@
+"""Host logic: the flattener (csrc/pack_forest.cpp via the C ABI) reproduces the
+reference's outputs when its layout is decoded on the CPU (tests/_layout.py)."""
+import numpy as np
+import pytest
+from numpy.testing import assert_array_equal
+
+import _golden
+import _layout
+import skgarden_b200 as sg
+
+
+@pytest.mark.parametrize("name", _golden.CASES)
+def test_layout_reproduces_reference(name):
+    g = _golden.load(name)
+    flat = _golden.flat_from_golden(g)
+    assert flat.n_trees == len(g.estimators)
+    assert flat.n_nodes == g.node_offsets[-1]
+    node_idx, start, count = _layout.decode_apply(flat, g.X_test)
+    assert_array_equal(_layout.sklearn_ids(flat, node_idx), g.apply)        # leaf ids bit-exact
+    assert count.min() >= 1                                                 # every leaf has members
+    assert count.sum(axis=1).max() <= flat.max_row_members
+    pred = _layout.decode_predict(flat, start, count, g.q)
+    assert_array_equal(pred.T, g.pred)                                      # bit-exact
+    # mean path data
+    got = flat.leaf_values[node_idx].sum(axis=1)                            # order-insensitive check
+    np.testing.assert_allclose(got / flat.n_trees, g.mean, rtol=1e-12)
+
+
+def test_best_first_trees_are_renumbered():
+    g = _golden.load("rf_maxleaf50")
+    flat = _golden.flat_from_golden(g)
+    assert flat.node_ids is not None             # max_leaf_nodes: sklearn order is not preorder
+    g2 = _golden.load("et_msl5")
+    assert _golden.flat_from_golden(g2).node_ids is None
+
+
+def test_members_sorted_by_rank_within_leaf():
+    g = _golden.load("et_msl5")
+    flat = _golden.flat_from_golden(g)
+    hi = (flat.nodes >> np.uint64(32)).astype(np.uint32)
+    lo = (flat.nodes & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    leaf = (hi & np.uint32(0x80000000)) != 0
+    rank = (flat.members & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    for s, c in zip(lo[leaf][:500], (hi[leaf] & np.uint32(0x7FFFFFFF))[:500]):
+        seg = rank[s:s + int(c)]
+        assert np.all(np.diff(seg) > 0)
+
+
+def test_floor_threshold_is_exact_on_grid_valued_features():
+    # thresholds are midpoints of float32 feature values; rounding them to the NEAREST
+    # float32 flips `<=` decisions (SURVEY.md Appendix C probe 12); floor does not.
+    from sklearn.ensemble import RandomForestRegressor
+    rng = np.random.RandomState(0)
+    X = (rng.randint(0, 4000, size=(3000, 5)) / np.float32(7.0)).astype(np.float32)
+    y = X[:, 0] - X[:, 1] + rng.randn(3000)
+    rf = RandomForestRegressor(n_estimators=5, random_state=0, bootstrap=False).fit(X, y)
+    trees = [e.tree_ for e in rf.estimators_]
+    leaves = [t.apply(X) for t in trees]
+    flat = sg.flatten_forest(trees, leaves, None, y, 5)
+    Xt = (rng.randint(0, 4000, size=(4000, 5)) / np.float32(7.0)).astype(np.float32)
+    node_idx, _, _ = _layout.decode_apply(flat, Xt)
+    assert_array_equal(_layout.sklearn_ids(flat, node_idx), rf.apply(Xt))
+
+
+def test_flat_forest_roundtrip(tmp_path):
+    g = _golden.load("c1_rfqr_boston")
+    flat = _golden.flat_from_golden(g)
+    p = str(tmp_path / "forest.npz")
+    flat.save(p)
+    back = sg.FlatForest.load(p)
+    assert_array_equal(back.nodes, flat.nodes)
+    assert_array_equal(back.members, flat.members)
+    assert back.max_row_members == flat.max_row_members and back.node_ids is None
+
+
+def test_pack_tree_rejects_bad_input():
+    from skgarden_b200 import _native
+    g = _golden.load("c1_rfqr_boston")
+    trees = [e.tree_ for e in g.estimators]
+    with pytest.raises(ValueError):
+        sg.flatten_forest(trees, [np.zeros(3, dtype=np.int64)] * len(trees), None, g.y_train, 13)
+    bad = [np.zeros(len(g.y_train), dtype=np.int64)] * len(trees)     # node 0 is not a leaf
+    with pytest.raises(_native.QFError):
+        sg.flatten_forest(trees, bad, None, g.y_train, 13)

@@ -1,0 +1,212 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).  Every call goes through
+the C ABI (libqforest_b200.so).  Oracles: committed outputs of the unmodified reference
+(tests/golden) and oracle/qrf_oracle.py.  Bars: leaf ids and QF_MODE_EXACT percentiles
+bit-exact; means bit-exact (float64 tree-order sum); QF_MODE_FAST within 1e-4."""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_array_almost_equal, assert_array_equal
+
+import _golden
+from oracle import qrf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _dev(flat, **opts):
+    import skgarden_b200 as sg
+    d = sg.DeviceForest(flat, device=0)
+    for k, v in opts.items():
+        d.set_option(k, v)
+    return d
+
+
+def _cuda(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def test_native_library_is_loaded():
+    from skgarden_b200 import _native
+    assert _native.lib().qf_abi_version() == 1
+    with open("/proc/self/maps") as fh:
+        assert "libqforest_b200.so" in fh.read()
+
+
+# ---- golden fixtures: the reference's own outputs ------------------------------------------------
+@pytest.mark.parametrize("name", _golden.CASES)
+def test_golden_apply_quantiles_mean(name):
+    g = _golden.load(name)
+    flat = _golden.flat_from_golden(g)
+    dev = _dev(flat)
+    X = _cuda(g.X_test)
+    assert_array_equal(dev.apply(X).cpu().numpy(), g.apply)                  # leaf ids bit-exact
+    got = dev.predict_quantiles(X, g.q).cpu().numpy()
+    assert_array_equal(got.T, g.pred)                                        # bit-exact, all q
+    assert_array_equal(dev.predict_mean(X).cpu().numpy(), g.mean)            # float64, tree order
+    host = dev.predict_quantiles_host(g.X_test, g.q)
+    assert_array_equal(host, got)                                            # host-buffer path
+    dev.close()
+
+
+@pytest.mark.parametrize("name", ["et_msl5", "et_depth2_large_sets", "c1_rfqr_boston"])
+def test_dense_fallback_is_identical(name):
+    # force rows out of shared memory into the global-scratch path
+    g = _golden.load(name)
+    flat = _golden.flat_from_golden(g)
+    dev = _dev(flat, cta_capacity=8, dense_ctas=3)
+    got = dev.predict_quantiles(_cuda(g.X_test), g.q).cpu().numpy()
+    assert_array_equal(got.T, g.pred)
+    dev.close()
+
+
+@pytest.mark.parametrize("opts", [dict(apply_row_warps=1, apply_ilp=1), dict(apply_row_warps=2, apply_ilp=2),
+                                  dict(apply_row_warps=8, apply_ilp=8), dict(rows_per_chunk=37)])
+def test_launch_shapes_do_not_change_results(opts):
+    g = _golden.load("et_msl5")
+    flat = _golden.flat_from_golden(g)
+    dev = _dev(flat, **opts)
+    X = _cuda(g.X_test)
+    assert_array_equal(dev.apply(X).cpu().numpy(), g.apply)
+    assert_array_equal(dev.predict_quantiles(X, g.q).cpu().numpy().T, g.pred)
+    assert_array_equal(dev.predict_quantiles_host(g.X_test, g.q, chunk_rows=41).T, g.pred)
+    dev.close()
+
+
+def test_many_quantiles_and_ragged_rows():
+    g = _golden.load("c1_etqr_boston")
+    flat = _golden.flat_from_golden(g)
+    dev = _dev(flat)
+    qs = np.linspace(0, 100, 301)                              # > 128 per launch -> several launches
+    leaves, weights = O.fit_attributes(g.estimators, g.X_train, g.bootstrap)
+    index = O.SparseIndex(g.y_train, leaves, weights, g.sorter)
+    for n in (1, 31, 33):
+        got = dev.predict_quantiles(_cuda(g.X_test[:n]), qs).cpu().numpy()
+        assert_array_equal(got, O.predict_sparse(index, g.apply[:n], qs))
+    dev.close()
+
+
+def test_error_paths():
+    from skgarden_b200 import _native
+    g = _golden.load("c1_rfqr_boston")
+    dev = _dev(_golden.flat_from_golden(g))
+    X = _cuda(g.X_test)
+    with pytest.raises(_native.QFError, match="in-between 0 and 100"):
+        dev.predict_quantiles(X, [50, 100.5])
+    with pytest.raises(ValueError):
+        dev.predict_quantiles(_cuda(g.X_test[:, :4]), [50])
+    with pytest.raises(TypeError):
+        dev.predict_quantiles(_cuda(g.X_test.astype(np.float64)), [50])
+    with pytest.raises(_native.QFError):
+        dev.set_option("no_such_option", 1)
+    dev.close()
+
+
+# ---- the reference's estimator-level tests, through the drop-in API ------------------------------
+def test_estimator_matches_reference_outputs():
+    import skgarden_b200 as sg
+    for name, cls in (("c1_rfqr_boston", sg.RandomForestQuantileRegressor),
+                      ("c1_etqr_boston", sg.ExtraTreesQuantileRegressor)):
+        g = _golden.load(name)
+        est = cls(n_estimators=10, random_state=0).fit(g.X_train, g.y_train)
+        if not np.array_equal(np.concatenate([e.tree_.threshold for e in est.estimators_]), g.threshold):
+            pytest.skip("scikit-learn on this box grows different trees than the fixture's")
+        assert_array_equal(est.apply(g.X_test), g.apply)
+        for k in (0, 4, 6, 11, 13):
+            q = g.q[k]
+            assert_array_equal(est.predict(g.X_test, quantile=int(q) if float(q).is_integer() else q), g.pred[k])
+        assert_array_equal(est.predict(g.X_test), g.mean)
+        assert_array_equal(est.predict(g.X_test, quantile=[5, 50, 95]), g.pred[[2, 6, 10]].T)
+        assert est.predict(g.X_test, quantile=50).dtype == np.float64
+        assert est.score(g.X_test, g.mean) == 1.0
+
+
+def test_max_depth_None_rfqr():                                 # test_ensemble.py:69-83
+    import skgarden_b200 as sg
+    rng = np.random.RandomState(0)
+    X = rng.randn(10, 1)
+    y = np.linspace(0.0, 100.0, 10)
+    rfqr = sg.RandomForestQuantileRegressor(random_state=0, bootstrap=False, max_depth=None).fit(X, y)
+    for quantile in [20, 40, 50, 60, 80, 90]:
+        assert_array_almost_equal(rfqr.predict(X, quantile=None), rfqr.predict(X, quantile=quantile), 5)
+
+
+def test_forest_toy_data():                                     # test_ensemble.py:105-126
+    import skgarden_b200 as sg
+    rng = np.random.RandomState(1)
+    x1 = rng.randn(1, 10)
+    X1 = np.tile(x1, (10000, 1))
+    x2 = 20.0 * rng.randn(1, 10)
+    X2 = np.tile(x2, (10000, 1))
+    X = np.vstack((X1, X2))
+    y1 = rng.randn(10000)
+    y2 = 5.0 + rng.randn(10000)
+    y = np.concatenate((y1, y2))
+    # bootstrap=False as in the reference run order (test_ensemble.py:42 leaves it off)
+    for est in (sg.RandomForestQuantileRegressor(random_state=0, bootstrap=False, max_depth=1),
+                sg.ExtraTreesQuantileRegressor(random_state=0, bootstrap=False, max_depth=1)):
+        est.fit(X, y)
+        for quantile in [20, 30, 40, 50, 60, 70, 80]:
+            assert_array_almost_equal(est.predict(x1, quantile=quantile), [np.percentile(y1, quantile)], 3)
+            assert_array_almost_equal(est.predict(x2, quantile=quantile), [np.percentile(y2, quantile)], 3)
+
+
+def test_tree_forest_equivalence():                             # test_ensemble.py:51-66
+    # forest(bootstrap=False, max_depth=2) == single tree: every tree of the forest sees
+    # the same data, so the forest's percentile equals the one-tree percentile.
+    import skgarden_b200 as sg
+    g = _golden.load("c1_rfqr_boston")
+    f10 = sg.RandomForestQuantileRegressor(n_estimators=10, random_state=0, bootstrap=False, max_depth=2)
+    f1 = sg.RandomForestQuantileRegressor(n_estimators=1, random_state=0, bootstrap=False, max_depth=2)
+    f10.fit(g.X_train, g.y_train)
+    f1.fit(g.X_train, g.y_train)
+    assert_array_almost_equal(f10.predict(g.X_test, quantile=10), f1.predict(g.X_test, quantile=10), 5)
+
+
+# ---- randomized differential tests against the oracle at sizes it finishes in seconds -------------
+@pytest.mark.parametrize("kind,bootstrap,msl,ties,depth", [
+    ("rf", True, 1, True, None), ("et", True, 5, False, None), ("rf", False, 2, False, None),
+    ("et", True, 40, True, None), ("rf", True, 1, False, 6)])
+def test_random_forests_bit_exact_vs_oracle(kind, bootstrap, msl, ties, depth):
+    import skgarden_b200 as sg
+    cls = sg.RandomForestQuantileRegressor if kind == "rf" else sg.ExtraTreesQuantileRegressor
+    rng = np.random.RandomState(7)
+    N, n, F = 6000, 3000, 9
+    X = rng.randn(N + n, F).astype(np.float32)
+    y = 3 * X[:, 0] + 2 * np.sin(3 * X[:, 1]) + X[:, 2] * X[:, 3] + rng.randn(N + n)
+    if ties:
+        y = np.round(y, 1)
+    est = cls(n_estimators=30, random_state=3, bootstrap=bootstrap, min_samples_leaf=msl,
+              max_depth=depth, n_jobs=-1).fit(X[:N], y[:N])
+    Xt = X[N:]
+    leaves = est.apply(Xt)
+    assert_array_equal(leaves, O.forest_apply(est.estimators_, Xt))          # all rows, bit-exact
+    qs = [0, 2.5, 5, 50, 95, 97.5, 100]
+    got = est.predict(Xt, quantile=qs)
+    rows = rng.choice(n, 400, replace=False)
+    index = O.SparseIndex(est.y_train_, est.y_train_leaves_, est.y_weights_, est._flat.sorter)
+    assert_array_equal(got[rows], O.predict_sparse(index, leaves[rows], qs))
+    assert_array_equal(est.predict(Xt), O.predict_mean(est.estimators_, Xt, leaves))
+    # size-independent properties on ALL rows: monotone in q, inside the training range,
+    # q=0 / q=100 are order statistics (exact members of y_train)
+    assert np.all(np.diff(got, axis=1) >= 0)
+    y32 = est.y_train_.astype(np.float32).astype(np.float64)
+    assert np.isin(got[:, 0], y32).all() and np.isin(got[:, -1], y32).all()
+    assert got.min() >= y32.min() and got.max() <= y32.max()
+
+
+def test_fast_mode_within_tolerance():
+    import skgarden_b200 as sg
+    rng = np.random.RandomState(5)
+    N, n, F = 5000, 2000, 8
+    X = rng.randn(N + n, F).astype(np.float32)
+    y = 3 * X[:, 0] + 2 * np.sin(3 * X[:, 1]) + X[:, 2] * X[:, 3] + rng.randn(N + n)
+    est = sg.ExtraTreesQuantileRegressor(n_estimators=40, random_state=1, min_samples_leaf=5, n_jobs=-1)
+    est.fit(X[:N], y[:N])
+    qs = [5, 50, 95]
+    exact = est.predict(X[N:], quantile=qs)
+    est.mode = "fast"
+    fast = est.predict(X[N:], quantile=qs)
+    # tolerance stated by BASELINE.json north_star for float32 arithmetic: 1e-4 relative
+    # (relative to the scale of y where the value itself is near zero)
+    assert_allclose(fast, exact, rtol=1e-4, atol=1e-4 * np.abs(y).max())
