@@ -187,9 +187,10 @@ def test_random_forests_bit_exact_vs_oracle(kind, bootstrap, msl, ties, depth):
     index = O.SparseIndex(est.y_train_, est.y_train_leaves_, est.y_weights_, est._flat.sorter)
     assert_array_equal(got[rows], O.predict_sparse(index, leaves[rows], qs))
     assert_array_equal(est.predict(Xt), O.predict_mean(est.estimators_, Xt, leaves))
-    # size-independent properties on ALL rows: monotone in q, inside the training range,
-    # q=0 / q=100 are order statistics (exact members of y_train)
-    assert np.all(np.diff(got, axis=1) >= 0)
+    # size-independent properties on ALL rows: monotone in q (up to the float32 rounding
+    # of the reference's interpolation), inside the training range, q=0 / q=100 are order
+    # statistics (exact members of y_train)
+    assert np.all(np.diff(got, axis=1) >= -1e-5 * np.abs(y).max())
     y32 = est.y_train_.astype(np.float32).astype(np.float64)
     assert np.isin(got[:, 0], y32).all() and np.isin(got[:, -1], y32).all()
     assert got.min() >= y32.min() and got.max() <= y32.max()
