@@ -114,6 +114,140 @@ apply_kernel(const ApplyParams p, void* __restrict__ out) {
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// K1, shared-memory top-block variant (the default).
+//
+// ncu on the kernel above shows it bound by L1TEX wavefronts: every lane of a node load
+// touches its own 128-byte line, so a warp-level load costs ~32 tag lookups and the SM
+// retires about one (row, tree, level) visit per cycle.  Here the first `top_levels`
+// levels of each tree come from a breadth-first "top block" (qf_build_top_blocks) that
+// the CTA stages in shared memory with coalesced 16-byte loads, `trees_per_chunk` trees
+// at a time: those levels cost shared-memory reads (no tags), all lanes in lock step, no
+// divergence.  Only the deeper levels walk the depth-first array in global memory.
+// Leaf results are staged in shared memory and written out as contiguous runs of
+// trees_per_chunk entries per row (4 wavefronts per warp store instead of 32).
+//
+// CTA = `rows` threads, thread == row.  smem: xt[F][rows] | top[TC][2^L] | res[TC][rows+1]
+// ---------------------------------------------------------------------------------------
+struct ApplyTopParams {
+    const uint2* __restrict__ nodes;
+    const uint2* __restrict__ top;         // [T][2^top_levels]
+    const float* __restrict__ X;
+    int64_t ldx;
+    int64_t n;
+    int T;
+    int F;
+    int fbits;
+    int top_levels;                        // L
+    int chunk_log2;                        // trees per chunk TC = 1 << chunk_log2
+};
+
+template <int ILP, int EMIT>
+__global__ void __launch_bounds__(256)
+apply_top_kernel(const ApplyTopParams p, void* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_apply[];
+    const int rows = blockDim.x;
+    const int TC = 1 << p.chunk_log2;
+    const int S = 1 << p.top_levels;
+    float* xt = reinterpret_cast<float*>(smem_apply);                           // [F][rows]
+    uint2* stop = reinterpret_cast<uint2*>(xt + static_cast<size_t>(p.F) * rows);  // [TC][S]
+    uint2* sres = stop + static_cast<size_t>(TC) * S;                            // [TC][rows+1]
+    const int tid = threadIdx.x;
+    const int64_t row0 = static_cast<int64_t>(blockIdx.x) * rows;
+    const int64_t row = row0 + tid;
+    const bool row_ok = row < p.n;
+
+    const int tile = rows * p.F;
+    for (int i = tid; i < tile; i += rows) {
+        const int r = i / p.F;
+        const int f = i - r * p.F;
+        const int64_t rr = row0 + r;
+        xt[f * rows + r] = (rr < p.n) ? __ldg(p.X + rr * p.ldx + f) : 0.0f;
+    }
+    const float* __restrict__ xcol = xt + tid;
+    const uint32_t fmask = (1u << p.fbits) - 1u;
+
+    for (int c0 = 0; c0 < p.T; c0 += TC) {
+        const int tc = min(TC, p.T - c0);
+        __syncthreads();                                // previous chunk fully written out / xt staged
+        {   // stage the chunk's top blocks: tc * S contiguous 8-byte slots
+            const uint4* __restrict__ src = reinterpret_cast<const uint4*>(p.top + static_cast<size_t>(c0) * S);
+            uint4* dst = reinterpret_cast<uint4*>(stop);
+            const int n16 = tc * (S >> 1);
+            for (int i = tid; i < n16; i += rows) dst[i] = __ldg(src + i);
+        }
+        __syncthreads();
+
+        for (int g = 0; g < tc; g += ILP) {
+            uint32_t node[ILP];
+            bool live[ILP];
+            {   // upper levels from shared memory, lock step
+                uint32_t h[ILP];
+#pragma unroll
+                for (int k = 0; k < ILP; ++k) h[k] = 1u;
+                for (int l = 0; l + 1 < p.top_levels; ++l) {
+#pragma unroll
+                    for (int k = 0; k < ILP; ++k) {
+                        if (g + k < tc) {
+                            const uint2 s = stop[(g + k) * S + h[k]];
+                            if (static_cast<int32_t>(s.y) >= 0) {
+                                const float x = xcol[s.y * rows];
+                                h[k] = 2u * h[k] + ((x <= __uint_as_float(s.x)) ? 0u : 1u);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < ILP; ++k) {
+                    live[k] = row_ok && (g + k < tc);
+                    node[k] = live[k] ? stop[(g + k) * S + h[k]].x : 0u;
+                }
+            }
+            // deeper levels from the depth-first array
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < ILP; ++k) any |= live[k];
+            while (any) {
+                uint2 nd[ILP];
+#pragma unroll
+                for (int k = 0; k < ILP; ++k)
+                    if (live[k]) nd[k] = __ldg(p.nodes + node[k]);
+                any = false;
+#pragma unroll
+                for (int k = 0; k < ILP; ++k) {
+                    if (!live[k]) continue;
+                    if (static_cast<int32_t>(nd[k].y) < 0) {
+                        sres[(g + k) * (rows + 1) + tid] =
+                            (EMIT == APPLY_EMIT_SEGMENT) ? make_uint2(nd[k].x, nd[k].y & 0x7fffffffu)
+                                                         : make_uint2(node[k], 0u);
+                        live[k] = false;
+                    } else {
+                        const uint32_t f = nd[k].y & fmask;
+                        const uint32_t off = nd[k].y >> p.fbits;
+                        const float x = xcol[f * rows];
+                        node[k] += (x <= __uint_as_float(nd[k].x)) ? 1u : off;   // _tree.pyx:989
+                        any = true;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // write the chunk: for every row a contiguous run of tc entries
+        const int total = rows << p.chunk_log2;
+        for (int i = tid; i < total; i += rows) {
+            const int r = i >> p.chunk_log2;
+            const int j = i & (TC - 1);
+            const int64_t rr = row0 + r;
+            if (j < tc && rr < p.n) {
+                const uint2 v = sres[j * (rows + 1) + r];
+                const int64_t o = rr * p.T + c0 + j;
+                if (EMIT == APPLY_EMIT_SEGMENT) static_cast<uint2*>(out)[o] = v;
+                else static_cast<int32_t*>(out)[o] = static_cast<int32_t>(v.x);
+            }
+        }
+    }
+}
+
 // EMIT_NODE output -> scikit-learn node ids (int64), what BaseForest.apply returns
 // (forest.py:604).  node_ids == nullptr means packed position - root == sklearn id.
 __global__ void node_to_sklearn_id_kernel(const int32_t* __restrict__ node_idx, int64_t total,

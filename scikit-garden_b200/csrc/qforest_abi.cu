@@ -50,9 +50,11 @@ struct HostPipe {                 // per-slot buffers of the host-buffer path
 
 struct qf_forest {
     int device = 0;
-    int T = 0, F = 0, fbits = 0;
+    int T = 0, F = 0, fbits = 0, top_levels = 0;
     int64_t N = 0, n_nodes = 0, n_members = 0, max_row_members = 0;
+    double expected_row_members = 0.0;
     uint2* d_nodes = nullptr;
+    uint2* d_top = nullptr;
     uint32_t* d_roots = nullptr;
     int32_t* d_node_ids = nullptr;
     uint2* d_members = nullptr;
@@ -60,11 +62,15 @@ struct qf_forest {
     double* d_values = nullptr;
     int64_t device_bytes = 0;
     int sm_count = 148;
-    // options
-    int apply_row_warps = 0;      // 0 = auto
+    // options (0 = auto where noted)
+    int apply_variant = 0;        // 0 auto, 1 = direct kernel, 2 = shared-memory top blocks
+    int apply_row_warps = 0;      // direct kernel: warps along rows per CTA (0 auto)
     int apply_ilp = 4;
+    int apply_rows_per_cta = 0;   // top-block kernel: 128 or 256 (0 auto)
+    int apply_chunk_log2 = -1;    // top-block kernel: log2(trees per chunk) (-1 auto)
     int64_t rows_per_chunk = 131072;
-    int cta_capacity = 4096;      // members per row held in shared memory (power of two)
+    int cta_capacity = 4096;      // members per row held in shared memory by the CTA kernel
+    int warp_elems = -1;          // warp kernel: keys per lane (2, 4, 8), 0 = never, -1 = auto
     int dense_ctas = 0;           // 0 = auto
     // counters
     int launches = 0;
@@ -112,52 +118,137 @@ void reset_call_counters(qf_forest* f) {
     f->spans.clear();
 }
 
-struct Plan {                      // workspace carve-up for one chunk of rows
-    int64_t chunk_rows;
-    int cap;                       // shared-memory member capacity of the CTA kernel
-    bool dense_needed;
-    int dense_ctas;
-    int64_t off_seg, off_count, off_rows, off_dense, total;
-};
-
 int next_pow2(int64_t v) {
     int p = 2;
     while (p < v && p < (1 << 30)) p <<= 1;
     return p;
 }
 
+// Which kernels a call runs, and how the caller's workspace is carved up for one chunk.
+//   warp kernel (P <= 32*E, registers)  --overflow list 1-->  CTA kernel (P <= cap, smem)
+//   --overflow list 2-->  dense kernel (any P, global scratch)
+struct Plan {
+    int64_t chunk_rows;
+    int warp_elems;                // 0 = warp kernel not used (CTA kernel is the primary)
+    int cap;                       // shared-memory member capacity of the CTA kernel
+    bool cta_needed;               // CTA kernel runs (as primary or on overflow list 1)
+    bool dense_needed;
+    int dense_ctas;
+    int64_t off_seg, off_counts, off_rows1, off_rows2, off_dense, total;
+};
+
 Plan make_plan(const qf_forest* f, int64_t n_rows) {
     Plan pl;
     pl.chunk_rows = std::max<int64_t>(1, std::min<int64_t>(n_rows, f->rows_per_chunk));
     pl.cap = std::min(next_pow2(std::max<int64_t>(f->max_row_members, 2)), f->cta_capacity);
+    // warp kernel: ranks must fit 32 - log2(32*E) bits, and the typical row must fit 32*E
+    int we = f->warp_elems;
+    if (we < 0) {
+        const double typical = std::max(1.0, f->expected_row_members) * 1.2;
+        we = typical <= 64 ? 2 : (typical <= 128 ? 4 : (typical <= 256 ? 8 : 0));
+        if (f->max_row_members <= 64) we = 2;
+        else if (f->max_row_members <= 128 && we != 2) we = 4;
+    }
+    if (we != 0 && f->N > (int64_t(1) << 24)) we = 0;
+    pl.warp_elems = we;
+    const int warp_cap = 32 * we;
+    pl.cta_needed = we == 0 || f->max_row_members > warp_cap;
     pl.dense_needed = f->max_row_members > pl.cap;
     pl.dense_ctas = 0;
     if (pl.dense_needed) {
-        // bound the scratch to ~2 GiB
-        const int64_t per = qf::dense_scratch_bytes(f->N);
+        const int64_t per = qf::dense_scratch_bytes(f->N);         // bound the scratch to ~2 GiB
         int64_t g = f->dense_ctas > 0 ? f->dense_ctas : f->sm_count;
         g = std::min<int64_t>(g, std::max<int64_t>(1, (int64_t(2) << 30) / per));
         pl.dense_ctas = static_cast<int>(std::min<int64_t>(g, pl.chunk_rows));
     }
     int64_t o = 0;
-    pl.off_seg = o;   o += align_up(pl.chunk_rows * f->T * 8);
-    pl.off_count = o; o += kAlign;
-    pl.off_rows = o;  o += align_up(pl.chunk_rows * 4);
-    pl.off_dense = o; o += pl.dense_needed ? qf::dense_scratch_bytes(f->N) * pl.dense_ctas : 0;
+    pl.off_seg = o;    o += align_up(pl.chunk_rows * f->T * 8);
+    pl.off_counts = o; o += kAlign;                               // two int counters
+    pl.off_rows1 = o;  o += align_up(pl.chunk_rows * 4);
+    pl.off_rows2 = o;  o += align_up(pl.chunk_rows * 4);
+    pl.off_dense = o;  o += pl.dense_needed ? qf::dense_scratch_bytes(f->N) * pl.dense_ctas : 0;
     pl.total = o;
     return pl;
 }
 
 int pick_row_warps(const qf_forest* f) {
     if (f->apply_row_warps > 0) return f->apply_row_warps;
-    // keep the transposed row tile (F * 32*row_warps * 4 B) around 16 KB per CTA
-    int rw = 8;
+    int rw = 8;                    // keep the transposed row tile around 16 KB per CTA
     while (rw > 1 && static_cast<int64_t>(f->F) * 32 * rw * 4 > 16384) rw >>= 1;
     return rw;
 }
 
+// shape of the top-block kernel: rows per CTA and trees per chunk so that a CTA needs at
+// most ~110 KB of shared memory (two CTAs per SM); returns false if no shape fits (very
+// wide X), in which case the direct kernel runs.
+bool pick_top_shape(const qf_forest* f, int* rows, int* chunk_log2, size_t* smem) {
+    if (f->top_levels < 2 || !f->d_top) return false;
+    const size_t S = size_t(1) << f->top_levels;
+    auto bytes = [&](int r, int cl) {
+        return static_cast<size_t>(f->F) * r * 4 + (size_t(1) << cl) * S * 8 + (size_t(1) << cl) * (r + 1) * 8;
+    };
+    const int row_opts[2] = {256, 128};
+    for (int budget_kb : {110, 220}) {
+        for (int r : row_opts) {
+            if (f->apply_rows_per_cta && r != f->apply_rows_per_cta) continue;
+            for (int cl = 4; cl >= 0; --cl) {
+                if (f->apply_chunk_log2 >= 0 ? cl != f->apply_chunk_log2 : (cl > 3 || cl < 1)) continue;
+                if (bytes(r, cl) <= static_cast<size_t>(budget_kb) * 1024) {
+                    *rows = r; *chunk_log2 = cl; *smem = bytes(r, cl);
+                    return true;
+                }
+            }
+        }
+    }
+    return false;
+}
+
+template <typename Kernel>
+int set_smem(Kernel kernel, size_t smem) {
+    if (smem > 48 * 1024)
+        QF_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+    return QF_OK;
+}
+
 template <int EMIT>
 int launch_apply(qf_forest* f, const float* X, int64_t n, int64_t ldx, void* out, cudaStream_t st) {
+    int rows = 0, chunk_log2 = 0;
+    size_t smem = 0;
+    const bool use_top = f->apply_variant != 1 && pick_top_shape(f, &rows, &chunk_log2, &smem);
+    if (f->apply_variant == 2 && !use_top)
+        return qf::fail(QF_ERR_LIMIT, "apply: top-block kernel requested but its shared memory does not fit");
+    if (use_top) {
+        qf::ApplyTopParams ap;
+        ap.nodes = f->d_nodes;
+        ap.top = f->d_top;
+        ap.X = X;
+        ap.ldx = ldx;
+        ap.n = n;
+        ap.T = f->T;
+        ap.F = f->F;
+        ap.fbits = f->fbits;
+        ap.top_levels = f->top_levels;
+        ap.chunk_log2 = chunk_log2;
+        const int64_t grid = (n + rows - 1) / rows;
+        auto run = [&](auto kernel) -> int {
+            int rc = set_smem(kernel, smem);
+            if (rc != QF_OK) return rc;
+            {
+                SpanTimer span(f, SPAN_APPLY, st);
+                kernel<<<static_cast<unsigned>(grid), rows, smem, st>>>(ap, out);
+            }
+            QF_CUDA_TRY(cudaGetLastError());
+            ++f->launches;
+            return QF_OK;
+        };
+        switch (f->apply_ilp) {
+            case 1: return run(qf::apply_top_kernel<1, EMIT>);
+            case 2: return run(qf::apply_top_kernel<2, EMIT>);
+            case 8: return run(qf::apply_top_kernel<8, EMIT>);
+            default: return run(qf::apply_top_kernel<4, EMIT>);
+        }
+    }
     qf::ApplyParams ap;
     ap.nodes = f->d_nodes;
     ap.roots = f->d_roots;
@@ -169,14 +260,13 @@ int launch_apply(qf_forest* f, const float* X, int64_t n, int64_t ldx, void* out
     ap.fbits = f->fbits;
     ap.row_warps = pick_row_warps(f);
     const int rows_per_cta = 32 * ap.row_warps;
-    const size_t smem = static_cast<size_t>(f->F) * rows_per_cta * sizeof(float);
+    smem = static_cast<size_t>(f->F) * rows_per_cta * sizeof(float);
     if (smem > 200 * 1024)
         return qf::fail(QF_ERR_LIMIT, "apply: n_features too large for the shared-memory row tile");
     const int64_t grid = (n + rows_per_cta - 1) / rows_per_cta;
     auto run = [&](auto kernel) -> int {
-        if (smem > 48 * 1024)
-            QF_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(smem)));
+        int rc = set_smem(kernel, smem);
+        if (rc != QF_OK) return rc;
         {
             SpanTimer span(f, SPAN_APPLY, st);
             kernel<<<static_cast<unsigned>(grid), qf::kApplyThreads, smem, st>>>(ap, out);
@@ -202,6 +292,16 @@ int check_forest_call(const qf_forest* f, const void* X, int64_t n, int64_t ldx,
     return QF_OK;
 }
 
+int check_quantiles(const double* q_host, int nq, int mode, const char* who) {
+    if (nq <= 0 || !q_host) return qf::fail(QF_ERR_INVALID, std::string(who) + ": no quantiles");
+    for (int i = 0; i < nq; ++i)
+        if (!(q_host[i] >= 0.0 && q_host[i] <= 100.0))          // utils.py:42-44
+            return qf::fail(QF_ERR_INVALID, "q should be in-between 0 and 100");
+    if (mode != QF_MODE_EXACT && mode != QF_MODE_FAST)
+        return qf::fail(QF_ERR_INVALID, std::string(who) + ": unknown mode");
+    return QF_OK;
+}
+
 // `pl` is the caller's carve-up of `ws` (made once for the largest chunk, so that the
 // zeroed dense scratch stays where the kernels expect it for every chunk).
 int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, const double* q_host,
@@ -212,19 +312,19 @@ int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, co
         return qf::fail(QF_ERR_WORKSPACE, "predict_quantiles: workspace too small");
     unsigned char* base = static_cast<unsigned char*>(ws);
     uint2* seg = reinterpret_cast<uint2*>(base + pl.off_seg);
-    int* over_count = reinterpret_cast<int*>(base + pl.off_count);
-    int* over_rows = reinterpret_cast<int*>(base + pl.off_rows);
+    int* counts = reinterpret_cast<int*>(base + pl.off_counts);   // [0]: list 1, [1]: list 2
+    int* rows1 = reinterpret_cast<int*>(base + pl.off_rows1);
+    int* rows2 = reinterpret_cast<int*>(base + pl.off_rows2);
 
-    const int threads = pl.cap <= 256 ? 64 : 256;
-    const size_t smem = static_cast<size_t>(pl.cap) * 16 + static_cast<size_t>(f->T) * 8 + 16;
-    if (smem > 220 * 1024)
-        return qf::fail(QF_ERR_LIMIT, "predict_quantiles: n_estimators too large for shared memory");
-    if (threads == 64)
-        QF_CUDA_TRY(cudaFuncSetAttribute(qf::quantile_cta_kernel<64>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    else
-        QF_CUDA_TRY(cudaFuncSetAttribute(qf::quantile_cta_kernel<256>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const int cta_threads = pl.cap <= 256 ? 64 : 256;
+    const size_t cta_smem = static_cast<size_t>(pl.cap) * 16 + static_cast<size_t>(f->T) * 8 + 16;
+    if (pl.cta_needed) {
+        if (cta_smem > 220 * 1024)
+            return qf::fail(QF_ERR_LIMIT, "predict_quantiles: n_estimators too large for shared memory");
+        int rc = cta_threads == 64 ? set_smem(qf::quantile_cta_kernel<64>, cta_smem)
+                                   : set_smem(qf::quantile_cta_kernel<256>, cta_smem);
+        if (rc != QF_OK) return rc;
+    }
 
     for (int64_t r0 = 0; r0 < n; r0 += pl.chunk_rows) {
         const int64_t rows = std::min(pl.chunk_rows, n - r0);
@@ -245,25 +345,53 @@ int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, co
             qp.T = f->T;
             qp.Q = qn;
             qp.cap = pl.cap;
-            qp.overflow_count = over_count;
-            qp.overflow_rows = over_rows;
-            if (pl.dense_needed) QF_CUDA_TRY(cudaMemsetAsync(over_count, 0, sizeof(int), st));
-            {
+            qp.row_list = nullptr;
+            qp.row_count = nullptr;
+            qp.overflow_count = counts + 1;
+            qp.overflow_rows = rows2;
+            const bool lists = (pl.warp_elems && pl.cta_needed) || pl.dense_needed;
+            if (lists) QF_CUDA_TRY(cudaMemsetAsync(counts, 0, 2 * sizeof(int), st));
+
+            if (pl.warp_elems) {                         // primary: one warp per row
+                qp.overflow_count = counts + 0;
+                qp.overflow_rows = rows1;
+                const unsigned grid =
+                    static_cast<unsigned>((rows + qf::kWarpKernelWarps - 1) / qf::kWarpKernelWarps);
                 SpanTimer span(f, SPAN_QUANTILE, st);
-                if (threads == 64)
-                    qf::quantile_cta_kernel<64><<<static_cast<unsigned>(rows), 64, smem, st>>>(qp, ql);
+                if (pl.warp_elems == 2)
+                    qf::quantile_warp_kernel<2><<<grid, qf::kWarpKernelWarps * 32, 0, st>>>(qp, ql);
+                else if (pl.warp_elems == 4)
+                    qf::quantile_warp_kernel<4><<<grid, qf::kWarpKernelWarps * 32, 0, st>>>(qp, ql);
                 else
-                    qf::quantile_cta_kernel<256><<<static_cast<unsigned>(rows), 256, smem, st>>>(qp, ql);
-            }
-            QF_CUDA_TRY(cudaGetLastError());
-            ++f->launches;
-            if (pl.dense_needed) {
-                SpanTimer span(f, SPAN_QUANTILE, st);
-                qf::quantile_dense_kernel<256><<<pl.dense_ctas, 256, 0, st>>>(
-                    qp, ql, base + pl.off_dense, f->N);
-                QF_CUDA_TRY(cudaGetLastError());
+                    qf::quantile_warp_kernel<8><<<grid, qf::kWarpKernelWarps * 32, 0, st>>>(qp, ql);
                 ++f->launches;
             }
+            QF_CUDA_TRY(cudaGetLastError());
+            if (pl.cta_needed) {                         // primary, or the warp kernel's overflow list
+                unsigned grid = static_cast<unsigned>(rows);
+                if (pl.warp_elems) {
+                    qp.row_list = rows1;
+                    qp.row_count = counts + 0;
+                    grid = static_cast<unsigned>(std::min<int64_t>(rows, int64_t(f->sm_count) * 8));
+                }
+                qp.overflow_count = counts + 1;
+                qp.overflow_rows = rows2;
+                SpanTimer span(f, SPAN_QUANTILE, st);
+                if (cta_threads == 64)
+                    qf::quantile_cta_kernel<64><<<grid, 64, cta_smem, st>>>(qp, ql);
+                else
+                    qf::quantile_cta_kernel<256><<<grid, 256, cta_smem, st>>>(qp, ql);
+                ++f->launches;
+            }
+            QF_CUDA_TRY(cudaGetLastError());
+            if (pl.dense_needed) {
+                qp.row_list = rows2;
+                qp.row_count = counts + 1;
+                SpanTimer span(f, SPAN_QUANTILE, st);
+                qf::quantile_dense_kernel<256><<<pl.dense_ctas, 256, 0, st>>>(qp, ql, base + pl.off_dense, f->N);
+                ++f->launches;
+            }
+            QF_CUDA_TRY(cudaGetLastError());
         }
     }
     return QF_OK;
@@ -295,6 +423,8 @@ int qf_forest_create(const qf_forest_desc* d, qf_forest** out) {
         return qf::fail(QF_ERR_INVALID, "qf_forest_create: feature_bits does not cover n_features");
     if (d->n_nodes >= (int64_t(1) << 31) || d->n_members > 0xFFFFFFFFll || d->n_train >= (int64_t(1) << 31))
         return qf::fail(QF_ERR_LIMIT, "qf_forest_create: forest exceeds the 32-bit packed layout");
+    if (d->top_blocks && (d->top_levels < 2 || d->top_levels > 14))
+        return qf::fail(QF_ERR_INVALID, "qf_forest_create: top_levels must be in [2,14]");
     int count = 0;
     QF_CUDA_TRY(cudaGetDeviceCount(&count));
     if (d->device < 0 || d->device >= count)
@@ -315,6 +445,9 @@ int qf_forest_create(const qf_forest_desc* d, qf_forest** out) {
     f->n_nodes = d->n_nodes;
     f->n_members = d->n_members;
     f->max_row_members = d->max_row_members > 0 ? d->max_row_members : d->n_members;
+    f->expected_row_members = d->expected_row_members > 0 ? d->expected_row_members
+                                                          : static_cast<double>(f->max_row_members);
+    f->top_levels = d->top_blocks ? d->top_levels : 0;
     f->sm_count = prop.multiProcessorCount;
 
     std::vector<uint32_t> roots(d->n_trees);
@@ -336,6 +469,9 @@ int qf_forest_create(const qf_forest_desc* d, qf_forest** out) {
     if (rc == QF_OK) rc = upload(reinterpret_cast<void**>(&f->d_y_sorted), d->y_sorted, d->n_train * 4);
     if (rc == QF_OK && d->leaf_values)
         rc = upload(reinterpret_cast<void**>(&f->d_values), d->leaf_values, d->n_nodes * 8);
+    if (rc == QF_OK && d->top_blocks)
+        rc = upload(reinterpret_cast<void**>(&f->d_top), d->top_blocks,
+                    (static_cast<int64_t>(d->n_trees) << d->top_levels) * 8);
     if (rc != QF_OK) {
         const std::string keep = qf::last_error_slot();
         qf_forest_destroy(f);
@@ -349,6 +485,7 @@ void qf_forest_destroy(qf_forest* f) {
     if (!f) return;
     DeviceGuard guard(f->device);
     cudaFree(f->d_nodes);
+    cudaFree(f->d_top);
     cudaFree(f->d_roots);
     cudaFree(f->d_node_ids);
     cudaFree(f->d_members);
@@ -392,7 +529,11 @@ int qf_forest_last_timings(qf_forest* f, double* apply_ms, double* quantile_ms) 
 int qf_forest_set_option(qf_forest* f, const char* key, int64_t value) {
     if (!f || !key) return qf::fail(QF_ERR_INVALID, "qf_forest_set_option: null argument");
     const std::string k(key);
-    if (k == "apply_row_warps") {
+    if (k == "apply_variant") {
+        if (value < 0 || value > 2)
+            return qf::fail(QF_ERR_INVALID, "apply_variant must be 0 (auto), 1 (direct) or 2 (top blocks)");
+        f->apply_variant = static_cast<int>(value);
+    } else if (k == "apply_row_warps") {
         if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8)
             return qf::fail(QF_ERR_INVALID, "apply_row_warps must be 0 (auto), 1, 2, 4 or 8");
         f->apply_row_warps = static_cast<int>(value);
@@ -400,6 +541,13 @@ int qf_forest_set_option(qf_forest* f, const char* key, int64_t value) {
         if (value != 1 && value != 2 && value != 4 && value != 8)
             return qf::fail(QF_ERR_INVALID, "apply_ilp must be 1, 2, 4 or 8");
         f->apply_ilp = static_cast<int>(value);
+    } else if (k == "apply_rows_per_cta") {
+        if (value != 0 && value != 128 && value != 256)
+            return qf::fail(QF_ERR_INVALID, "apply_rows_per_cta must be 0 (auto), 128 or 256");
+        f->apply_rows_per_cta = static_cast<int>(value);
+    } else if (k == "apply_chunk_log2") {
+        if (value < -1 || value > 4) return qf::fail(QF_ERR_INVALID, "apply_chunk_log2 must be in [-1, 4]");
+        f->apply_chunk_log2 = static_cast<int>(value);
     } else if (k == "rows_per_chunk") {
         if (value < 1) return qf::fail(QF_ERR_INVALID, "rows_per_chunk must be >= 1");
         f->rows_per_chunk = value;
@@ -407,6 +555,10 @@ int qf_forest_set_option(qf_forest* f, const char* key, int64_t value) {
         if (value < 2 || value > 8192 || (value & (value - 1)))
             return qf::fail(QF_ERR_INVALID, "cta_capacity must be a power of two in [2, 8192]");
         f->cta_capacity = static_cast<int>(value);
+    } else if (k == "warp_elems") {
+        if (value != -1 && value != 0 && value != 2 && value != 4 && value != 8)
+            return qf::fail(QF_ERR_INVALID, "warp_elems must be -1 (auto), 0 (off), 2, 4 or 8");
+        f->warp_elems = static_cast<int>(value);
     } else if (k == "profile") {
         f->profile = value != 0;
     } else if (k == "dense_ctas") {
@@ -447,12 +599,14 @@ int qf_forest_predict_mean(qf_forest* f, const float* X, int64_t n, int64_t ldx,
                            void* ws, int64_t ws_bytes, void* stream) {
     int rc = check_forest_call(f, X, n, ldx, out, "qf_forest_predict_mean");
     if (rc != QF_OK) return rc;
-    if (!f->d_values) return qf::fail(QF_ERR_INVALID, "qf_forest_predict_mean: forest was created without leaf_values");
+    if (!f->d_values)
+        return qf::fail(QF_ERR_INVALID, "qf_forest_predict_mean: forest was created without leaf_values");
     reset_call_counters(f);
     if (n == 0) return QF_OK;
     DeviceGuard guard(f->device);
     const Plan pl = make_plan(f, n);
-    if (ws_bytes < pl.total || !ws) return qf::fail(QF_ERR_WORKSPACE, "qf_forest_predict_mean: workspace too small");
+    if (ws_bytes < pl.total || !ws)
+        return qf::fail(QF_ERR_WORKSPACE, "qf_forest_predict_mean: workspace too small");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int32_t* idx = reinterpret_cast<int32_t*>(static_cast<unsigned char*>(ws) + pl.off_seg);
     for (int64_t r0 = 0; r0 < n; r0 += pl.chunk_rows) {
@@ -472,12 +626,8 @@ int qf_forest_predict_quantiles(qf_forest* f, const float* X, int64_t n, int64_t
                                 void* ws, int64_t ws_bytes, void* stream) {
     int rc = check_forest_call(f, X, n, ldx, out, "qf_forest_predict_quantiles");
     if (rc != QF_OK) return rc;
-    if (nq <= 0 || !q_host) return qf::fail(QF_ERR_INVALID, "qf_forest_predict_quantiles: no quantiles");
-    for (int i = 0; i < nq; ++i)
-        if (!(q_host[i] >= 0.0 && q_host[i] <= 100.0))          // utils.py:42-44
-            return qf::fail(QF_ERR_INVALID, "q should be in-between 0 and 100");
-    if (mode != QF_MODE_EXACT && mode != QF_MODE_FAST)
-        return qf::fail(QF_ERR_INVALID, "qf_forest_predict_quantiles: unknown mode");
+    rc = check_quantiles(q_host, nq, mode, "qf_forest_predict_quantiles");
+    if (rc != QF_OK) return rc;
     reset_call_counters(f);
     if (n == 0) return QF_OK;
     DeviceGuard guard(f->device);
@@ -495,16 +645,17 @@ int qf_forest_predict_quantiles_host(qf_forest* f, const float* X_host, int64_t 
                                      int64_t chunk_rows) {
     int rc = check_forest_call(f, X_host, n, ldx, out_host, "qf_forest_predict_quantiles_host");
     if (rc != QF_OK) return rc;
-    if (nq <= 0 || !q_host) return qf::fail(QF_ERR_INVALID, "qf_forest_predict_quantiles_host: no quantiles");
-    for (int i = 0; i < nq; ++i)
-        if (!(q_host[i] >= 0.0 && q_host[i] <= 100.0))
-            return qf::fail(QF_ERR_INVALID, "q should be in-between 0 and 100");
+    rc = check_quantiles(q_host, nq, mode, "qf_forest_predict_quantiles_host");
+    if (rc != QF_OK) return rc;
     reset_call_counters(f);
     if (n == 0) return QF_OK;
     DeviceGuard guard(f->device);
     if (chunk_rows <= 0) chunk_rows = f->rows_per_chunk;
     chunk_rows = std::min(chunk_rows, n);
+    const int64_t saved_chunk = f->rows_per_chunk;
+    f->rows_per_chunk = chunk_rows;                       // one kernel chunk per pipeline slot
     const Plan pl = make_plan(f, chunk_rows);
+    f->rows_per_chunk = saved_chunk;
     const int64_t x_bytes = chunk_rows * f->F * 4, out_bytes = chunk_rows * nq * 8;
     const int slots = n > chunk_rows ? 2 : 1;
     for (int s = 0; s < slots; ++s) {

@@ -37,8 +37,10 @@ struct QuantileParams {
     int T;
     int Q;                                // quantiles in this launch (<= kMaxQuantilesPerLaunch)
     int cap;                              // smem capacity in members (power of two)
-    int* overflow_count;                  // rows whose gather exceeds cap go to the dense path
-    int* overflow_rows;
+    const int* row_list;                  // nullptr: rows 0..n-1; else rows row_list[0..*row_count)
+    const int* row_count;
+    int* overflow_count;                  // rows whose gather exceeds this kernel's capacity
+    int* overflow_rows;                   //   are appended here for the next, larger kernel
 };
 
 // p_k of utils.py:72 from (C_k, W_k); s = 100f / total.
@@ -71,6 +73,220 @@ __device__ __forceinline__ double select_percentile(double q, int m, float s, Ra
 }
 
 // ---------------------------------------------------------------------------------------
+// Warp-per-row kernel for small member sets (P <= 32*E): the sort runs in registers.
+//
+//   gather (rank,weight) pairs in tree order into a per-warp shared-memory strip
+//   -> 32-bit keys (rank << log2(CAP)) | position, E per lane, blocked layout
+//   -> bitonic network in its all-ascending form (mirror step + xor steps): in-register
+//      compare-exchanges for strides < E, one SHFL + one predicated min/max per key for
+//      strides >= E
+//   -> group heads add their duplicates in tree order (float32, exact), compaction by a
+//      warp scan, lane 0 runs the float32 running sum over the compacted weights with
+//      128-bit shared loads/stores, then one lane per requested percentile selects and
+//      interpolates.
+// Rows that do not fit are appended to the overflow list for the CTA kernel.
+// ---------------------------------------------------------------------------------------
+constexpr int kWarpKernelWarps = 8;
+
+__device__ __forceinline__ void cmpswap(uint32_t& a, uint32_t& b) {
+    const uint32_t lo = min(a, b), hi = max(a, b);
+    a = lo;
+    b = hi;
+}
+
+// sorts the 32*E keys of a warp ascending; key v lives in lane v / E, register v % E
+template <int E>
+__device__ __forceinline__ void warp_bitonic_sort(uint32_t (&key)[E], int lane) {
+#pragma unroll
+    for (int k = 2; k <= E; k <<= 1) {
+#pragma unroll
+        for (int i = 0; i < E; ++i)
+            if ((i ^ (k - 1)) > i) cmpswap(key[i], key[i ^ (k - 1)]);
+#pragma unroll
+        for (int j = k >> 2; j > 0; j >>= 1)
+#pragma unroll
+            for (int i = 0; i < E; ++i)
+                if ((i ^ j) > i) cmpswap(key[i], key[i ^ j]);
+    }
+#pragma unroll
+    for (int k = 2 * E; k <= 32 * E; k <<= 1) {
+        {   // mirror step: v <-> v ^ (k-1)
+            const int lm = k / E - 1;
+            const bool lower = (lane & ((k / E) >> 1)) == 0;
+            uint32_t other[E];
+#pragma unroll
+            for (int i = 0; i < E; ++i) other[i] = __shfl_xor_sync(0xffffffffu, key[E - 1 - i], lm);
+#pragma unroll
+            for (int i = 0; i < E; ++i) key[i] = lower ? min(key[i], other[i]) : max(key[i], other[i]);
+        }
+#pragma unroll
+        for (int j = k >> 2; j >= E; j >>= 1) {
+            const int lx = j / E;
+            const bool lower = (lane & lx) == 0;
+#pragma unroll
+            for (int i = 0; i < E; ++i) {
+                const uint32_t o = __shfl_xor_sync(0xffffffffu, key[i], lx);
+                key[i] = lower ? min(key[i], o) : max(key[i], o);
+            }
+        }
+#pragma unroll
+        for (int j = E >> 1; j > 0; j >>= 1)
+#pragma unroll
+            for (int i = 0; i < E; ++i)
+                if ((i ^ j) > i) cmpswap(key[i], key[i ^ j]);
+    }
+}
+
+template <int E>
+__global__ void __launch_bounds__(kWarpKernelWarps * 32)
+quantile_warp_kernel(const QuantileParams p, const __grid_constant__ QuantileList ql) {
+    constexpr int CAP = 32 * E;
+    constexpr int POSBITS = (E == 4) ? 7 : ((E == 8) ? 8 : 6);
+    constexpr uint32_t POSMASK = CAP - 1;
+    static_assert(E == 2 || E == 4 || E == 8, "E must be 2, 4 or 8");
+    __shared__ __align__(16) uint32_t sA[kWarpKernelWarps][CAP];   // keys -> sorted ranks -> compact ranks
+    __shared__ __align__(16) float sB[kWarpKernelWarps][CAP];      // weights by position -> sorted -> compact
+    __shared__ __align__(16) float sC[kWarpKernelWarps][CAP];      // running sum
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * kWarpKernelWarps + warp;
+    if (row >= p.n) return;                              // warps are independent: no block barriers
+    uint32_t* __restrict__ A = sA[warp];
+    float* __restrict__ B = sB[warp];
+    float* __restrict__ Cc = sC[warp];
+    const uint2* __restrict__ seg = p.seg + row * p.T;
+
+    // 1. gather in tree order
+    uint32_t P = 0;
+    for (int base = 0; base < p.T; base += 32) {
+        const int t = base + lane;
+        const uint2 s = (t < p.T) ? seg[t] : make_uint2(0u, 0u);
+        uint32_t incl = s.y;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += u;
+        }
+        const uint32_t excl = P + incl - s.y;
+        if (excl + s.y <= CAP) {
+            const uint2* __restrict__ src = p.members + s.x;
+            for (uint32_t i = 0; i < s.y; ++i) {
+                const uint2 e = __ldg(src + i);
+                A[excl + i] = (e.x << POSBITS) | (excl + i);
+                B[excl + i] = __uint_as_float(e.y);
+            }
+        }
+        P += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (P > CAP) {
+        if (lane == 0) p.overflow_rows[atomicAdd(p.overflow_count, 1)] = static_cast<int>(row);
+        return;
+    }
+    double* __restrict__ out = p.out + row * p.ldo;
+    __syncwarp();
+
+    // 2. keys into registers (blocked: v = lane*E + i), padding sorts last
+    uint32_t key[E];
+    if constexpr (E >= 4) {
+#pragma unroll
+        for (int c = 0; c < E / 4; ++c) {
+            const uint4 v = reinterpret_cast<const uint4*>(A)[lane * (E / 4) + c];
+            key[4 * c + 0] = v.x; key[4 * c + 1] = v.y; key[4 * c + 2] = v.z; key[4 * c + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < E; ++i) key[i] = A[lane * E + i];
+    }
+#pragma unroll
+    for (int i = 0; i < E; ++i)
+        if (static_cast<uint32_t>(lane * E + i) >= P) key[i] = 0xffffffffu;
+
+    // 3. sort by (rank, position): equal ranks stay in tree order
+    warp_bitonic_sort<E>(key, lane);
+
+    // 4. sorted (rank, weight) back to shared memory
+    uint32_t rk[E];
+    float w[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        const bool valid = static_cast<uint32_t>(lane * E + i) < P;
+        w[i] = valid ? B[key[i] & POSMASK] : 0.0f;
+        rk[i] = valid ? (key[i] >> POSBITS) : 0xffffffffu;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        A[lane * E + i] = rk[i];
+        B[lane * E + i] = w[i];
+    }
+    __syncwarp();
+
+    // 5. group heads sum their duplicates in tree order (ensemble.py:140), then compact
+    uint32_t prev = __shfl_up_sync(0xffffffffu, rk[E - 1], 1);
+    if (lane == 0) prev = 0xfffffffeu;
+    float Wg[E];
+    bool head[E];
+    uint32_t n_heads = 0;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        const uint32_t v = lane * E + i;
+        const uint32_t before = (i == 0) ? prev : rk[i - 1];
+        head[i] = (v < P) && (rk[i] != before);
+        Wg[i] = 0.0f;
+        if (head[i]) {
+            float W = w[i];
+            for (uint32_t u = v + 1; u < P && A[u] == rk[i]; ++u) W = __fadd_rn(W, B[u]);
+            Wg[i] = W;
+            head[i] = W != 0.0f;                         // utils.py:55-57
+        }
+        n_heads += head[i] ? 1u : 0u;
+    }
+    uint32_t incl = n_heads;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += u;
+    }
+    const int m = static_cast<int>(__shfl_sync(0xffffffffu, incl, 31));
+    __syncwarp();
+    {
+        uint32_t c = incl - n_heads;
+#pragma unroll
+        for (int i = 0; i < E; ++i)
+            if (head[i]) { A[c] = rk[i]; B[c] = Wg[i]; ++c; }
+    }
+    __syncwarp();
+    if (m == 0) {
+        for (int qi = lane; qi < p.Q; qi += 32) out[qi] = __longlong_as_double(0x7ff8000000000000LL);
+        return;
+    }
+
+    // 6. lane 0: float32 running sum in rank order (utils.py:68), 4 entries per shared access
+    if (lane == 0) {
+        float C = 0.0f;
+        for (int c = 0; c < m; c += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(B + c);
+            float4 o;
+            C = __fadd_rn(C, w4.x); o.x = C;
+            C = __fadd_rn(C, w4.y); o.y = C;
+            C = __fadd_rn(C, w4.z); o.z = C;
+            C = __fadd_rn(C, w4.w); o.w = C;
+            *reinterpret_cast<float4*>(Cc + c) = o;
+        }
+    }
+    __syncwarp();
+
+    // 7. one lane per requested percentile
+    const float s = __fdiv_rn(100.0f, Cc[m - 1]);       // utils.py:69,72
+    auto rankOf = [&](int k) { return A[k]; };
+    auto weightOf = [&](int k) { return B[k]; };
+    auto cumOf = [&](int k) { return Cc[k]; };
+    for (int qi = lane; qi < p.Q; qi += 32)
+        out[qi] = select_percentile(ql.q[qi], m, s, rankOf, weightOf, cumOf, p.y_sorted);
+}
+
+// ---------------------------------------------------------------------------------------
 // CTA-per-row kernel: the row's members live in shared memory.
 //   smem: u64 keys[cap] | f32 wts[cap] | f32 cum[cap] | u32 offs[T+1] | u32 starts[T]
 // ---------------------------------------------------------------------------------------
@@ -87,8 +303,11 @@ quantile_cta_kernel(const QuantileParams p, const __grid_constant__ QuantileList
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int64_t row = blockIdx.x;
+    const int64_t n_work = p.row_list ? static_cast<int64_t>(*p.row_count) : p.n;
+    for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x) {
+    const int64_t row = p.row_list ? static_cast<int64_t>(p.row_list[work]) : work;
     const uint2* __restrict__ seg = p.seg + row * p.T;
+    __syncthreads();                                    // shared memory reused from the previous row
 
     // 1. member counts of the row's leaves -> exclusive offsets (tree order)
     for (int t = tid; t < p.T; t += THREADS) {
@@ -117,12 +336,12 @@ quantile_cta_kernel(const QuantileParams p, const __grid_constant__ QuantileList
     const uint32_t P = offs[p.T];
     if (P > static_cast<uint32_t>(p.cap)) {             // too many members for shared memory
         if (tid == 0) p.overflow_rows[atomicAdd(p.overflow_count, 1)] = static_cast<int>(row);
-        return;
+        continue;
     }
     double* __restrict__ out = p.out + row * p.ldo;
     if (P == 0) {                                       // cannot happen for a fitted forest
         for (int qi = tid; qi < p.Q; qi += THREADS) out[qi] = __longlong_as_double(0x7ff8000000000000LL);
-        return;
+        continue;
     }
 
     // 2. gather: 8 lanes per leaf, key = (rank << 32) | position-in-tree-order
@@ -212,7 +431,7 @@ quantile_cta_kernel(const QuantileParams p, const __grid_constant__ QuantileList
     const int m = s_m;
     if (m == 0) {
         for (int qi = tid; qi < p.Q; qi += THREADS) out[qi] = __longlong_as_double(0x7ff8000000000000LL);
-        return;
+        continue;
     }
     const float s = __fdiv_rn(100.0f, cum[m - 1]);      // utils.py:69,72
     auto rankOf = [&](int k) { return static_cast<uint32_t>(keys[k]); };
@@ -220,6 +439,7 @@ quantile_cta_kernel(const QuantileParams p, const __grid_constant__ QuantileList
     auto cumOf = [&](int k) { return cum[k]; };
     for (int qi = tid; qi < p.Q; qi += THREADS)
         out[qi] = select_percentile(ql.q[qi], m, s, rankOf, weightOf, cumOf, p.y_sorted);
+    }   // rows
 }
 
 // ---------------------------------------------------------------------------------------
@@ -266,10 +486,10 @@ quantile_dense_kernel(const QuantileParams p, const __grid_constant__ QuantileLi
     const int warp = tid >> 5;
     const DenseScratch sc = dense_scratch_at(scratch_base, N, blockIdx.x);
     const int64_t words = (N + 31) / 32;
-    const int n_over = *p.overflow_count;
+    const int n_over = *p.row_count;                    // this kernel always runs off a row list
 
     for (int oi = blockIdx.x; oi < n_over; oi += gridDim.x) {
-        const int64_t row = p.overflow_rows[oi];
+        const int64_t row = p.row_list[oi];
         const uint2* __restrict__ seg = p.seg + row * p.T;
 
         // A. trees in order; inside one leaf every sample appears once, so the plain

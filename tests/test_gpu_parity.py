@@ -49,22 +49,44 @@ def test_golden_apply_quantiles_mean(name):
     dev.close()
 
 
-@pytest.mark.parametrize("name", ["et_msl5", "et_depth2_large_sets", "c1_rfqr_boston"])
-def test_dense_fallback_is_identical(name):
-    # force rows out of shared memory into the global-scratch path
+@pytest.mark.parametrize("name", _golden.CASES)
+@pytest.mark.parametrize("warp_elems", [0, 2, 8])
+def test_every_quantile_kernel_is_identical(name, warp_elems):
+    # warp kernel / CTA kernel as the primary, each with its overflow chain
     g = _golden.load(name)
     flat = _golden.flat_from_golden(g)
-    dev = _dev(flat, cta_capacity=8, dense_ctas=3)
+    dev = _dev(flat, warp_elems=warp_elems)
     got = dev.predict_quantiles(_cuda(g.X_test), g.q).cpu().numpy()
     assert_array_equal(got.T, g.pred)
     dev.close()
 
 
-@pytest.mark.parametrize("opts", [dict(apply_row_warps=1, apply_ilp=1), dict(apply_row_warps=2, apply_ilp=2),
-                                  dict(apply_row_warps=8, apply_ilp=8), dict(rows_per_chunk=37)])
+@pytest.mark.parametrize("name", ["et_msl5", "et_depth2_large_sets", "c1_rfqr_boston"])
+def test_dense_fallback_is_identical(name):
+    # force rows out of shared memory into the global-scratch path
+    g = _golden.load(name)
+    flat = _golden.flat_from_golden(g)
+    dev = _dev(flat, cta_capacity=8, dense_ctas=3, warp_elems=0)
+    got = dev.predict_quantiles(_cuda(g.X_test), g.q).cpu().numpy()
+    assert_array_equal(got.T, g.pred)
+    dev.close()
+
+
+@pytest.mark.parametrize("opts", [
+    dict(apply_variant=1, apply_row_warps=1, apply_ilp=1), dict(apply_variant=1, apply_row_warps=2, apply_ilp=2),
+    dict(apply_variant=1, apply_row_warps=8, apply_ilp=8), dict(rows_per_chunk=37),
+    dict(apply_variant=2, apply_rows_per_cta=128, apply_chunk_log2=0, apply_ilp=1),
+    dict(apply_variant=2, apply_rows_per_cta=256, apply_chunk_log2=2, apply_ilp=2),
+    dict(apply_variant=2, apply_rows_per_cta=128, apply_chunk_log2=4, apply_ilp=8),
+    dict(apply_variant=2, top_levels=3), dict(apply_variant=2, top_levels=12, apply_chunk_log2=1),
+    dict(warp_elems=0), dict(warp_elems=2), dict(warp_elems=4), dict(warp_elems=8),
+    dict(warp_elems=2, cta_capacity=64), dict(warp_elems=4, cta_capacity=128, dense_ctas=2)])
 def test_launch_shapes_do_not_change_results(opts):
     g = _golden.load("et_msl5")
     flat = _golden.flat_from_golden(g)
+    opts = dict(opts)
+    if "top_levels" in opts:
+        flat.build_top_blocks(opts.pop("top_levels"))
     dev = _dev(flat, **opts)
     X = _cuda(g.X_test)
     assert_array_equal(dev.apply(X).cpu().numpy(), g.apply)
