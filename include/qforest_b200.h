@@ -92,17 +92,6 @@ int qf_pack_tree(int64_t n_nodes,
 /* Number of in-bag samples of one tree (size of members_out); counts NULL = n_train. */
 int64_t qf_count_inbag(int64_t n_train, const int64_t* counts);
 
-/* Host side: breadth-first "top blocks" for the leaf-lookup kernel.  For every tree the
- * first `levels` levels in heap order (slot 1 = root, children of slot h are 2h, 2h+1),
- * 2^levels 8-byte slots per tree, top_out[n_trees << levels]:
- *   internal slot: lo32 = float bits of the floor-f32 threshold, hi32 = feature
- *   exit slot:     lo32 = global packed index of the node where the walk continues in
- *                  `nodes` (a leaf, or the node on the last level), hi32 = 0x80000000
- * The kernel stages these blocks in shared memory so the upper levels of every walk do
- * not go through the L1 tag stage.  nodes / tree_offsets as produced by qf_pack_tree. */
-int qf_build_top_blocks(int32_t n_trees, const int64_t* tree_offsets, const uint64_t* nodes,
-                        int32_t feature_bits, int32_t levels, uint64_t* top_out);
-
 /* ------------------------------------------------------------------------------------
  * Device side.
  */
@@ -128,9 +117,6 @@ typedef struct qf_forest_desc {
                                    (sum over trees of max_leaf_members)                 */
     double expected_row_members;/* typical members per row (sum over trees of the mean
                                    leaf size seen by a training row); picks the kernel  */
-    int32_t top_levels;         /* levels in top_blocks (0 / NULL: direct kernel only)  */
-    int32_t reserved;
-    const uint64_t* top_blocks; /* [n_trees << top_levels] from qf_build_top_blocks     */
 } qf_forest_desc;
 
 /* Copies everything the descriptor points at into HBM on desc->device.  Synchronous.
@@ -188,9 +174,9 @@ int qf_forest_last_launches(const qf_forest* f);
  * on those events. */
 int qf_forest_last_timings(qf_forest* f, double* apply_ms, double* quantile_ms);
 
-/* Tuning knobs (bench / tests): key in {"apply_variant", "apply_row_warps", "apply_ilp",
- * "apply_rows_per_cta", "apply_chunk_log2", "rows_per_chunk", "cta_capacity", "warp_elems",
- * "dense_ctas", "profile"}.  Returns QF_ERR_INVALID for unknown keys or values. */
+/* Tuning knobs (bench / tests): key in {"sort_rows", "apply_row_warps", "apply_ilp",
+ * "rows_per_chunk", "cta_capacity", "warp_elems", "dense_ctas", "profile"}.
+ * Returns QF_ERR_INVALID for unknown keys or values. */
 int qf_forest_set_option(qf_forest* f, const char* key, int64_t value);
 
 #ifdef __cplusplus

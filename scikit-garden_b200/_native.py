@@ -39,8 +39,6 @@ class ForestDesc(C.Structure):
         ("members", C.c_void_p), ("y_sorted", C.c_void_p), ("leaf_values", C.c_void_p),
         ("max_row_members", C.c_int64),
         ("expected_row_members", C.c_double),
-        ("top_levels", C.c_int32), ("reserved", C.c_int32),
-        ("top_blocks", C.c_void_p),
     ]
 
 
@@ -52,7 +50,6 @@ SIGNATURES = {
     "qf_pack_tree": (C.c_int, [_I64, _P, _P, _P, _P, _I32, _I64, _P, _P, _P, _U64,
                                _P, _P, _P, _P, _P, _P, _P]),
     "qf_count_inbag": (_I64, [_I64, _P]),
-    "qf_build_top_blocks": (C.c_int, [_I32, _P, _P, _I32, _I32, _P]),
     "qf_forest_create": (C.c_int, [C.POINTER(ForestDesc), C.POINTER(C.c_void_p)]),
     "qf_forest_destroy": (None, [_P]),
     "qf_forest_device_bytes": (_I64, [_P]),

@@ -4,15 +4,27 @@
 // (sklearn:tree/_tree.pyx:954-996): for every (row, tree) walk root -> leaf, going left
 // iff x[feature] <= threshold.
 //
-// Mapping: a CTA owns ROWS = 32 * row_warps test rows, staged ONCE into shared memory
-// as a transposed tile xt[f][row] (coalesced global reads; lane == row, so every
+// What bounds this kernel is not HBM but the L1TEX tag stage: a warp-level node load costs
+// one wavefront per DISTINCT 128-byte line its 32 lanes touch, ~1 wavefront per cycle per
+// SM.  With test rows in arrival order every lane is in a different part of the tree after
+// a few levels (32 wavefronts per load; ncu: l1tex wavefronts 66 % of peak, the limiter).
+// Two measures bring that down ~3x (tools/sim_wavefronts.py counts them on real forests):
+//
+//   1. locality order: rows are first bucketed by the leaf they reach in ONE tree (its
+//      depth-first leaf position is a space-filling order adapted to the data), and the
+//      kernel walks the rows in that order.  Neighbouring lanes then follow the same path
+//      through the upper ~10 levels of EVERY tree and share lines far below that.
+//   2. lock step: all lanes of a warp walk the same tree at the same time (a chain is
+//      re-armed with the warp's next tree only when every lane has reached its leaf), so
+//      that the coherence of (1) is not lost to lanes drifting into different trees.
+//
+// Mapping: a CTA owns ROWS = 32 * row_warps consecutive rows of the locality order, staged
+// ONCE into shared memory as a transposed tile xt[f][row] (lane == row, so every
 // shared-memory read of a feature is bank-conflict free whatever feature each lane
-// needs).  The CTA's warps are split into row_warps x tree_warps; a warp walks its 32
-// rows through the trees t = tree_warp, tree_warp + tree_warps, ...  Each lane keeps
-// ILP independent root->leaf chains in flight (different trees) so the dependent 8-byte
-// node loads (L1/L2 hits: one tree is a few MB, co-resident CTAs sweep the trees in the
-// same order) overlap.  When a chain reaches a leaf the lane emits the result and
-// starts its next tree at once, so lanes never wait for the deepest path of the warp.
+// needs).  The CTA's 8 warps are split into row_warps x tree_warps; a warp walks its 32
+// rows through the trees t = tree_warp, tree_warp + tree_warps, ...  keeping ILP
+// independent chains (different trees) in flight per lane so that the dependent 8-byte
+// node loads overlap.
 //
 // Node format: include/qforest_b200.h (8 bytes: floor-f32 threshold | offset<<fb | feature;
 // leaf: member start | 0x80000000|count).  Left child = node + 1 (preorder).
@@ -26,35 +38,46 @@ struct ApplyParams {
     const uint2* __restrict__ nodes;       // packed nodes of all trees
     const uint32_t* __restrict__ roots;    // [T] packed index of each tree's root
     const float* __restrict__ X;           // (n, ldx) float32
+    const int* __restrict__ order;         // [n] position in the locality order -> row of X; nullptr = identity
     int64_t ldx;
     int64_t n;
-    int T;
+    int T;                                 // row stride of the output (trees of the forest)
+    int t_begin, t_end;                    // trees walked by this launch
     int F;
     int fbits;
     int row_warps;                         // warps along rows per CTA (block = 256 threads)
+    int key_shift;                         // EMIT_KEY: bucket = (leaf position in the tree) >> key_shift
+    int* __restrict__ key_hist;            // EMIT_KEY: bucket populations (atomicAdd)
 };
 
-enum { APPLY_EMIT_SEGMENT = 0, APPLY_EMIT_NODE = 1 };
+// what a finished walk writes
+//   SEGMENT: uint2 out[pos][T]   (member start, member count), pos = position in the locality order
+//   NODE   : int32 out[row][T]   packed node index of the leaf, row = row of X
+//   KEY    : int32 out[row]      locality bucket of the row (single tree), + histogram
+enum { APPLY_EMIT_SEGMENT = 0, APPLY_EMIT_NODE = 1, APPLY_EMIT_KEY = 2 };
 
 constexpr int kApplyThreads = 256;
 
-// out: EMIT_SEGMENT -> uint2 [n][T] (member start, member count)
-//      EMIT_NODE    -> int32 [n][T] packed node index of the leaf
 template <int ILP, int EMIT>
 __global__ void __launch_bounds__(kApplyThreads)
 apply_kernel(const ApplyParams p, void* __restrict__ out) {
     extern __shared__ float xt[];                       // [F][ROWS]
     const int rows_per_cta = 32 * p.row_warps;
     const int tree_warps = (kApplyThreads / 32) / p.row_warps;
-    const int64_t row0 = static_cast<int64_t>(blockIdx.x) * rows_per_cta;
+    const int64_t pos0 = static_cast<int64_t>(blockIdx.x) * rows_per_cta;
 
-    // stage the row tile transposed
+    // stage the row tile transposed (threads sweep a row's features: coalesced per row)
     const int tile = rows_per_cta * p.F;
     for (int i = threadIdx.x; i < tile; i += kApplyThreads) {
         const int r = i / p.F;
         const int f = i - r * p.F;
-        const int64_t row = row0 + r;
-        xt[f * rows_per_cta + r] = (row < p.n) ? __ldg(p.X + row * p.ldx + f) : 0.0f;
+        const int64_t pos = pos0 + r;
+        float v = 0.0f;
+        if (pos < p.n) {
+            const int64_t row = p.order ? static_cast<int64_t>(__ldg(p.order + pos)) : pos;
+            v = __ldg(p.X + row * p.ldx + f);
+        }
+        xt[f * rows_per_cta + r] = v;
     }
     __syncthreads();
 
@@ -63,45 +86,52 @@ apply_kernel(const ApplyParams p, void* __restrict__ out) {
     const int rw = warp % p.row_warps;
     const int tw = warp / p.row_warps;
     const int r = rw * 32 + lane;
-    const int64_t row = row0 + r;
-    if (row >= p.n) return;                             // no further barriers below
+    const int64_t pos = pos0 + r;
+    const bool row_ok = pos < p.n;
+    int64_t out_row = pos;
+    if (EMIT != APPLY_EMIT_SEGMENT && row_ok && p.order) out_row = __ldg(p.order + pos);
     const float* __restrict__ xcol = xt + r;
     const uint32_t fmask = (1u << p.fbits) - 1u;
 
+    // chain k of every lane walks the same tree (warp-uniform tree[k])
     uint32_t node[ILP];
     int tree[ILP];
-    bool live[ILP];
-    int next_tree = tw;
+    uint32_t live = 0;                                  // bit k: this lane is still walking chain k
+    uint32_t armed = 0;                                 // bit k: chain k holds a tree (warp-uniform)
+    int next_tree = p.t_begin + tw;
 #pragma unroll
     for (int k = 0; k < ILP; ++k) {
         tree[k] = next_tree;
-        live[k] = next_tree < p.T;
-        node[k] = live[k] ? __ldg(p.roots + next_tree) : 0u;
+        node[k] = 0u;
+        if (next_tree < p.t_end) {
+            armed |= 1u << k;
+            node[k] = __ldg(p.roots + next_tree);
+        }
         next_tree += tree_warps;
     }
+    if (row_ok) live = armed;
 
-    bool any = false;
-#pragma unroll
-    for (int k = 0; k < ILP; ++k) any |= live[k];
-    while (any) {
+    while (armed) {
         uint2 nd[ILP];
 #pragma unroll
         for (int k = 0; k < ILP; ++k)
-            if (live[k]) nd[k] = __ldg(p.nodes + node[k]);
-        any = false;
+            if (live & (1u << k)) nd[k] = __ldg(p.nodes + node[k]);
 #pragma unroll
         for (int k = 0; k < ILP; ++k) {
-            if (!live[k]) continue;
+            if (!(live & (1u << k))) continue;
             if (static_cast<int32_t>(nd[k].y) < 0) {    // leaf
-                const int64_t o = row * p.T + tree[k];
-                if (EMIT == APPLY_EMIT_SEGMENT)
-                    static_cast<uint2*>(out)[o] = make_uint2(nd[k].x, nd[k].y & 0x7fffffffu);
-                else
-                    static_cast<int32_t*>(out)[o] = static_cast<int32_t>(node[k]);
-                tree[k] = next_tree;
-                live[k] = next_tree < p.T;
-                if (live[k]) node[k] = __ldg(p.roots + next_tree);
-                next_tree += tree_warps;
+                if (EMIT == APPLY_EMIT_SEGMENT) {
+                    static_cast<uint2*>(out)[out_row * p.T + tree[k]] =
+                        make_uint2(nd[k].x, nd[k].y & 0x7fffffffu);
+                } else if (EMIT == APPLY_EMIT_NODE) {
+                    static_cast<int32_t*>(out)[out_row * p.T + tree[k]] = static_cast<int32_t>(node[k]);
+                } else {
+                    const int bucket =
+                        static_cast<int>((node[k] - __ldg(p.roots + tree[k])) >> p.key_shift);
+                    static_cast<int32_t*>(out)[out_row] = bucket;
+                    atomicAdd(p.key_hist + bucket, 1);
+                }
+                live &= ~(1u << k);
             } else {
                 const uint32_t f = nd[k].y & fmask;
                 const uint32_t off = nd[k].y >> p.fbits;
@@ -109,143 +139,79 @@ apply_kernel(const ApplyParams p, void* __restrict__ out) {
                 // sklearn:tree/_tree.pyx:989  `X[i, feature] <= threshold` -> left
                 node[k] += (x <= __uint_as_float(nd[k].x)) ? 1u : off;
             }
-            any |= live[k];
+        }
+        // re-arm the chains every lane has finished with the warp's next trees
+        const uint32_t busy = __reduce_or_sync(0xffffffffu, live);
+        uint32_t idle = armed & ~busy;
+        if (idle) {
+#pragma unroll
+            for (int k = 0; k < ILP; ++k) {
+                if (!(idle & (1u << k))) continue;
+                if (next_tree < p.t_end) {
+                    tree[k] = next_tree;
+                    node[k] = __ldg(p.roots + next_tree);
+                    if (row_ok) live |= 1u << k;
+                } else {
+                    armed &= ~(1u << k);
+                }
+                next_tree += tree_warps;
+            }
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------
-// K1, shared-memory top-block variant (the default).
-//
-// ncu on the kernel above shows it bound by L1TEX wavefronts: every lane of a node load
-// touches its own 128-byte line, so a warp-level load costs ~32 tag lookups and the SM
-// retires about one (row, tree, level) visit per cycle.  Here the first `top_levels`
-// levels of each tree come from a breadth-first "top block" (qf_build_top_blocks) that
-// the CTA stages in shared memory with coalesced 16-byte loads, `trees_per_chunk` trees
-// at a time: those levels cost shared-memory reads (no tags), all lanes in lock step, no
-// divergence.  Only the deeper levels walk the depth-first array in global memory.
-// Leaf results are staged in shared memory and written out as contiguous runs of
-// trees_per_chunk entries per row (4 wavefronts per warp store instead of 32).
-//
-// CTA = `rows` threads, thread == row.  smem: xt[F][rows] | top[TC][2^L] | res[TC][rows+1]
+// Locality order: counting sort of the rows by their bucket (EMIT_KEY pass above).
+//   exclusive_scan_kernel : single CTA, in-place exclusive prefix sum of the histogram
+//   order_scatter_kernel  : order[atomicAdd(&cursor[bucket[row]], 1)] = row
+// The order inside a bucket is whatever the atomics give; results do not depend on it
+// (every row is computed independently and written to its own output row).
 // ---------------------------------------------------------------------------------------
-struct ApplyTopParams {
-    const uint2* __restrict__ nodes;
-    const uint2* __restrict__ top;         // [T][2^top_levels]
-    const float* __restrict__ X;
-    int64_t ldx;
-    int64_t n;
-    int T;
-    int F;
-    int fbits;
-    int top_levels;                        // L
-    int chunk_log2;                        // trees per chunk TC = 1 << chunk_log2
-};
+constexpr int kScanThreads = 1024;
 
-template <int ILP, int EMIT>
-__global__ void __launch_bounds__(256)
-apply_top_kernel(const ApplyTopParams p, void* __restrict__ out) {
-    extern __shared__ __align__(16) unsigned char smem_apply[];
-    const int rows = blockDim.x;
-    const int TC = 1 << p.chunk_log2;
-    const int S = 1 << p.top_levels;
-    float* xt = reinterpret_cast<float*>(smem_apply);                           // [F][rows]
-    uint2* stop = reinterpret_cast<uint2*>(xt + static_cast<size_t>(p.F) * rows);  // [TC][S]
-    uint2* sres = stop + static_cast<size_t>(TC) * S;                            // [TC][rows+1]
-    const int tid = threadIdx.x;
-    const int64_t row0 = static_cast<int64_t>(blockIdx.x) * rows;
-    const int64_t row = row0 + tid;
-    const bool row_ok = row < p.n;
-
-    const int tile = rows * p.F;
-    for (int i = tid; i < tile; i += rows) {
-        const int r = i / p.F;
-        const int f = i - r * p.F;
-        const int64_t rr = row0 + r;
-        xt[f * rows + r] = (rr < p.n) ? __ldg(p.X + rr * p.ldx + f) : 0.0f;
+__global__ void __launch_bounds__(kScanThreads)
+exclusive_scan_kernel(int* __restrict__ hist, int n_bins) {
+    __shared__ int warp_tot[kScanThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n_bins + kScanThreads - 1) / kScanThreads;     // contiguous bins per thread
+    const int b0 = tid * per;
+    int sum = 0;
+    for (int i = 0; i < per; ++i)
+        if (b0 + i < n_bins) sum += hist[b0 + i];
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += u;
     }
-    const float* __restrict__ xcol = xt + tid;
-    const uint32_t fmask = (1u << p.fbits) - 1u;
-
-    for (int c0 = 0; c0 < p.T; c0 += TC) {
-        const int tc = min(TC, p.T - c0);
-        __syncthreads();                                // previous chunk fully written out / xt staged
-        {   // stage the chunk's top blocks: tc * S contiguous 8-byte slots
-            const uint4* __restrict__ src = reinterpret_cast<const uint4*>(p.top + static_cast<size_t>(c0) * S);
-            uint4* dst = reinterpret_cast<uint4*>(stop);
-            const int n16 = tc * (S >> 1);
-            for (int i = tid; i < n16; i += rows) dst[i] = __ldg(src + i);
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int v = warp_tot[lane];
+        int iv = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, iv, d);
+            if (lane >= d) iv += u;
         }
-        __syncthreads();
-
-        for (int g = 0; g < tc; g += ILP) {
-            uint32_t node[ILP];
-            bool live[ILP];
-            {   // upper levels from shared memory, lock step
-                uint32_t h[ILP];
-#pragma unroll
-                for (int k = 0; k < ILP; ++k) h[k] = 1u;
-                for (int l = 0; l + 1 < p.top_levels; ++l) {
-#pragma unroll
-                    for (int k = 0; k < ILP; ++k) {
-                        if (g + k < tc) {
-                            const uint2 s = stop[(g + k) * S + h[k]];
-                            if (static_cast<int32_t>(s.y) >= 0) {
-                                const float x = xcol[s.y * rows];
-                                h[k] = 2u * h[k] + ((x <= __uint_as_float(s.x)) ? 0u : 1u);
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < ILP; ++k) {
-                    live[k] = row_ok && (g + k < tc);
-                    node[k] = live[k] ? stop[(g + k) * S + h[k]].x : 0u;
-                }
-            }
-            // deeper levels from the depth-first array
-            bool any = false;
-#pragma unroll
-            for (int k = 0; k < ILP; ++k) any |= live[k];
-            while (any) {
-                uint2 nd[ILP];
-#pragma unroll
-                for (int k = 0; k < ILP; ++k)
-                    if (live[k]) nd[k] = __ldg(p.nodes + node[k]);
-                any = false;
-#pragma unroll
-                for (int k = 0; k < ILP; ++k) {
-                    if (!live[k]) continue;
-                    if (static_cast<int32_t>(nd[k].y) < 0) {
-                        sres[(g + k) * (rows + 1) + tid] =
-                            (EMIT == APPLY_EMIT_SEGMENT) ? make_uint2(nd[k].x, nd[k].y & 0x7fffffffu)
-                                                         : make_uint2(node[k], 0u);
-                        live[k] = false;
-                    } else {
-                        const uint32_t f = nd[k].y & fmask;
-                        const uint32_t off = nd[k].y >> p.fbits;
-                        const float x = xcol[f * rows];
-                        node[k] += (x <= __uint_as_float(nd[k].x)) ? 1u : off;   // _tree.pyx:989
-                        any = true;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        // write the chunk: for every row a contiguous run of tc entries
-        const int total = rows << p.chunk_log2;
-        for (int i = tid; i < total; i += rows) {
-            const int r = i >> p.chunk_log2;
-            const int j = i & (TC - 1);
-            const int64_t rr = row0 + r;
-            if (j < tc && rr < p.n) {
-                const uint2 v = sres[j * (rows + 1) + r];
-                const int64_t o = rr * p.T + c0 + j;
-                if (EMIT == APPLY_EMIT_SEGMENT) static_cast<uint2*>(out)[o] = v;
-                else static_cast<int32_t*>(out)[o] = static_cast<int32_t>(v.x);
-            }
+        warp_tot[lane] = iv - v;                       // exclusive offset of each warp
+    }
+    __syncthreads();
+    int run = warp_tot[warp] + incl - sum;
+    for (int i = 0; i < per; ++i) {
+        if (b0 + i < n_bins) {
+            const int c = hist[b0 + i];
+            hist[b0 + i] = run;
+            run += c;
         }
     }
+}
+
+__global__ void order_scatter_kernel(const int* __restrict__ bucket, int64_t n, int* __restrict__ cursor,
+                                     int* __restrict__ order) {
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    order[atomicAdd(cursor + bucket[row], 1)] = static_cast<int>(row);
 }
 
 // EMIT_NODE output -> scikit-learn node ids (int64), what BaseForest.apply returns

@@ -149,44 +149,3 @@ extern "C" int qf_pack_tree(int64_t n_nodes, const int64_t* left, const int64_t*
     if (sum_sq_leaf_members_out) *sum_sq_leaf_members_out = sum_sq;
     return QF_OK;
 }
-
-// Breadth-first "top blocks": the first `levels` levels of every tree in heap order
-// (slot 1 = root, children of slot h are 2h and 2h+1), 2^levels 8-byte slots per tree.
-//   internal slot: lo32 = float bits of the floor-f32 threshold, hi32 = feature (bit31 = 0)
-//   exit slot    : lo32 = global packed index of the node at which the walk continues in
-//                  the depth-first array (a leaf, or the node sitting on the last level),
-//                  hi32 = 0x80000000
-// The apply kernel stages these blocks in shared memory, so the upper levels of every
-// root->leaf walk cost shared-memory reads instead of one L1 wavefront per lane.
-extern "C" int qf_build_top_blocks(int32_t n_trees, const int64_t* tree_offsets, const uint64_t* nodes,
-                                   int32_t feature_bits, int32_t levels, uint64_t* top_out) {
-    if (n_trees <= 0 || !tree_offsets || !nodes || !top_out)
-        return qf::fail(QF_ERR_INVALID, "qf_build_top_blocks: null or empty argument");
-    if (levels < 2 || levels > 14) return qf::fail(QF_ERR_INVALID, "qf_build_top_blocks: levels must be in [2,14]");
-    const uint64_t slots = uint64_t(1) << levels;
-    const uint32_t fmask = (1u << feature_bits) - 1u;
-    struct Item { int64_t node; uint32_t slot; int32_t level; };
-    std::vector<Item> stack;
-    for (int32_t t = 0; t < n_trees; ++t) {
-        uint64_t* top = top_out + static_cast<uint64_t>(t) * slots;
-        for (uint64_t h = 0; h < slots; ++h) top[h] = (uint64_t(0x80000000u) << 32) | 0xFFFFFFFFu;
-        stack.clear();
-        stack.push_back({tree_offsets[t], 1u, 0});
-        while (!stack.empty()) {
-            const Item it = stack.back();
-            stack.pop_back();
-            if (it.node < tree_offsets[t] || it.node >= tree_offsets[t + 1])
-                return qf::fail(QF_ERR_INVALID, "qf_build_top_blocks: node offset leaves its tree");
-            const uint64_t nd = nodes[it.node];
-            const uint32_t hi = static_cast<uint32_t>(nd >> 32);
-            if ((hi & 0x80000000u) || it.level == levels - 1) {
-                top[it.slot] = (uint64_t(0x80000000u) << 32) | static_cast<uint32_t>(it.node);
-            } else {
-                top[it.slot] = (static_cast<uint64_t>(hi & fmask) << 32) | static_cast<uint32_t>(nd);
-                stack.push_back({it.node + (hi >> feature_bits), 2 * it.slot + 1, it.level + 1});
-                stack.push_back({it.node + 1, 2 * it.slot, it.level + 1});
-            }
-        }
-    }
-    return QF_OK;
-}

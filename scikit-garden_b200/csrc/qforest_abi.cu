@@ -50,11 +50,10 @@ struct HostPipe {                 // per-slot buffers of the host-buffer path
 
 struct qf_forest {
     int device = 0;
-    int T = 0, F = 0, fbits = 0, top_levels = 0;
+    int T = 0, F = 0, fbits = 0;
     int64_t N = 0, n_nodes = 0, n_members = 0, max_row_members = 0;
     double expected_row_members = 0.0;
     uint2* d_nodes = nullptr;
-    uint2* d_top = nullptr;
     uint32_t* d_roots = nullptr;
     int32_t* d_node_ids = nullptr;
     uint2* d_members = nullptr;
@@ -63,11 +62,10 @@ struct qf_forest {
     int64_t device_bytes = 0;
     int sm_count = 148;
     // options (0 = auto where noted)
-    int apply_variant = 0;        // 0 auto, 1 = direct kernel, 2 = shared-memory top blocks
-    int apply_row_warps = 0;      // direct kernel: warps along rows per CTA (0 auto)
+    int apply_row_warps = 0;      // warps along rows per CTA (0 auto)
     int apply_ilp = 4;
-    int apply_rows_per_cta = 0;   // top-block kernel: 128 or 256 (0 auto)
-    int apply_chunk_log2 = -1;    // top-block kernel: log2(trees per chunk) (-1 auto)
+    int sort_rows = -1;           // walk rows in locality order: -1 auto, 0 never, 1 always
+    int key_shift = 0, key_bins = 1;   // locality buckets = leaf position in tree 0 >> key_shift
     int64_t rows_per_chunk = 131072;
     int cta_capacity = 4096;      // members per row held in shared memory by the CTA kernel
     int warp_elems = -1;          // warp kernel: keys per lane (2, 4, 8), 0 = never, -1 = auto
@@ -134,8 +132,11 @@ struct Plan {
     bool cta_needed;               // CTA kernel runs (as primary or on overflow list 1)
     bool dense_needed;
     int dense_ctas;
-    int64_t off_seg, off_counts, off_rows1, off_rows2, off_dense, total;
+    bool sort_rows;                // rows are walked in locality order (bucket/order/hist in use)
+    int64_t off_seg, off_counts, off_rows1, off_rows2, off_bucket, off_order, off_hist, off_dense, total;
 };
+
+constexpr int kMaxKeyBins = 65536;
 
 Plan make_plan(const qf_forest* f, int64_t n_rows) {
     Plan pl;
@@ -166,6 +167,12 @@ Plan make_plan(const qf_forest* f, int64_t n_rows) {
     pl.off_counts = o; o += kAlign;                               // two int counters
     pl.off_rows1 = o;  o += align_up(pl.chunk_rows * 4);
     pl.off_rows2 = o;  o += align_up(pl.chunk_rows * 4);
+    // locality order is worth its three small launches once there are enough rows for
+    // neighbours in the order to be neighbours in feature space
+    pl.sort_rows = f->sort_rows > 0 || (f->sort_rows < 0 && n_rows >= 2048);
+    pl.off_bucket = o; o += align_up(pl.chunk_rows * 4);
+    pl.off_order = o;  o += align_up(pl.chunk_rows * 4);
+    pl.off_hist = o;   o += align_up((kMaxKeyBins + 1) * 4);
     pl.off_dense = o;  o += pl.dense_needed ? qf::dense_scratch_bytes(f->N) * pl.dense_ctas : 0;
     pl.total = o;
     return pl;
@@ -173,34 +180,11 @@ Plan make_plan(const qf_forest* f, int64_t n_rows) {
 
 int pick_row_warps(const qf_forest* f) {
     if (f->apply_row_warps > 0) return f->apply_row_warps;
-    int rw = 8;                    // keep the transposed row tile around 16 KB per CTA
-    while (rw > 1 && static_cast<int64_t>(f->F) * 32 * rw * 4 > 16384) rw >>= 1;
+    // 2 row-warps x 4 tree-warps measured best at config 2; fewer trees than tree-warps
+    // would leave warps idle
+    int rw = 2;
+    while (rw < 8 && (8 / rw) > f->T) rw <<= 1;
     return rw;
-}
-
-// shape of the top-block kernel: rows per CTA and trees per chunk so that a CTA needs at
-// most ~110 KB of shared memory (two CTAs per SM); returns false if no shape fits (very
-// wide X), in which case the direct kernel runs.
-bool pick_top_shape(const qf_forest* f, int* rows, int* chunk_log2, size_t* smem) {
-    if (f->top_levels < 2 || !f->d_top) return false;
-    const size_t S = size_t(1) << f->top_levels;
-    auto bytes = [&](int r, int cl) {
-        return static_cast<size_t>(f->F) * r * 4 + (size_t(1) << cl) * S * 8 + (size_t(1) << cl) * (r + 1) * 8;
-    };
-    const int row_opts[2] = {256, 128};
-    for (int budget_kb : {110, 220}) {
-        for (int r : row_opts) {
-            if (f->apply_rows_per_cta && r != f->apply_rows_per_cta) continue;
-            for (int cl = 4; cl >= 0; --cl) {
-                if (f->apply_chunk_log2 >= 0 ? cl != f->apply_chunk_log2 : (cl > 3 || cl < 1)) continue;
-                if (bytes(r, cl) <= static_cast<size_t>(budget_kb) * 1024) {
-                    *rows = r; *chunk_log2 = cl; *smem = bytes(r, cl);
-                    return true;
-                }
-            }
-        }
-    }
-    return false;
 }
 
 template <typename Kernel>
@@ -211,56 +195,31 @@ int set_smem(Kernel kernel, size_t smem) {
     return QF_OK;
 }
 
+// One launch of the leaf-lookup kernel over trees [t_begin, t_end).  `order` (device,
+// nullable) is the locality order of the rows.
 template <int EMIT>
-int launch_apply(qf_forest* f, const float* X, int64_t n, int64_t ldx, void* out, cudaStream_t st) {
-    int rows = 0, chunk_log2 = 0;
-    size_t smem = 0;
-    const bool use_top = f->apply_variant != 1 && pick_top_shape(f, &rows, &chunk_log2, &smem);
-    if (f->apply_variant == 2 && !use_top)
-        return qf::fail(QF_ERR_LIMIT, "apply: top-block kernel requested but its shared memory does not fit");
-    if (use_top) {
-        qf::ApplyTopParams ap;
-        ap.nodes = f->d_nodes;
-        ap.top = f->d_top;
-        ap.X = X;
-        ap.ldx = ldx;
-        ap.n = n;
-        ap.T = f->T;
-        ap.F = f->F;
-        ap.fbits = f->fbits;
-        ap.top_levels = f->top_levels;
-        ap.chunk_log2 = chunk_log2;
-        const int64_t grid = (n + rows - 1) / rows;
-        auto run = [&](auto kernel) -> int {
-            int rc = set_smem(kernel, smem);
-            if (rc != QF_OK) return rc;
-            {
-                SpanTimer span(f, SPAN_APPLY, st);
-                kernel<<<static_cast<unsigned>(grid), rows, smem, st>>>(ap, out);
-            }
-            QF_CUDA_TRY(cudaGetLastError());
-            ++f->launches;
-            return QF_OK;
-        };
-        switch (f->apply_ilp) {
-            case 1: return run(qf::apply_top_kernel<1, EMIT>);
-            case 2: return run(qf::apply_top_kernel<2, EMIT>);
-            case 8: return run(qf::apply_top_kernel<8, EMIT>);
-            default: return run(qf::apply_top_kernel<4, EMIT>);
-        }
-    }
+int launch_apply(qf_forest* f, const float* X, int64_t n, int64_t ldx, void* out, const int* order,
+                 int t_begin, int t_end, int* key_hist, cudaStream_t st) {
     qf::ApplyParams ap;
     ap.nodes = f->d_nodes;
     ap.roots = f->d_roots;
     ap.X = X;
+    ap.order = order;
     ap.ldx = ldx;
     ap.n = n;
     ap.T = f->T;
+    ap.t_begin = t_begin;
+    ap.t_end = t_end;
     ap.F = f->F;
     ap.fbits = f->fbits;
-    ap.row_warps = pick_row_warps(f);
+    // a single tree cannot feed several tree-warps: all 8 warps along rows
+    ap.row_warps = (t_end - t_begin == 1) ? 8 : pick_row_warps(f);
+    ap.key_shift = f->key_shift;
+    ap.key_hist = key_hist;
+    while (ap.row_warps > 1 && static_cast<size_t>(f->F) * 32 * ap.row_warps * sizeof(float) > 200 * 1024)
+        ap.row_warps >>= 1;
     const int rows_per_cta = 32 * ap.row_warps;
-    smem = static_cast<size_t>(f->F) * rows_per_cta * sizeof(float);
+    const size_t smem = static_cast<size_t>(f->F) * rows_per_cta * sizeof(float);
     if (smem > 200 * 1024)
         return qf::fail(QF_ERR_LIMIT, "apply: n_features too large for the shared-memory row tile");
     const int64_t grid = (n + rows_per_cta - 1) / rows_per_cta;
@@ -268,7 +227,7 @@ int launch_apply(qf_forest* f, const float* X, int64_t n, int64_t ldx, void* out
         int rc = set_smem(kernel, smem);
         if (rc != QF_OK) return rc;
         {
-            SpanTimer span(f, SPAN_APPLY, st);
+            SpanTimer span(f, EMIT == qf::APPLY_EMIT_KEY ? SPAN_OTHER : SPAN_APPLY, st);
             kernel<<<static_cast<unsigned>(grid), qf::kApplyThreads, smem, st>>>(ap, out);
         }
         QF_CUDA_TRY(cudaGetLastError());
@@ -281,6 +240,34 @@ int launch_apply(qf_forest* f, const float* X, int64_t n, int64_t ldx, void* out
         case 8: return run(qf::apply_kernel<8, EMIT>);
         default: return run(qf::apply_kernel<4, EMIT>);
     }
+}
+
+// Locality order of one chunk of rows (apply_kernel.cuh): bucket every row by its leaf in
+// tree 0, exclusive scan of the bucket populations, scatter.  Returns the device order
+// array, or nullptr when the plan does not sort.
+int build_locality_order(qf_forest* f, const float* X, int64_t n, int64_t ldx, const Plan& pl,
+                         unsigned char* base, cudaStream_t st, const int** order_out) {
+    *order_out = nullptr;
+    if (!pl.sort_rows) return QF_OK;
+    int* bucket = reinterpret_cast<int*>(base + pl.off_bucket);
+    int* order = reinterpret_cast<int*>(base + pl.off_order);
+    int* hist = reinterpret_cast<int*>(base + pl.off_hist);
+    QF_CUDA_TRY(cudaMemsetAsync(hist, 0, static_cast<size_t>(f->key_bins) * sizeof(int), st));
+    int rc = launch_apply<qf::APPLY_EMIT_KEY>(f, X, n, ldx, bucket, nullptr, 0, 1, hist, st);
+    if (rc != QF_OK) return rc;
+    {
+        SpanTimer span(f, SPAN_OTHER, st);
+        qf::exclusive_scan_kernel<<<1, qf::kScanThreads, 0, st>>>(hist, f->key_bins);
+    }
+    QF_CUDA_TRY(cudaGetLastError());
+    {
+        SpanTimer span(f, SPAN_OTHER, st);
+        qf::order_scatter_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(bucket, n, hist, order);
+    }
+    QF_CUDA_TRY(cudaGetLastError());
+    f->launches += 2;
+    *order_out = order;
+    return QF_OK;
 }
 
 int check_forest_call(const qf_forest* f, const void* X, int64_t n, int64_t ldx, const void* out,
@@ -328,7 +315,10 @@ int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, co
 
     for (int64_t r0 = 0; r0 < n; r0 += pl.chunk_rows) {
         const int64_t rows = std::min(pl.chunk_rows, n - r0);
-        int rc = launch_apply<qf::APPLY_EMIT_SEGMENT>(f, X + r0 * ldx, rows, ldx, seg, st);
+        const int* order = nullptr;
+        int rc = build_locality_order(f, X + r0 * ldx, rows, ldx, pl, base, st, &order);
+        if (rc != QF_OK) return rc;
+        rc = launch_apply<qf::APPLY_EMIT_SEGMENT>(f, X + r0 * ldx, rows, ldx, seg, order, 0, f->T, nullptr, st);
         if (rc != QF_OK) return rc;
         for (int q0 = 0; q0 < nq; q0 += qf::kMaxQuantilesPerLaunch) {
             const int qn = std::min(qf::kMaxQuantilesPerLaunch, nq - q0);
@@ -337,6 +327,7 @@ int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, co
             for (int i = 0; i < qn; ++i) ql.q[i] = q_host[q0 + i];
             qf::QuantileParams qp;
             qp.seg = seg;
+            qp.order = order;
             qp.members = f->d_members;
             qp.y_sorted = f->d_y_sorted;
             qp.out = out + r0 * nq + q0;
@@ -423,8 +414,6 @@ int qf_forest_create(const qf_forest_desc* d, qf_forest** out) {
         return qf::fail(QF_ERR_INVALID, "qf_forest_create: feature_bits does not cover n_features");
     if (d->n_nodes >= (int64_t(1) << 31) || d->n_members > 0xFFFFFFFFll || d->n_train >= (int64_t(1) << 31))
         return qf::fail(QF_ERR_LIMIT, "qf_forest_create: forest exceeds the 32-bit packed layout");
-    if (d->top_blocks && (d->top_levels < 2 || d->top_levels > 14))
-        return qf::fail(QF_ERR_INVALID, "qf_forest_create: top_levels must be in [2,14]");
     int count = 0;
     QF_CUDA_TRY(cudaGetDeviceCount(&count));
     if (d->device < 0 || d->device >= count)
@@ -447,7 +436,13 @@ int qf_forest_create(const qf_forest_desc* d, qf_forest** out) {
     f->max_row_members = d->max_row_members > 0 ? d->max_row_members : d->n_members;
     f->expected_row_members = d->expected_row_members > 0 ? d->expected_row_members
                                                           : static_cast<double>(f->max_row_members);
-    f->top_levels = d->top_blocks ? d->top_levels : 0;
+    {   // locality buckets: leaf position inside tree 0, at most kMaxKeyBins of them
+        const int64_t n0 = d->tree_offsets[1] - d->tree_offsets[0];
+        int shift = 0;
+        while (((n0 - 1) >> shift) >= kMaxKeyBins) ++shift;
+        f->key_shift = shift;
+        f->key_bins = static_cast<int>(((n0 - 1) >> shift) + 1);
+    }
     f->sm_count = prop.multiProcessorCount;
 
     std::vector<uint32_t> roots(d->n_trees);
@@ -469,9 +464,6 @@ int qf_forest_create(const qf_forest_desc* d, qf_forest** out) {
     if (rc == QF_OK) rc = upload(reinterpret_cast<void**>(&f->d_y_sorted), d->y_sorted, d->n_train * 4);
     if (rc == QF_OK && d->leaf_values)
         rc = upload(reinterpret_cast<void**>(&f->d_values), d->leaf_values, d->n_nodes * 8);
-    if (rc == QF_OK && d->top_blocks)
-        rc = upload(reinterpret_cast<void**>(&f->d_top), d->top_blocks,
-                    (static_cast<int64_t>(d->n_trees) << d->top_levels) * 8);
     if (rc != QF_OK) {
         const std::string keep = qf::last_error_slot();
         qf_forest_destroy(f);
@@ -485,7 +477,6 @@ void qf_forest_destroy(qf_forest* f) {
     if (!f) return;
     DeviceGuard guard(f->device);
     cudaFree(f->d_nodes);
-    cudaFree(f->d_top);
     cudaFree(f->d_roots);
     cudaFree(f->d_node_ids);
     cudaFree(f->d_members);
@@ -529,10 +520,9 @@ int qf_forest_last_timings(qf_forest* f, double* apply_ms, double* quantile_ms) 
 int qf_forest_set_option(qf_forest* f, const char* key, int64_t value) {
     if (!f || !key) return qf::fail(QF_ERR_INVALID, "qf_forest_set_option: null argument");
     const std::string k(key);
-    if (k == "apply_variant") {
-        if (value < 0 || value > 2)
-            return qf::fail(QF_ERR_INVALID, "apply_variant must be 0 (auto), 1 (direct) or 2 (top blocks)");
-        f->apply_variant = static_cast<int>(value);
+    if (k == "sort_rows") {
+        if (value < -1 || value > 1) return qf::fail(QF_ERR_INVALID, "sort_rows must be -1 (auto), 0 or 1");
+        f->sort_rows = static_cast<int>(value);
     } else if (k == "apply_row_warps") {
         if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8)
             return qf::fail(QF_ERR_INVALID, "apply_row_warps must be 0 (auto), 1, 2, 4 or 8");
@@ -541,13 +531,6 @@ int qf_forest_set_option(qf_forest* f, const char* key, int64_t value) {
         if (value != 1 && value != 2 && value != 4 && value != 8)
             return qf::fail(QF_ERR_INVALID, "apply_ilp must be 1, 2, 4 or 8");
         f->apply_ilp = static_cast<int>(value);
-    } else if (k == "apply_rows_per_cta") {
-        if (value != 0 && value != 128 && value != 256)
-            return qf::fail(QF_ERR_INVALID, "apply_rows_per_cta must be 0 (auto), 128 or 256");
-        f->apply_rows_per_cta = static_cast<int>(value);
-    } else if (k == "apply_chunk_log2") {
-        if (value < -1 || value > 4) return qf::fail(QF_ERR_INVALID, "apply_chunk_log2 must be in [-1, 4]");
-        f->apply_chunk_log2 = static_cast<int>(value);
     } else if (k == "rows_per_chunk") {
         if (value < 1) return qf::fail(QF_ERR_INVALID, "rows_per_chunk must be >= 1");
         f->rows_per_chunk = value;
@@ -583,7 +566,10 @@ int qf_forest_apply(qf_forest* f, const float* X, int64_t n, int64_t ldx, int64_
     int32_t* idx = reinterpret_cast<int32_t*>(static_cast<unsigned char*>(ws) + pl.off_seg);
     for (int64_t r0 = 0; r0 < n; r0 += pl.chunk_rows) {
         const int64_t rows = std::min(pl.chunk_rows, n - r0);
-        rc = launch_apply<qf::APPLY_EMIT_NODE>(f, X + r0 * ldx, rows, ldx, idx, st);
+        const int* order = nullptr;
+        rc = build_locality_order(f, X + r0 * ldx, rows, ldx, pl, static_cast<unsigned char*>(ws), st, &order);
+        if (rc != QF_OK) return rc;
+        rc = launch_apply<qf::APPLY_EMIT_NODE>(f, X + r0 * ldx, rows, ldx, idx, order, 0, f->T, nullptr, st);
         if (rc != QF_OK) return rc;
         const int64_t total = rows * f->T;
         const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, f->sm_count * 16));
@@ -611,7 +597,10 @@ int qf_forest_predict_mean(qf_forest* f, const float* X, int64_t n, int64_t ldx,
     int32_t* idx = reinterpret_cast<int32_t*>(static_cast<unsigned char*>(ws) + pl.off_seg);
     for (int64_t r0 = 0; r0 < n; r0 += pl.chunk_rows) {
         const int64_t rows = std::min(pl.chunk_rows, n - r0);
-        rc = launch_apply<qf::APPLY_EMIT_NODE>(f, X + r0 * ldx, rows, ldx, idx, st);
+        const int* order = nullptr;
+        rc = build_locality_order(f, X + r0 * ldx, rows, ldx, pl, static_cast<unsigned char*>(ws), st, &order);
+        if (rc != QF_OK) return rc;
+        rc = launch_apply<qf::APPLY_EMIT_NODE>(f, X + r0 * ldx, rows, ldx, idx, order, 0, f->T, nullptr, st);
         if (rc != QF_OK) return rc;
         qf::mean_kernel<<<static_cast<unsigned>((rows + 127) / 128), 128, 0, st>>>(idx, rows, f->T, f->d_values,
                                                                                    out + r0);

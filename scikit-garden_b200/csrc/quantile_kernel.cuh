@@ -28,10 +28,12 @@ struct QuantileList {
 };
 
 struct QuantileParams {
-    const uint2* __restrict__ seg;        // [n][T] (member start, member count) from K1
+    const uint2* __restrict__ seg;        // [n][T] (member start, member count) from K1, rows in
+                                          //   the locality order of K1
+    const int* __restrict__ order;        // [n] locality position -> output row; nullptr = identity
     const uint2* __restrict__ members;    // (rank, float bits of weight)
     const float* __restrict__ y_sorted;   // [N]  y_train_.astype(f32)[sorter]
-    double* __restrict__ out;             // [n][ldo]
+    double* __restrict__ out;             // [n][ldo], indexed by output row
     int64_t n;
     int64_t ldo;                          // row stride of out (total number of quantiles)
     int T;
@@ -183,7 +185,7 @@ quantile_warp_kernel(const QuantileParams p, const __grid_constant__ QuantileLis
         if (lane == 0) p.overflow_rows[atomicAdd(p.overflow_count, 1)] = static_cast<int>(row);
         return;
     }
-    double* __restrict__ out = p.out + row * p.ldo;
+    double* __restrict__ out = p.out + (p.order ? static_cast<int64_t>(__ldg(p.order + row)) : row) * p.ldo;
     __syncwarp();
 
     // 2. keys into registers (blocked: v = lane*E + i), padding sorts last
@@ -338,7 +340,7 @@ quantile_cta_kernel(const QuantileParams p, const __grid_constant__ QuantileList
         if (tid == 0) p.overflow_rows[atomicAdd(p.overflow_count, 1)] = static_cast<int>(row);
         continue;
     }
-    double* __restrict__ out = p.out + row * p.ldo;
+    double* __restrict__ out = p.out + (p.order ? static_cast<int64_t>(__ldg(p.order + row)) : row) * p.ldo;
     if (P == 0) {                                       // cannot happen for a fitted forest
         for (int qi = tid; qi < p.Q; qi += THREADS) out[qi] = __longlong_as_double(0x7ff8000000000000LL);
         continue;
@@ -578,7 +580,7 @@ quantile_dense_kernel(const QuantileParams p, const __grid_constant__ QuantileLi
 
         // D. percentiles
         const int m = s_m;
-        double* __restrict__ out = p.out + row * p.ldo;
+        double* __restrict__ out = p.out + (p.order ? static_cast<int64_t>(__ldg(p.order + row)) : row) * p.ldo;
         if (m == 0) {
             for (int qi = tid; qi < p.Q; qi += THREADS) out[qi] = __longlong_as_double(0x7ff8000000000000LL);
         } else {

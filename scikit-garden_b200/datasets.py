@@ -21,6 +21,8 @@ CONFIGS = {
     # reduced-size stand-ins used by tests and quick runs (NOT bench lines)
     "c2_small": dict(kind="rf", n_estimators=20, min_samples_leaf=1, n_train=20_000, n_test=20_000,
                      n_features=20, quantiles=[5.0, 50.0, 95.0], label="C2 at 1/5 scale"),
+    "c3q": dict(kind="et", n_estimators=500, min_samples_leaf=5, n_train=250_000, n_test=250_000,
+                n_features=50, quantiles=[5.0, 50.0, 95.0], label="C3 with a quarter of the rows (same T, leaf size)"),
     "c3_small": dict(kind="et", n_estimators=50, min_samples_leaf=5, n_train=100_000, n_test=50_000,
                      n_features=50, quantiles=[5.0, 50.0, 95.0], label="C3 at 1/10 scale"),
 }

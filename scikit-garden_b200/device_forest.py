@@ -45,8 +45,7 @@ class DeviceForest:
         keep = [np.ascontiguousarray(flat.nodes), np.ascontiguousarray(flat.tree_offsets),
                 None if flat.node_ids is None else np.ascontiguousarray(flat.node_ids),
                 np.ascontiguousarray(flat.members), np.ascontiguousarray(flat.y_sorted),
-                np.ascontiguousarray(flat.leaf_values) if with_leaf_values else None,
-                None if flat.top_blocks is None else np.ascontiguousarray(flat.top_blocks)]
+                np.ascontiguousarray(flat.leaf_values) if with_leaf_values else None]
         desc.nodes = keep[0].ctypes.data
         desc.tree_offsets = keep[1].ctypes.data
         desc.node_ids = None if keep[2] is None else keep[2].ctypes.data
@@ -55,8 +54,6 @@ class DeviceForest:
         desc.leaf_values = None if keep[5] is None else keep[5].ctypes.data
         desc.max_row_members = flat.max_row_members
         desc.expected_row_members = float(flat.expected_row_members)
-        desc.top_levels = int(flat.top_levels) if keep[6] is not None else 0
-        desc.top_blocks = None if keep[6] is None else keep[6].ctypes.data
         torch.cuda.init()
         with torch.cuda.device(self.device):
             torch.cuda.current_stream().synchronize()      # make sure the primary context exists

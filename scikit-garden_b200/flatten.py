@@ -56,25 +56,6 @@ class FlatForest:
     expected_row_members: float  # sum over trees of E[leaf size] for a training-like row
     max_depth: int
     sorter: np.ndarray = field(repr=False, default=None)   # int64 [N] np.argsort(y_train_)
-    top_levels: int = 0                                    # levels held by top_blocks
-    top_blocks: Optional[np.ndarray] = field(repr=False, default=None)   # uint64 [T << top_levels]
-
-    def __post_init__(self):
-        if self.top_blocks is None:
-            self.build_top_blocks()
-
-    def build_top_blocks(self, levels: Optional[int] = None) -> None:
-        """Breadth-first copies of the upper tree levels for the leaf-lookup kernel
-        (qf_build_top_blocks).  Default: 10 levels (8 KB per tree), fewer for shallow forests."""
-        if levels is None:
-            levels = int(min(10, max(2, self.max_depth + 1)))
-        top = np.empty(self.n_trees << levels, dtype=np.uint64)
-        rc = _native.lib().qf_build_top_blocks(
-            self.n_trees, _ptr(np.ascontiguousarray(self.tree_offsets)), _ptr(self.nodes),
-            self.feature_bits, levels, _ptr(top))
-        if rc != 0:
-            raise _native.QFError(rc, _native.last_error())
-        self.top_levels, self.top_blocks = levels, top
 
     @property
     def n_nodes(self) -> int:
@@ -86,7 +67,7 @@ class FlatForest:
 
     def nbytes(self) -> int:
         return int(self.nodes.nbytes + self.members.nbytes + self.y_sorted.nbytes +
-                   self.leaf_values.nbytes + self.top_blocks.nbytes +
+                   self.leaf_values.nbytes +
                    (0 if self.node_ids is None else self.node_ids.nbytes))
 
     # -- on-disk format: a plain .npz of the arrays above

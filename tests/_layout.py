@@ -29,44 +29,6 @@ def decode_apply(flat, X):
     return node_idx, start, count
 
 
-def decode_apply_top(flat, X):
-    """Same walk, but the upper levels come from the breadth-first top blocks (what the
-    shared-memory kernel does): heap slot h -> 2h (left) / 2h+1 (right) until an exit slot,
-    then the depth-first array from the exit's node."""
-    X = np.asarray(X, dtype=np.float32)
-    n, T, L = X.shape[0], flat.n_trees, flat.top_levels
-    S = 1 << L
-    lo = (flat.nodes & np.uint64(0xFFFFFFFF)).astype(np.uint32)
-    hi = (flat.nodes >> np.uint64(32)).astype(np.uint32)
-    tlo = (flat.top_blocks & np.uint64(0xFFFFFFFF)).astype(np.uint32)
-    thi = (flat.top_blocks >> np.uint64(32)).astype(np.uint32)
-    fmask = np.uint32((1 << flat.feature_bits) - 1)
-    rows = np.arange(n)
-    node_idx = np.zeros((n, T), dtype=np.int64)
-    for t in range(T):
-        h = np.ones(n, dtype=np.int64)
-        for _ in range(L - 1):
-            slot = t * S + h
-            internal = (thi[slot] & np.uint32(0x80000000)) == 0
-            r = rows[internal]
-            sl = slot[r]
-            go_right = ~(X[r, thi[sl].astype(np.int64)] <= tlo[sl].view(np.float32))
-            h[r] = 2 * h[r] + go_right
-        slot = t * S + h
-        assert np.all((thi[slot] & np.uint32(0x80000000)) != 0)
-        node = tlo[slot].astype(np.int64)
-        active = (hi[node] & np.uint32(0x80000000)) == 0
-        while active.any():
-            r = np.flatnonzero(active)
-            nd = node[r]
-            f = (hi[nd] & fmask).astype(np.int64)
-            off = (hi[nd] >> np.uint32(flat.feature_bits)).astype(np.int64)
-            node[r] = nd + np.where(X[r, f] <= lo[nd].view(np.float32), 1, off)
-            active[r] = (hi[node[r]] & np.uint32(0x80000000)) == 0
-        node_idx[:, t] = node
-    return node_idx
-
-
 def sklearn_ids(flat, node_idx):
     if flat.node_ids is None:
         return node_idx - flat.tree_offsets[:-1][None, :]

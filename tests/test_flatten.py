@@ -26,18 +26,6 @@ def test_layout_reproduces_reference(name):
     np.testing.assert_allclose(got / flat.n_trees, g.mean, rtol=1e-12)
 
 
-@pytest.mark.parametrize("name", _golden.CASES)
-@pytest.mark.parametrize("levels", [None, 2, 5])
-def test_top_blocks_reach_the_same_leaves(name, levels):
-    g = _golden.load(name)
-    flat = _golden.flat_from_golden(g)
-    if levels is not None:
-        flat.build_top_blocks(levels)
-    assert flat.top_blocks.shape[0] == flat.n_trees << flat.top_levels
-    node_idx = _layout.decode_apply_top(flat, g.X_test)
-    assert_array_equal(_layout.sklearn_ids(flat, node_idx), g.apply)
-
-
 def test_best_first_trees_are_renumbered():
     g = _golden.load("rf_maxleaf50")
     flat = _golden.flat_from_golden(g)

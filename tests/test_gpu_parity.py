@@ -73,23 +73,19 @@ def test_dense_fallback_is_identical(name):
 
 
 @pytest.mark.parametrize("opts", [
-    dict(apply_variant=1, apply_row_warps=1, apply_ilp=1), dict(apply_variant=1, apply_row_warps=2, apply_ilp=2),
-    dict(apply_variant=1, apply_row_warps=8, apply_ilp=8), dict(rows_per_chunk=37),
-    dict(apply_variant=2, apply_rows_per_cta=128, apply_chunk_log2=0, apply_ilp=1),
-    dict(apply_variant=2, apply_rows_per_cta=256, apply_chunk_log2=2, apply_ilp=2),
-    dict(apply_variant=2, apply_rows_per_cta=128, apply_chunk_log2=4, apply_ilp=8),
-    dict(apply_variant=2, top_levels=3), dict(apply_variant=2, top_levels=12, apply_chunk_log2=1),
+    dict(apply_row_warps=1, apply_ilp=1), dict(apply_row_warps=2, apply_ilp=2),
+    dict(apply_row_warps=8, apply_ilp=8), dict(rows_per_chunk=37),
+    dict(sort_rows=0), dict(sort_rows=1), dict(sort_rows=1, rows_per_chunk=100, apply_row_warps=4),
+    dict(sort_rows=1, warp_elems=0), dict(sort_rows=1, warp_elems=2, cta_capacity=64, dense_ctas=2),
     dict(warp_elems=0), dict(warp_elems=2), dict(warp_elems=4), dict(warp_elems=8),
     dict(warp_elems=2, cta_capacity=64), dict(warp_elems=4, cta_capacity=128, dense_ctas=2)])
 def test_launch_shapes_do_not_change_results(opts):
     g = _golden.load("et_msl5")
     flat = _golden.flat_from_golden(g)
-    opts = dict(opts)
-    if "top_levels" in opts:
-        flat.build_top_blocks(opts.pop("top_levels"))
     dev = _dev(flat, **opts)
     X = _cuda(g.X_test)
     assert_array_equal(dev.apply(X).cpu().numpy(), g.apply)
+    assert_array_equal(dev.predict_mean(X).cpu().numpy(), g.mean)
     assert_array_equal(dev.predict_quantiles(X, g.q).cpu().numpy().T, g.pred)
     assert_array_equal(dev.predict_quantiles_host(g.X_test, g.q, chunk_rows=41).T, g.pred)
     dev.close()
