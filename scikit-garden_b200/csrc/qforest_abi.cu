@@ -67,7 +67,8 @@ struct qf_forest {
     int sort_rows = -1;           // walk rows in locality order: -1 auto, 0 never, 1 always
     int key_shift = 0, key_bins = 1;   // locality buckets = leaf position in tree 0 >> key_shift
     int64_t rows_per_chunk = 131072;
-    int cta_capacity = 4096;      // members per row held in shared memory by the CTA kernel
+    int cta_capacity = 0;         // cap on the members per row of the first bucket stage (0 = its capacity)
+    int cta2_capacity = 8192;     // same for the 512-thread overflow stage (0 = stage not used)
     int warp_elems = -1;          // warp kernel: keys per lane (2, 4, 8), 0 = never, -1 = auto
     int dense_ctas = 0;           // 0 = auto
     // counters
@@ -116,45 +117,56 @@ void reset_call_counters(qf_forest* f) {
     f->spans.clear();
 }
 
-int next_pow2(int64_t v) {
-    int p = 2;
-    while (p < v && p < (1 << 30)) p <<= 1;
-    return p;
-}
-
 // Which kernels a call runs, and how the caller's workspace is carved up for one chunk.
-//   warp kernel (P <= 32*E, registers)  --overflow list 1-->  CTA kernel (P <= cap, smem)
-//   --overflow list 2-->  dense kernel (any P, global scratch)
+// The weight+percentile kernels form a chain; a row that does not fit a stage is appended
+// to that stage's overflow list and picked up by the next one:
+//   warp kernel (P <= 32*E, registers)  ->  bucket kernel (P <= 16 * threads, shared memory)
+//   ->  bucket kernel with 512 threads (P <= 8192)  ->  dense kernel (any P, global scratch)
 struct Plan {
     int64_t chunk_rows;
-    int warp_elems;                // 0 = warp kernel not used (CTA kernel is the primary)
-    int cap;                       // shared-memory member capacity of the CTA kernel
-    bool cta_needed;               // CTA kernel runs (as primary or on overflow list 1)
+    int warp_elems;                // 0 = warp kernel not used
+    int s1_threads, s1_limit;      // first bucket stage (0 threads = not used)
+    int s2_limit;                  // second bucket stage, 512 threads (0 = not used)
     bool dense_needed;
     int dense_ctas;
     bool sort_rows;                // rows are walked in locality order (bucket/order/hist in use)
-    int64_t off_seg, off_counts, off_rows1, off_rows2, off_bucket, off_order, off_hist, off_dense, total;
+    int64_t off_seg, off_counts, off_rows[3], off_bucket, off_order, off_hist, off_dense, total;
 };
 
 constexpr int kMaxKeyBins = 65536;
+constexpr int kMaxBucketThreads = 512;
 
 Plan make_plan(const qf_forest* f, int64_t n_rows) {
     Plan pl;
     pl.chunk_rows = std::max<int64_t>(1, std::min<int64_t>(n_rows, f->rows_per_chunk));
-    pl.cap = std::min(next_pow2(std::max<int64_t>(f->max_row_members, 2)), f->cta_capacity);
+    const int64_t max_members = std::max<int64_t>(f->max_row_members, 1);
+    const double typical = std::max(1.0, f->expected_row_members) * 1.25;
     // warp kernel: ranks must fit 32 - log2(32*E) bits, and the typical row must fit 32*E
     int we = f->warp_elems;
     if (we < 0) {
-        const double typical = std::max(1.0, f->expected_row_members) * 1.2;
         we = typical <= 64 ? 2 : (typical <= 128 ? 4 : (typical <= 256 ? 8 : 0));
-        if (f->max_row_members <= 64) we = 2;
-        else if (f->max_row_members <= 128 && we != 2) we = 4;
+        if (max_members <= 64) we = 2;
+        else if (max_members <= 128 && we != 2) we = 4;
     }
     if (we != 0 && f->N > (int64_t(1) << 24)) we = 0;
     pl.warp_elems = we;
-    const int warp_cap = 32 * we;
-    pl.cta_needed = we == 0 || f->max_row_members > warp_cap;
-    pl.dense_needed = f->max_row_members > pl.cap;
+    int64_t covered = 32 * we;                                    // largest row handled so far
+    pl.s1_threads = pl.s1_limit = pl.s2_limit = 0;
+    if (we == 0 || max_members > covered) {
+        const int64_t want = std::min<int64_t>(max_members, static_cast<int64_t>(typical * 1.1) + 1);
+        int threads = 64;
+        while (threads < kMaxBucketThreads && qf::bucket_kernel_capacity(threads) < want) threads <<= 1;
+        pl.s1_threads = threads;
+        pl.s1_limit = qf::bucket_kernel_capacity(threads);
+        if (f->cta_capacity > 0) pl.s1_limit = std::min(pl.s1_limit, f->cta_capacity);
+        covered = pl.s1_limit;
+        if (max_members > covered && f->cta2_capacity > 0 &&
+            (threads < kMaxBucketThreads || pl.s1_limit < qf::bucket_kernel_capacity(threads))) {
+            pl.s2_limit = std::min(qf::bucket_kernel_capacity(kMaxBucketThreads), f->cta2_capacity);
+            covered = std::max<int64_t>(covered, pl.s2_limit);
+        }
+    }
+    pl.dense_needed = max_members > covered;
     pl.dense_ctas = 0;
     if (pl.dense_needed) {
         const int64_t per = qf::dense_scratch_bytes(f->N);         // bound the scratch to ~2 GiB
@@ -164,9 +176,8 @@ Plan make_plan(const qf_forest* f, int64_t n_rows) {
     }
     int64_t o = 0;
     pl.off_seg = o;    o += align_up(pl.chunk_rows * f->T * 8);
-    pl.off_counts = o; o += kAlign;                               // two int counters
-    pl.off_rows1 = o;  o += align_up(pl.chunk_rows * 4);
-    pl.off_rows2 = o;  o += align_up(pl.chunk_rows * 4);
+    pl.off_counts = o; o += kAlign;                               // one int counter per overflow list
+    for (int k = 0; k < 3; ++k) { pl.off_rows[k] = o; o += align_up(pl.chunk_rows * 4); }
     // locality order is worth its three small launches once there are enough rows for
     // neighbours in the order to be neighbours in feature space
     pl.sort_rows = f->sort_rows > 0 || (f->sort_rows < 0 && n_rows >= 2048);
@@ -289,6 +300,25 @@ int check_quantiles(const double* q_host, int nq, int mode, const char* who) {
     return QF_OK;
 }
 
+int launch_bucket_kernel(int threads, unsigned grid, const qf::QuantileParams& qp, const qf::QuantileList& ql,
+                         int T, cudaStream_t st) {
+    const size_t smem = qf::bucket_kernel_smem(threads, T);
+    if (smem > 220 * 1024)
+        return qf::fail(QF_ERR_LIMIT, "predict_quantiles: n_estimators too large for shared memory");
+    auto run = [&](auto kernel) -> int {
+        int rc = set_smem(kernel, smem);
+        if (rc != QF_OK) return rc;
+        kernel<<<grid, threads, smem, st>>>(qp, ql);
+        return QF_OK;
+    };
+    switch (threads) {
+        case 64: return run(qf::quantile_bucket_kernel<64>);
+        case 128: return run(qf::quantile_bucket_kernel<128>);
+        case 256: return run(qf::quantile_bucket_kernel<256>);
+        default: return run(qf::quantile_bucket_kernel<512>);
+    }
+}
+
 // `pl` is the caller's carve-up of `ws` (made once for the largest chunk, so that the
 // zeroed dense scratch stays where the kernels expect it for every chunk).
 int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, const double* q_host,
@@ -299,19 +329,9 @@ int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, co
         return qf::fail(QF_ERR_WORKSPACE, "predict_quantiles: workspace too small");
     unsigned char* base = static_cast<unsigned char*>(ws);
     uint2* seg = reinterpret_cast<uint2*>(base + pl.off_seg);
-    int* counts = reinterpret_cast<int*>(base + pl.off_counts);   // [0]: list 1, [1]: list 2
-    int* rows1 = reinterpret_cast<int*>(base + pl.off_rows1);
-    int* rows2 = reinterpret_cast<int*>(base + pl.off_rows2);
-
-    const int cta_threads = pl.cap <= 256 ? 64 : 256;
-    const size_t cta_smem = static_cast<size_t>(pl.cap) * 16 + static_cast<size_t>(f->T) * 8 + 16;
-    if (pl.cta_needed) {
-        if (cta_smem > 220 * 1024)
-            return qf::fail(QF_ERR_LIMIT, "predict_quantiles: n_estimators too large for shared memory");
-        int rc = cta_threads == 64 ? set_smem(qf::quantile_cta_kernel<64>, cta_smem)
-                                   : set_smem(qf::quantile_cta_kernel<256>, cta_smem);
-        if (rc != QF_OK) return rc;
-    }
+    int* counts = reinterpret_cast<int*>(base + pl.off_counts);   // [k]: rows in overflow list k
+    int* lists[3];
+    for (int k = 0; k < 3; ++k) lists[k] = reinterpret_cast<int*>(base + pl.off_rows[k]);
 
     for (int64_t r0 = 0; r0 < n; r0 += pl.chunk_rows) {
         const int64_t rows = std::min(pl.chunk_rows, n - r0);
@@ -335,54 +355,64 @@ int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, co
             qp.ldo = nq;
             qp.T = f->T;
             qp.Q = qn;
-            qp.cap = pl.cap;
-            qp.row_list = nullptr;
+            qp.cap = 0;
+            qp.row_list = nullptr;                       // first stage: every row of the chunk
             qp.row_count = nullptr;
-            qp.overflow_count = counts + 1;
-            qp.overflow_rows = rows2;
-            const bool lists = (pl.warp_elems && pl.cta_needed) || pl.dense_needed;
-            if (lists) QF_CUDA_TRY(cudaMemsetAsync(counts, 0, 2 * sizeof(int), st));
-
-            if (pl.warp_elems) {                         // primary: one warp per row
-                qp.overflow_count = counts + 0;
-                qp.overflow_rows = rows1;
+            QF_CUDA_TRY(cudaMemsetAsync(counts, 0, 4 * sizeof(int), st));
+            int stage = 0;                               // stage k appends to lists[k]
+            auto chain = [&]() {                         // wire this stage's overflow, next stage's input
+                qp.overflow_count = counts + stage;
+                qp.overflow_rows = lists[stage];
+            };
+            auto advance = [&]() {
+                qp.row_list = lists[stage];
+                qp.row_count = counts + stage;
+                ++stage;
+            };
+            if (pl.warp_elems) {                         // one warp per row
+                chain();
                 const unsigned grid =
                     static_cast<unsigned>((rows + qf::kWarpKernelWarps - 1) / qf::kWarpKernelWarps);
-                SpanTimer span(f, SPAN_QUANTILE, st);
-                if (pl.warp_elems == 2)
-                    qf::quantile_warp_kernel<2><<<grid, qf::kWarpKernelWarps * 32, 0, st>>>(qp, ql);
-                else if (pl.warp_elems == 4)
-                    qf::quantile_warp_kernel<4><<<grid, qf::kWarpKernelWarps * 32, 0, st>>>(qp, ql);
-                else
-                    qf::quantile_warp_kernel<8><<<grid, qf::kWarpKernelWarps * 32, 0, st>>>(qp, ql);
-                ++f->launches;
-            }
-            QF_CUDA_TRY(cudaGetLastError());
-            if (pl.cta_needed) {                         // primary, or the warp kernel's overflow list
-                unsigned grid = static_cast<unsigned>(rows);
-                if (pl.warp_elems) {
-                    qp.row_list = rows1;
-                    qp.row_count = counts + 0;
-                    grid = static_cast<unsigned>(std::min<int64_t>(rows, int64_t(f->sm_count) * 8));
+                {
+                    SpanTimer span(f, SPAN_QUANTILE, st);
+                    if (pl.warp_elems == 2)
+                        qf::quantile_warp_kernel<2><<<grid, qf::kWarpKernelWarps * 32, 0, st>>>(qp, ql);
+                    else if (pl.warp_elems == 4)
+                        qf::quantile_warp_kernel<4><<<grid, qf::kWarpKernelWarps * 32, 0, st>>>(qp, ql);
+                    else
+                        qf::quantile_warp_kernel<8><<<grid, qf::kWarpKernelWarps * 32, 0, st>>>(qp, ql);
                 }
-                qp.overflow_count = counts + 1;
-                qp.overflow_rows = rows2;
-                SpanTimer span(f, SPAN_QUANTILE, st);
-                if (cta_threads == 64)
-                    qf::quantile_cta_kernel<64><<<grid, 64, cta_smem, st>>>(qp, ql);
-                else
-                    qf::quantile_cta_kernel<256><<<grid, 256, cta_smem, st>>>(qp, ql);
+                QF_CUDA_TRY(cudaGetLastError());
                 ++f->launches;
+                advance();
             }
-            QF_CUDA_TRY(cudaGetLastError());
+            const int bucket_threads[2] = {pl.s1_threads, pl.s2_limit ? kMaxBucketThreads : 0};
+            const int bucket_limit[2] = {pl.s1_limit, pl.s2_limit};
+            for (int b = 0; b < 2; ++b) {
+                if (!bucket_threads[b]) continue;
+                chain();
+                qp.cap = bucket_limit[b];
+                // the first stage gets a CTA per row; overflow stages a persistent grid over their list
+                const unsigned grid = qp.row_list ? static_cast<unsigned>(std::min<int64_t>(rows, int64_t(f->sm_count) * 4))
+                                                  : static_cast<unsigned>(rows);
+                {
+                    SpanTimer span(f, SPAN_QUANTILE, st);
+                    rc = launch_bucket_kernel(bucket_threads[b], grid, qp, ql, f->T, st);
+                }
+                if (rc != QF_OK) return rc;
+                QF_CUDA_TRY(cudaGetLastError());
+                ++f->launches;
+                advance();
+            }
             if (pl.dense_needed) {
-                qp.row_list = rows2;
-                qp.row_count = counts + 1;
-                SpanTimer span(f, SPAN_QUANTILE, st);
-                qf::quantile_dense_kernel<256><<<pl.dense_ctas, 256, 0, st>>>(qp, ql, base + pl.off_dense, f->N);
+                chain();                                 // the dense kernel never overflows
+                {
+                    SpanTimer span(f, SPAN_QUANTILE, st);
+                    qf::quantile_dense_kernel<256><<<pl.dense_ctas, 256, 0, st>>>(qp, ql, base + pl.off_dense, f->N);
+                }
+                QF_CUDA_TRY(cudaGetLastError());
                 ++f->launches;
             }
-            QF_CUDA_TRY(cudaGetLastError());
         }
     }
     return QF_OK;
@@ -535,9 +565,11 @@ int qf_forest_set_option(qf_forest* f, const char* key, int64_t value) {
         if (value < 1) return qf::fail(QF_ERR_INVALID, "rows_per_chunk must be >= 1");
         f->rows_per_chunk = value;
     } else if (k == "cta_capacity") {
-        if (value < 2 || value > 8192 || (value & (value - 1)))
-            return qf::fail(QF_ERR_INVALID, "cta_capacity must be a power of two in [2, 8192]");
+        if (value < 0 || value > 8192) return qf::fail(QF_ERR_INVALID, "cta_capacity must be in [0, 8192]");
         f->cta_capacity = static_cast<int>(value);
+    } else if (k == "cta2_capacity") {
+        if (value < 0 || value > 8192) return qf::fail(QF_ERR_INVALID, "cta2_capacity must be in [0, 8192]");
+        f->cta2_capacity = static_cast<int>(value);
     } else if (k == "warp_elems") {
         if (value != -1 && value != 0 && value != 2 && value != 4 && value != 8)
             return qf::fail(QF_ERR_INVALID, "warp_elems must be -1 (auto), 0 (off), 2, 4 or 8");

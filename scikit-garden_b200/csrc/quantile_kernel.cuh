@@ -289,35 +289,74 @@ quantile_warp_kernel(const QuantileParams p, const __grid_constant__ QuantileLis
 }
 
 // ---------------------------------------------------------------------------------------
-// CTA-per-row kernel: the row's members live in shared memory.
-//   smem: u64 keys[cap] | f32 wts[cap] | f32 cum[cap] | u32 offs[T+1] | u32 starts[T]
+// CTA-per-row kernel for larger member sets (P <= 16 * THREADS): bucket sort in shared
+// memory, no O(P log^2 P) network.
+//
+//   1. gather the (rank, weight) pairs in tree order: rk[pos], wt[pos]; block min / max of
+//      the ranks gives the row's rank window [rmin, rmin + range]
+//   2. counting sort by bucket = (rank - rmin) >> shift with B = 8 * THREADS buckets
+//      (about two members per bucket): integer shared-memory atomics for the histogram
+//      and for the slots (ATOMS ~16 lanes/clk/SM measured, tools/microbench), one block
+//      scan in between.  An entry is the 32-bit word (low rank bits << POSBITS) | pos.
+//   3. order inside a bucket: every entry counts the smaller entries of its bucket
+//      (entries are distinct, so this is a permutation) and moves to base + count.  Equal
+//      ranks end up adjacent and in tree order (pos ascending).
+//   4. group heads add their duplicates in tree order (float32, ensemble.py:140); block
+//      compaction of the heads by ballots + one small scan
+//   5. lane 0: float32 running sum in rank order (utils.py:68) with 128-bit shared accesses
+//   6. one thread per requested percentile (utils.py:72-81)
+//
+// smem: u32 rk[cap] | f32 wt[cap] | u32 srt[cap] | u32 cnt[B + 8] | u32 offs[T + 1] | u32 starts[T]
 // ---------------------------------------------------------------------------------------
+constexpr int kBucketEPT = 16;                          // entries per thread at full capacity
+
+__host__ __device__ constexpr int bucket_kernel_capacity(int threads) { return threads * kBucketEPT; }
+
+__host__ __device__ inline size_t bucket_kernel_smem(int threads, int T) {
+    const size_t cap = static_cast<size_t>(bucket_kernel_capacity(threads));
+    return cap * 12 + (cap / 2 + 8) * 4 + static_cast<size_t>(2 * T + 1) * 4 + 16;
+}
+
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
-quantile_cta_kernel(const QuantileParams p, const __grid_constant__ QuantileList ql) {
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256) ? 768 / THREADS : 1)
+quantile_bucket_kernel(const QuantileParams p, const __grid_constant__ QuantileList ql) {
+    constexpr int CAP = THREADS * kBucketEPT;
+    constexpr int NB = CAP / 2;                         // buckets
+    constexpr int NW = THREADS / 32;
+    constexpr int POSBITS = (THREADS == 64) ? 10 : (THREADS == 128) ? 11 : (THREADS == 256) ? 12 : 13;
+    constexpr int LOG2NB = POSBITS - 1;
+    constexpr uint32_t POSMASK = CAP - 1;
+    static_assert(THREADS == 64 || THREADS == 128 || THREADS == 256 || THREADS == 512, "unsupported block size");
+    static_assert((1 << POSBITS) == CAP, "POSBITS must be log2 of the capacity");
+
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
-    float* wts = reinterpret_cast<float*>(keys + p.cap);
-    float* cum = wts + p.cap;
-    uint32_t* offs = reinterpret_cast<uint32_t*>(cum + p.cap);
-    uint32_t* starts = offs + (p.T + 1);
+    uint32_t* rk = reinterpret_cast<uint32_t*>(smem_raw);          // rank by pos -> compact ranks
+    float* wt = reinterpret_cast<float*>(rk + CAP);                // weight by pos -> compact weights
+    uint32_t* srt = reinterpret_cast<uint32_t*>(wt + CAP);         // entries -> running sum
+    uint32_t* cnt = srt + CAP;                                     // [NB + 8]
+    uint32_t* offs = cnt + NB + 8;                                 // [T + 1]
+    uint32_t* starts = offs + (p.T + 1);                           // [T]
+    __shared__ uint32_t s_red[2 * NW];
+    __shared__ uint32_t s_part[kBucketEPT * NW + 1];
     __shared__ int s_m;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
+    const int warp = tid >> 5;
     const int64_t n_work = p.row_list ? static_cast<int64_t>(*p.row_count) : p.n;
     for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x) {
     const int64_t row = p.row_list ? static_cast<int64_t>(p.row_list[work]) : work;
     const uint2* __restrict__ seg = p.seg + row * p.T;
     __syncthreads();                                    // shared memory reused from the previous row
 
-    // 1. member counts of the row's leaves -> exclusive offsets (tree order)
+    // 0. member counts of the row's leaves -> exclusive offsets (tree order)
     for (int t = tid; t < p.T; t += THREADS) {
         const uint2 s = seg[t];
         starts[t] = s.x;
         offs[t + 1] = s.y;
     }
     if (tid == 0) offs[0] = 0;
+    for (int i = tid; i < NB + 8; i += THREADS) cnt[i] = 0u;
     __syncthreads();
     if (tid < 32) {
         uint32_t carry = 0;
@@ -336,7 +375,7 @@ quantile_cta_kernel(const QuantileParams p, const __grid_constant__ QuantileList
     }
     __syncthreads();
     const uint32_t P = offs[p.T];
-    if (P > static_cast<uint32_t>(p.cap)) {             // too many members for shared memory
+    if (P > static_cast<uint32_t>(min(p.cap, CAP))) {   // too many members for this kernel
         if (tid == 0) p.overflow_rows[atomicAdd(p.overflow_count, 1)] = static_cast<int>(row);
         continue;
     }
@@ -346,98 +385,181 @@ quantile_cta_kernel(const QuantileParams p, const __grid_constant__ QuantileList
         continue;
     }
 
-    // 2. gather: 8 lanes per leaf, key = (rank << 32) | position-in-tree-order
+    // 1. gather: 8 lanes per leaf; rank window of the row
+    uint32_t rmin, shift;
     {
+        uint32_t lo = 0xffffffffu, hi = 0u;
         const int group = tid >> 3, sub = tid & 7;
         for (int t = group; t < p.T; t += THREADS / 8) {
             const uint32_t o = offs[t], len = offs[t + 1] - o;
             const uint2* __restrict__ src = p.members + starts[t];
             for (uint32_t i = sub; i < len; i += 8) {
                 const uint2 e = __ldg(src + i);
-                const uint32_t pos = o + i;
-                keys[pos] = (static_cast<unsigned long long>(e.x) << 32) | pos;
-                wts[pos] = __uint_as_float(e.y);
+                rk[o + i] = e.x;
+                wt[o + i] = __uint_as_float(e.y);
+                lo = min(lo, e.x);
+                hi = max(hi, e.x);
             }
         }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        if (lane == 0) { s_red[warp] = lo; s_red[NW + warp] = hi; }
+        __syncthreads();
+        lo = 0xffffffffu;
+        hi = 0u;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { lo = min(lo, s_red[w]); hi = max(hi, s_red[NW + w]); }
+        rmin = lo;
+        const uint32_t range = hi - lo;
+        const int bits = 32 - __clz(range);             // range < 2^bits
+        shift = static_cast<uint32_t>(max(0, bits - LOG2NB));      // (range >> shift) < NB
     }
-    uint32_t P2 = 2;
-    while (P2 < P) P2 <<= 1;
-    for (uint32_t i = P + tid; i < P2; i += THREADS) keys[i] = ~0ull;
+    const uint32_t lowmask = (1u << shift) - 1u;
+
+    // 2a. bucket populations
+    for (uint32_t i = tid; i < P; i += THREADS) atomicAdd(&cnt[(rk[i] - rmin) >> shift], 1u);
+    __syncthreads();
+    // 2b. exclusive scan of the NB = 8 * THREADS populations (8 consecutive per thread)
+    {
+        uint4 c0 = reinterpret_cast<uint4*>(cnt)[2 * tid];
+        uint4 c1 = reinterpret_cast<uint4*>(cnt)[2 * tid + 1];
+        const uint32_t total = c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w;
+        uint32_t incl = total;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += u;
+        }
+        if (lane == 31) s_red[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) before += (w < warp) ? s_red[w] : 0u;
+        uint32_t run = before + incl - total;
+        uint4 o0, o1;
+        o0.x = run; run += c0.x; o0.y = run; run += c0.y; o0.z = run; run += c0.z; o0.w = run; run += c0.w;
+        o1.x = run; run += c1.x; o1.y = run; run += c1.y; o1.z = run; run += c1.z; o1.w = run;
+        reinterpret_cast<uint4*>(cnt)[2 * tid] = o0;
+        reinterpret_cast<uint4*>(cnt)[2 * tid + 1] = o1;
+    }
+    __syncthreads();
+    // 2c. slots: afterwards cnt[b] is the END of bucket b (= start of bucket b + 1)
+    for (uint32_t i = tid; i < P; i += THREADS) {
+        const uint32_t d = rk[i] - rmin;
+        const uint32_t slot = atomicAdd(&cnt[d >> shift], 1u);
+        srt[slot] = ((d & lowmask) << POSBITS) | i;
+    }
     __syncthreads();
 
-    // 3. bitonic sort by (rank, position): equal ranks stay in tree order
-    for (uint32_t k = 2; k <= P2; k <<= 1) {
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = tid; i < (P2 >> 1); i += THREADS) {
-                const uint32_t lo = i & (j - 1);
-                const uint32_t a = ((i - lo) << 1) + lo;
-                const uint32_t b = a + j;
-                const unsigned long long ka = keys[a], kb = keys[b];
-                const bool up = (a & k) == 0;
-                if ((ka > kb) == up) { keys[a] = kb; keys[b] = ka; }
+    // 3. order inside the buckets
+    {
+        uint32_t key[kBucketEPT], dst[kBucketEPT];
+#pragma unroll
+        for (int j = 0; j < kBucketEPT; ++j) {
+            const uint32_t i = j * THREADS + tid;
+            key[j] = 0u;
+            dst[j] = 0xffffffffu;
+            if (i < P) {
+                const uint32_t k = srt[i];
+                const uint32_t b = (rk[k & POSMASK] - rmin) >> shift;
+                const uint32_t lo = b ? cnt[b - 1] : 0u, hi = cnt[b];
+                uint32_t smaller = 0;
+                for (uint32_t u = lo; u < hi; ++u) smaller += (srt[u] < k) ? 1u : 0u;
+                key[j] = k;
+                dst[j] = lo + smaller;
             }
-            __syncthreads();
         }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kBucketEPT; ++j)
+            if (dst[j] != 0xffffffffu) srt[dst[j]] = key[j];
     }
+    __syncthreads();
 
-    // 4. warp 0: merge equal ranks (float32, tree order) and running sum (float32, rank
-    //    order).  Every lane replays the same sequential arithmetic on values broadcast by
-    //    shuffles, so there is no memory latency inside the dependent chain.
-    if (tid < 32) {
-        int m = 0;
-        uint32_t cur_rank = 0xffffffffu;
-        float W = 0.0f, C = 0.0f;
-        for (uint32_t base = 0; base < P; base += 32) {
-            const uint32_t k = base + lane;
-            uint32_t rk = 0xffffffffu;
-            float wk = 0.0f;
-            if (k < P) {
-                const unsigned long long key = keys[k];
-                rk = static_cast<uint32_t>(key >> 32);
-                wk = wts[static_cast<uint32_t>(key)];
+    // 4. group heads sum their duplicates in tree order (ensemble.py:140), then compact
+    {
+        uint32_t hr[kBucketEPT];
+        float hw[kBucketEPT];
+        uint32_t votes[kBucketEPT];
+#pragma unroll
+        for (int j = 0; j < kBucketEPT; ++j) {
+            const uint32_t i = j * THREADS + tid;
+            uint32_t r = 0xffffffffu;
+            float W = 0.0f;
+            if (i < P) {
+                const uint32_t pos = srt[i] & POSMASK;
+                r = rk[pos];
+                W = wt[pos];
             }
-            __syncwarp();                                // all reads of this batch done before writes below
-            const int cnt = min(32u, P - base);
-            for (int i = 0; i < cnt; ++i) {
-                const uint32_t ri = __shfl_sync(0xffffffffu, rk, i);
-                const float wi = __shfl_sync(0xffffffffu, wk, i);
-                if (ri == cur_rank) {
-                    W = __fadd_rn(W, wi);               // ensemble.py:140, next tree
-                } else {
-                    if (cur_rank != 0xffffffffu && W != 0.0f) {     // utils.py:55-57
-                        C = __fadd_rn(C, W);            // utils.py:68
-                        if (lane == 0) {
-                            keys[m] = (static_cast<unsigned long long>(__float_as_uint(W)) << 32) | cur_rank;
-                            cum[m] = C;
-                        }
-                        ++m;
-                    }
-                    cur_rank = ri;
-                    W = wi;
+            uint32_t prev = __shfl_up_sync(0xffffffffu, r, 1);
+            if (lane == 0) prev = (i > 0 && i < P) ? rk[srt[i - 1] & POSMASK] : 0xfffffffeu;
+            bool head = (i < P) && (r != prev);
+            if (head) {
+                for (uint32_t u = i + 1; u < P; ++u) {
+                    const uint32_t pu = srt[u] & POSMASK;
+                    if (rk[pu] != r) break;
+                    W = __fadd_rn(W, wt[pu]);
                 }
+                head = W != 0.0f;                       // utils.py:55-57
+            }
+            hr[j] = r;
+            hw[j] = W;
+            votes[j] = __ballot_sync(0xffffffffu, head);
+            if (lane == 0) s_part[j * NW + warp] = __popc(votes[j]);
+        }
+        __syncthreads();                                // every read of rk / wt / srt is done
+        if (warp == 0) {                                // exclusive scan of the EPT * NW partial counts
+            uint32_t carry = 0;
+            for (int base = 0; base < kBucketEPT * NW; base += 32) {
+                const uint32_t v = s_part[base + lane];
+                uint32_t incl = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += u;
+                }
+                s_part[base + lane] = carry + incl - v;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) s_m = static_cast<int>(carry);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kBucketEPT; ++j) {
+            if (votes[j] & (1u << lane)) {
+                const uint32_t c = s_part[j * NW + warp] + __popc(votes[j] & ((1u << lane) - 1u));
+                rk[c] = hr[j];
+                wt[c] = hw[j];
             }
         }
-        if (W != 0.0f) {
-            C = __fadd_rn(C, W);
-            if (lane == 0) {
-                keys[m] = (static_cast<unsigned long long>(__float_as_uint(W)) << 32) | cur_rank;
-                cum[m] = C;
-            }
-            ++m;
-        }
-        if (lane == 0) s_m = m;
     }
     __syncthreads();
-
-    // 5. every requested percentile
     const int m = s_m;
     if (m == 0) {
         for (int qi = tid; qi < p.Q; qi += THREADS) out[qi] = __longlong_as_double(0x7ff8000000000000LL);
         continue;
     }
+
+    // 5. lane 0: float32 running sum in rank order (utils.py:68), 4 entries per shared access
+    float* cum = reinterpret_cast<float*>(srt);
+    if (tid == 0) {
+        float C = 0.0f;
+        for (int c = 0; c < m; c += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wt + c);
+            float4 o;
+            C = __fadd_rn(C, w4.x); o.x = C;
+            C = __fadd_rn(C, w4.y); o.y = C;
+            C = __fadd_rn(C, w4.z); o.z = C;
+            C = __fadd_rn(C, w4.w); o.w = C;
+            *reinterpret_cast<float4*>(cum + c) = o;
+        }
+    }
+    __syncthreads();
+
+    // 6. every requested percentile
     const float s = __fdiv_rn(100.0f, cum[m - 1]);      // utils.py:69,72
-    auto rankOf = [&](int k) { return static_cast<uint32_t>(keys[k]); };
-    auto weightOf = [&](int k) { return __uint_as_float(static_cast<uint32_t>(keys[k] >> 32)); };
+    auto rankOf = [&](int k) { return rk[k]; };
+    auto weightOf = [&](int k) { return wt[k]; };
     auto cumOf = [&](int k) { return cum[k]; };
     for (int qi = tid; qi < p.Q; qi += THREADS)
         out[qi] = select_percentile(ql.q[qi], m, s, rankOf, weightOf, cumOf, p.y_sorted);

@@ -62,11 +62,14 @@ def test_every_quantile_kernel_is_identical(name, warp_elems):
 
 
 @pytest.mark.parametrize("name", ["et_msl5", "et_depth2_large_sets", "c1_rfqr_boston"])
-def test_dense_fallback_is_identical(name):
-    # force rows out of shared memory into the global-scratch path
+@pytest.mark.parametrize("cta2_capacity", [0, 40])
+def test_dense_fallback_is_identical(name, cta2_capacity):
+    # force rows out of shared memory into the global-scratch path: directly from the first
+    # bucket stage (cta2_capacity=0) and through the whole chain warp -> bucket -> bucket -> dense
     g = _golden.load(name)
     flat = _golden.flat_from_golden(g)
-    dev = _dev(flat, cta_capacity=8, dense_ctas=3, warp_elems=0)
+    dev = _dev(flat, cta_capacity=8, cta2_capacity=cta2_capacity, dense_ctas=3,
+               warp_elems=0 if cta2_capacity == 0 else 2)
     got = dev.predict_quantiles(_cuda(g.X_test), g.q).cpu().numpy()
     assert_array_equal(got.T, g.pred)
     dev.close()
@@ -78,7 +81,8 @@ def test_dense_fallback_is_identical(name):
     dict(sort_rows=0), dict(sort_rows=1), dict(sort_rows=1, rows_per_chunk=100, apply_row_warps=4),
     dict(sort_rows=1, warp_elems=0), dict(sort_rows=1, warp_elems=2, cta_capacity=64, dense_ctas=2),
     dict(warp_elems=0), dict(warp_elems=2), dict(warp_elems=4), dict(warp_elems=8),
-    dict(warp_elems=2, cta_capacity=64), dict(warp_elems=4, cta_capacity=128, dense_ctas=2)])
+    dict(warp_elems=2, cta_capacity=64), dict(warp_elems=4, cta_capacity=128, dense_ctas=2),
+    dict(warp_elems=0, cta_capacity=300, cta2_capacity=1000), dict(warp_elems=0, cta2_capacity=0)])
 def test_launch_shapes_do_not_change_results(opts):
     g = _golden.load("et_msl5")
     flat = _golden.flat_from_golden(g)
@@ -184,7 +188,7 @@ def test_tree_forest_equivalence():                             # test_ensemble.
 # ---- randomized differential tests against the oracle at sizes it finishes in seconds -------------
 @pytest.mark.parametrize("kind,bootstrap,msl,ties,depth", [
     ("rf", True, 1, True, None), ("et", True, 5, False, None), ("rf", False, 2, False, None),
-    ("et", True, 40, True, None), ("rf", True, 1, False, 6)])
+    ("et", True, 40, True, None), ("rf", True, 1, False, 6), ("rf", True, 1, True, 4)])
 def test_random_forests_bit_exact_vs_oracle(kind, bootstrap, msl, ties, depth):
     import skgarden_b200 as sg
     cls = sg.RandomForestQuantileRegressor if kind == "rf" else sg.ExtraTreesQuantileRegressor
