@@ -46,15 +46,12 @@ struct ApplyParams {
     int F;
     int fbits;
     int row_warps;                         // warps along rows per CTA (block = 256 threads)
-    int key_shift;                         // EMIT_KEY: bucket = (leaf position in the tree) >> key_shift
-    int* __restrict__ key_hist;            // EMIT_KEY: bucket populations (atomicAdd)
 };
 
 // what a finished walk writes
 //   SEGMENT: uint2 out[pos][T]   (member start, member count), pos = position in the locality order
 //   NODE   : int32 out[row][T]   packed node index of the leaf, row = row of X
-//   KEY    : int32 out[row]      locality bucket of the row (single tree), + histogram
-enum { APPLY_EMIT_SEGMENT = 0, APPLY_EMIT_NODE = 1, APPLY_EMIT_KEY = 2 };
+enum { APPLY_EMIT_SEGMENT = 0, APPLY_EMIT_NODE = 1 };
 
 constexpr int kApplyThreads = 256;
 
@@ -123,13 +120,8 @@ apply_kernel(const ApplyParams p, void* __restrict__ out) {
                 if (EMIT == APPLY_EMIT_SEGMENT) {
                     static_cast<uint2*>(out)[out_row * p.T + tree[k]] =
                         make_uint2(nd[k].x, nd[k].y & 0x7fffffffu);
-                } else if (EMIT == APPLY_EMIT_NODE) {
-                    static_cast<int32_t*>(out)[out_row * p.T + tree[k]] = static_cast<int32_t>(node[k]);
                 } else {
-                    const int bucket =
-                        static_cast<int>((node[k] - __ldg(p.roots + tree[k])) >> p.key_shift);
-                    static_cast<int32_t*>(out)[out_row] = bucket;
-                    atomicAdd(p.key_hist + bucket, 1);
+                    static_cast<int32_t*>(out)[out_row * p.T + tree[k]] = static_cast<int32_t>(node[k]);
                 }
                 live &= ~(1u << k);
             } else {
@@ -161,23 +153,44 @@ apply_kernel(const ApplyParams p, void* __restrict__ out) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Locality order: counting sort of the rows by their bucket (EMIT_KEY pass above).
-//   exclusive_scan_kernel : single CTA, in-place exclusive prefix sum of the histogram
+// Locality order: counting sort of the rows by the leaf they reach in ONE tree.
+//   locality_key_kernel   : bucket[row] = (leaf position in the tree) >> key_shift, histogram
+//   exclusive_scan_kernel : single CTA, in-place exclusive prefix sum of the kKeyBins counters
 //   order_scatter_kernel  : order[atomicAdd(&cursor[bucket[row]], 1)] = row
 // The order inside a bucket is whatever the atomics give; results do not depend on it
 // (every row is computed independently and written to its own output row).
 // ---------------------------------------------------------------------------------------
-constexpr int kScanThreads = 1024;
+constexpr int kKeyBins = 8192;                         // counters in the histogram (8 per scan thread)
+constexpr int kScanThreads = kKeyBins / 8;
+
+// lane == row; x is read straight from global memory (a row is one or two lines, L1-resident
+// after the first touch), so there is no tile staging and no barrier for a single tree
+__global__ void __launch_bounds__(128)
+locality_key_kernel(const uint2* __restrict__ nodes, uint32_t root, const float* __restrict__ X,
+                    int64_t ldx, int64_t n, int fbits, int key_shift, int* __restrict__ bucket,
+                    int* __restrict__ hist) {
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const float* __restrict__ x = X + row * ldx;
+    const uint32_t fmask = (1u << fbits) - 1u;
+    uint32_t node = root;
+    for (;;) {
+        const uint2 nd = __ldg(nodes + node);
+        if (static_cast<int32_t>(nd.y) < 0) break;
+        node += (__ldg(x + (nd.y & fmask)) <= __uint_as_float(nd.x)) ? 1u : (nd.y >> fbits);   // _tree.pyx:989
+    }
+    const int b = static_cast<int>((node - root) >> key_shift);
+    bucket[row] = b;
+    atomicAdd(hist + b, 1);
+}
 
 __global__ void __launch_bounds__(kScanThreads)
-exclusive_scan_kernel(int* __restrict__ hist, int n_bins) {
+exclusive_scan_kernel(int* __restrict__ hist) {
     __shared__ int warp_tot[kScanThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (n_bins + kScanThreads - 1) / kScanThreads;     // contiguous bins per thread
-    const int b0 = tid * per;
-    int sum = 0;
-    for (int i = 0; i < per; ++i)
-        if (b0 + i < n_bins) sum += hist[b0 + i];
+    int4 a = reinterpret_cast<int4*>(hist)[2 * tid];
+    int4 b = reinterpret_cast<int4*>(hist)[2 * tid + 1];
+    const int sum = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
     int incl = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -187,7 +200,7 @@ exclusive_scan_kernel(int* __restrict__ hist, int n_bins) {
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-        int v = warp_tot[lane];
+        const int v = warp_tot[lane];
         int iv = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -198,13 +211,11 @@ exclusive_scan_kernel(int* __restrict__ hist, int n_bins) {
     }
     __syncthreads();
     int run = warp_tot[warp] + incl - sum;
-    for (int i = 0; i < per; ++i) {
-        if (b0 + i < n_bins) {
-            const int c = hist[b0 + i];
-            hist[b0 + i] = run;
-            run += c;
-        }
-    }
+    int4 oa, ob;
+    oa.x = run; run += a.x; oa.y = run; run += a.y; oa.z = run; run += a.z; oa.w = run; run += a.w;
+    ob.x = run; run += b.x; ob.y = run; run += b.y; ob.z = run; run += b.z; ob.w = run;
+    reinterpret_cast<int4*>(hist)[2 * tid] = oa;
+    reinterpret_cast<int4*>(hist)[2 * tid + 1] = ob;
 }
 
 __global__ void order_scatter_kernel(const int* __restrict__ bucket, int64_t n, int* __restrict__ cursor,

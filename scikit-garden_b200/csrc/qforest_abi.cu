@@ -66,6 +66,7 @@ struct qf_forest {
     int apply_ilp = 4;
     int sort_rows = -1;           // walk rows in locality order: -1 auto, 0 never, 1 always
     int key_shift = 0, key_bins = 1;   // locality buckets = leaf position in tree 0 >> key_shift
+    uint32_t root0 = 0;
     int64_t rows_per_chunk = 131072;
     int cta_capacity = 0;         // cap on the members per row of the first bucket stage (0 = its capacity)
     int cta2_capacity = 8192;     // same for the 512-thread overflow stage (0 = stage not used)
@@ -133,7 +134,6 @@ struct Plan {
     int64_t off_seg, off_counts, off_rows[3], off_bucket, off_order, off_hist, off_dense, total;
 };
 
-constexpr int kMaxKeyBins = 65536;
 constexpr int kMaxBucketThreads = 512;
 
 Plan make_plan(const qf_forest* f, int64_t n_rows) {
@@ -153,7 +153,8 @@ Plan make_plan(const qf_forest* f, int64_t n_rows) {
     int64_t covered = 32 * we;                                    // largest row handled so far
     pl.s1_threads = pl.s1_limit = pl.s2_limit = 0;
     if (we == 0 || max_members > covered) {
-        const int64_t want = std::min<int64_t>(max_members, static_cast<int64_t>(typical * 1.1) + 1);
+        // the typical row must fit the first stage; rarer, larger rows go on to the 512-thread stage
+        const int64_t want = std::min<int64_t>(max_members, static_cast<int64_t>(f->expected_row_members * 1.15) + 1);
         int threads = 64;
         while (threads < kMaxBucketThreads && qf::bucket_kernel_capacity(threads) < want) threads <<= 1;
         pl.s1_threads = threads;
@@ -183,7 +184,7 @@ Plan make_plan(const qf_forest* f, int64_t n_rows) {
     pl.sort_rows = f->sort_rows > 0 || (f->sort_rows < 0 && n_rows >= 2048);
     pl.off_bucket = o; o += align_up(pl.chunk_rows * 4);
     pl.off_order = o;  o += align_up(pl.chunk_rows * 4);
-    pl.off_hist = o;   o += align_up((kMaxKeyBins + 1) * 4);
+    pl.off_hist = o;   o += align_up(qf::kKeyBins * 4);
     pl.off_dense = o;  o += pl.dense_needed ? qf::dense_scratch_bytes(f->N) * pl.dense_ctas : 0;
     pl.total = o;
     return pl;
@@ -210,7 +211,7 @@ int set_smem(Kernel kernel, size_t smem) {
 // nullable) is the locality order of the rows.
 template <int EMIT>
 int launch_apply(qf_forest* f, const float* X, int64_t n, int64_t ldx, void* out, const int* order,
-                 int t_begin, int t_end, int* key_hist, cudaStream_t st) {
+                 int t_begin, int t_end, cudaStream_t st) {
     qf::ApplyParams ap;
     ap.nodes = f->d_nodes;
     ap.roots = f->d_roots;
@@ -225,8 +226,6 @@ int launch_apply(qf_forest* f, const float* X, int64_t n, int64_t ldx, void* out
     ap.fbits = f->fbits;
     // a single tree cannot feed several tree-warps: all 8 warps along rows
     ap.row_warps = (t_end - t_begin == 1) ? 8 : pick_row_warps(f);
-    ap.key_shift = f->key_shift;
-    ap.key_hist = key_hist;
     while (ap.row_warps > 1 && static_cast<size_t>(f->F) * 32 * ap.row_warps * sizeof(float) > 200 * 1024)
         ap.row_warps >>= 1;
     const int rows_per_cta = 32 * ap.row_warps;
@@ -238,7 +237,7 @@ int launch_apply(qf_forest* f, const float* X, int64_t n, int64_t ldx, void* out
         int rc = set_smem(kernel, smem);
         if (rc != QF_OK) return rc;
         {
-            SpanTimer span(f, EMIT == qf::APPLY_EMIT_KEY ? SPAN_OTHER : SPAN_APPLY, st);
+            SpanTimer span(f, SPAN_APPLY, st);
             kernel<<<static_cast<unsigned>(grid), qf::kApplyThreads, smem, st>>>(ap, out);
         }
         QF_CUDA_TRY(cudaGetLastError());
@@ -263,12 +262,16 @@ int build_locality_order(qf_forest* f, const float* X, int64_t n, int64_t ldx, c
     int* bucket = reinterpret_cast<int*>(base + pl.off_bucket);
     int* order = reinterpret_cast<int*>(base + pl.off_order);
     int* hist = reinterpret_cast<int*>(base + pl.off_hist);
-    QF_CUDA_TRY(cudaMemsetAsync(hist, 0, static_cast<size_t>(f->key_bins) * sizeof(int), st));
-    int rc = launch_apply<qf::APPLY_EMIT_KEY>(f, X, n, ldx, bucket, nullptr, 0, 1, hist, st);
-    if (rc != QF_OK) return rc;
+    QF_CUDA_TRY(cudaMemsetAsync(hist, 0, qf::kKeyBins * sizeof(int), st));
     {
         SpanTimer span(f, SPAN_OTHER, st);
-        qf::exclusive_scan_kernel<<<1, qf::kScanThreads, 0, st>>>(hist, f->key_bins);
+        qf::locality_key_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(
+            f->d_nodes, f->root0, X, ldx, n, f->fbits, f->key_shift, bucket, hist);
+    }
+    QF_CUDA_TRY(cudaGetLastError());
+    {
+        SpanTimer span(f, SPAN_OTHER, st);
+        qf::exclusive_scan_kernel<<<1, qf::kScanThreads, 0, st>>>(hist);
     }
     QF_CUDA_TRY(cudaGetLastError());
     {
@@ -276,7 +279,7 @@ int build_locality_order(qf_forest* f, const float* X, int64_t n, int64_t ldx, c
         qf::order_scatter_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(bucket, n, hist, order);
     }
     QF_CUDA_TRY(cudaGetLastError());
-    f->launches += 2;
+    f->launches += 3;
     *order_out = order;
     return QF_OK;
 }
@@ -338,7 +341,7 @@ int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, co
         const int* order = nullptr;
         int rc = build_locality_order(f, X + r0 * ldx, rows, ldx, pl, base, st, &order);
         if (rc != QF_OK) return rc;
-        rc = launch_apply<qf::APPLY_EMIT_SEGMENT>(f, X + r0 * ldx, rows, ldx, seg, order, 0, f->T, nullptr, st);
+        rc = launch_apply<qf::APPLY_EMIT_SEGMENT>(f, X + r0 * ldx, rows, ldx, seg, order, 0, f->T, st);
         if (rc != QF_OK) return rc;
         for (int q0 = 0; q0 < nq; q0 += qf::kMaxQuantilesPerLaunch) {
             const int qn = std::min(qf::kMaxQuantilesPerLaunch, nq - q0);
@@ -469,7 +472,8 @@ int qf_forest_create(const qf_forest_desc* d, qf_forest** out) {
     {   // locality buckets: leaf position inside tree 0, at most kMaxKeyBins of them
         const int64_t n0 = d->tree_offsets[1] - d->tree_offsets[0];
         int shift = 0;
-        while (((n0 - 1) >> shift) >= kMaxKeyBins) ++shift;
+        while (((n0 - 1) >> shift) >= qf::kKeyBins) ++shift;
+        f->root0 = static_cast<uint32_t>(d->tree_offsets[0]);
         f->key_shift = shift;
         f->key_bins = static_cast<int>(((n0 - 1) >> shift) + 1);
     }
@@ -601,7 +605,7 @@ int qf_forest_apply(qf_forest* f, const float* X, int64_t n, int64_t ldx, int64_
         const int* order = nullptr;
         rc = build_locality_order(f, X + r0 * ldx, rows, ldx, pl, static_cast<unsigned char*>(ws), st, &order);
         if (rc != QF_OK) return rc;
-        rc = launch_apply<qf::APPLY_EMIT_NODE>(f, X + r0 * ldx, rows, ldx, idx, order, 0, f->T, nullptr, st);
+        rc = launch_apply<qf::APPLY_EMIT_NODE>(f, X + r0 * ldx, rows, ldx, idx, order, 0, f->T, st);
         if (rc != QF_OK) return rc;
         const int64_t total = rows * f->T;
         const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, f->sm_count * 16));
@@ -632,7 +636,7 @@ int qf_forest_predict_mean(qf_forest* f, const float* X, int64_t n, int64_t ldx,
         const int* order = nullptr;
         rc = build_locality_order(f, X + r0 * ldx, rows, ldx, pl, static_cast<unsigned char*>(ws), st, &order);
         if (rc != QF_OK) return rc;
-        rc = launch_apply<qf::APPLY_EMIT_NODE>(f, X + r0 * ldx, rows, ldx, idx, order, 0, f->T, nullptr, st);
+        rc = launch_apply<qf::APPLY_EMIT_NODE>(f, X + r0 * ldx, rows, ldx, idx, order, 0, f->T, st);
         if (rc != QF_OK) return rc;
         qf::mean_kernel<<<static_cast<unsigned>((rows + 127) / 128), 128, 0, st>>>(idx, rows, f->T, f->d_values,
                                                                                    out + r0);

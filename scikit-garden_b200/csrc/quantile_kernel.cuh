@@ -337,7 +337,6 @@ quantile_bucket_kernel(const QuantileParams p, const __grid_constant__ QuantileL
     uint32_t* offs = cnt + NB + 8;                                 // [T + 1]
     uint32_t* starts = offs + (p.T + 1);                           // [T]
     __shared__ uint32_t s_red[2 * NW];
-    __shared__ uint32_t s_part[kBucketEPT * NW + 1];
     __shared__ int s_m;
 
     const int tid = threadIdx.x;
@@ -385,25 +384,51 @@ quantile_bucket_kernel(const QuantileParams p, const __grid_constant__ QuantileL
         continue;
     }
 
-    // 1. gather: 8 lanes per leaf; rank window of the row
+    // 1. gather: 8 lanes per leaf, 4 leaves in flight per lane group; rank window of the row
     uint32_t rmin, shift;
+    bool full;                                          // an entry holds the whole (rank - rmin)
     {
         uint32_t lo = 0xffffffffu, hi = 0u;
         const int group = tid >> 3, sub = tid & 7;
-        for (int t = group; t < p.T; t += THREADS / 8) {
-            const uint32_t o = offs[t], len = offs[t + 1] - o;
-            const uint2* __restrict__ src = p.members + starts[t];
-            for (uint32_t i = sub; i < len; i += 8) {
-                const uint2 e = __ldg(src + i);
-                rk[o + i] = e.x;
-                wt[o + i] = __uint_as_float(e.y);
-                lo = min(lo, e.x);
-                hi = max(hi, e.x);
+        constexpr int GROUPS = THREADS / 8;
+        for (int t0 = group; t0 < p.T; t0 += 4 * GROUPS) {
+            uint32_t o[4], len[4];
+            uint2 e[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int t = t0 + k * GROUPS;
+                o[k] = 0u;
+                len[k] = 0u;
+                if (t < p.T) {
+                    o[k] = offs[t];
+                    len[k] = offs[t + 1] - o[k];
+                    if (sub < len[k]) e[k] = __ldg(p.members + starts[t] + sub);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (sub < len[k]) {
+                    rk[o[k] + sub] = e[k].x;
+                    wt[o[k] + sub] = __uint_as_float(e[k].y);
+                    lo = min(lo, e[k].x);
+                    hi = max(hi, e[k].x);
+                }
+                if (len[k] > 8) {                       // long leaf lists: the rest, 8 entries per step
+                    const uint2* __restrict__ src = p.members + starts[t0 + k * GROUPS];
+                    for (uint32_t i = sub + 8; i < len[k]; i += 8) {
+                        const uint2 x = __ldg(src + i);
+                        rk[o[k] + i] = x.x;
+                        wt[o[k] + i] = __uint_as_float(x.y);
+                        lo = min(lo, x.x);
+                        hi = max(hi, x.x);
+                    }
+                }
             }
         }
         lo = __reduce_min_sync(0xffffffffu, lo);
         hi = __reduce_max_sync(0xffffffffu, hi);
         if (lane == 0) { s_red[warp] = lo; s_red[NW + warp] = hi; }
+        if (tid < 4 && P + tid < CAP) srt[P + tid] = 0xffffffffu;   // pad for the 128-bit reads of step 3
         __syncthreads();
         lo = 0xffffffffu;
         hi = 0u;
@@ -413,8 +438,9 @@ quantile_bucket_kernel(const QuantileParams p, const __grid_constant__ QuantileL
         const uint32_t range = hi - lo;
         const int bits = 32 - __clz(range);             // range < 2^bits
         shift = static_cast<uint32_t>(max(0, bits - LOG2NB));      // (range >> shift) < NB
+        full = bits + POSBITS <= 32;
     }
-    const uint32_t lowmask = (1u << shift) - 1u;
+    const uint32_t lowmask = full ? 0xffffffffu : ((1u << shift) - 1u);
 
     // 2a. bucket populations
     for (uint32_t i = tid; i < P; i += THREADS) atomicAdd(&cnt[(rk[i] - rmin) >> shift], 1u);
@@ -443,7 +469,9 @@ quantile_bucket_kernel(const QuantileParams p, const __grid_constant__ QuantileL
         reinterpret_cast<uint4*>(cnt)[2 * tid + 1] = o1;
     }
     __syncthreads();
-    // 2c. slots: afterwards cnt[b] is the END of bucket b (= start of bucket b + 1)
+    // 2c. slots: afterwards cnt[b] is the END of bucket b (= start of bucket b + 1).
+    //     entry = ((rank - rmin) << POSBITS) | pos when that fits 32 bits (`full`: entries of
+    //     different buckets compare like their buckets), else only the bits below the bucket
     for (uint32_t i = tid; i < P; i += THREADS) {
         const uint32_t d = rk[i] - rmin;
         const uint32_t slot = atomicAdd(&cnt[d >> shift], 1u);
@@ -451,7 +479,7 @@ quantile_bucket_kernel(const QuantileParams p, const __grid_constant__ QuantileL
     }
     __syncthreads();
 
-    // 3. order inside the buckets
+    // 3. order inside the buckets: count the smaller entries, 4 per shared-memory access
     {
         uint32_t key[kBucketEPT], dst[kBucketEPT];
 #pragma unroll
@@ -461,12 +489,25 @@ quantile_bucket_kernel(const QuantileParams p, const __grid_constant__ QuantileL
             dst[j] = 0xffffffffu;
             if (i < P) {
                 const uint32_t k = srt[i];
-                const uint32_t b = (rk[k & POSMASK] - rmin) >> shift;
+                const uint32_t b = full ? ((k >> POSBITS) >> shift) : ((rk[k & POSMASK] - rmin) >> shift);
                 const uint32_t lo = b ? cnt[b - 1] : 0u, hi = cnt[b];
+                const uint32_t lo4 = lo & ~3u;
                 uint32_t smaller = 0;
-                for (uint32_t u = lo; u < hi; ++u) smaller += (srt[u] < k) ? 1u : 0u;
+                if (full) {                             // entries before lo are smaller, entries from hi on larger
+                    for (uint32_t u = lo4; u < hi; u += 4) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(srt + u);
+                        smaller += (v.x < k) + (v.y < k) + (v.z < k) + (v.w < k);
+                    }
+                    dst[j] = lo4 + smaller;
+                } else {
+                    for (uint32_t u = lo4; u < hi; u += 4) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(srt + u);
+                        smaller += (u >= lo && u < hi && v.x < k) + (u + 1 >= lo && u + 1 < hi && v.y < k) +
+                                   (u + 2 >= lo && u + 2 < hi && v.z < k) + (u + 3 >= lo && u + 3 < hi && v.w < k);
+                    }
+                    dst[j] = lo + smaller;
+                }
                 key[j] = k;
-                dst[j] = lo + smaller;
             }
         }
         __syncthreads();
@@ -476,60 +517,79 @@ quantile_bucket_kernel(const QuantileParams p, const __grid_constant__ QuantileL
     }
     __syncthreads();
 
-    // 4. group heads sum their duplicates in tree order (ensemble.py:140), then compact
+    // 4. merge equal ranks in tree order (ensemble.py:140).  Thread t walks the entries
+    //    [16 t, 16 t + 16) of the sorted array; a group belongs to the thread that holds its
+    //    first entry, which follows it past the end of its chunk if need be, so that the
+    //    float32 additions happen in exactly the reference's order.
     {
-        uint32_t hr[kBucketEPT];
-        float hw[kBucketEPT];
-        uint32_t votes[kBucketEPT];
+        auto rank_of = [&](uint32_t entry) -> uint32_t {
+            return full ? (rmin + (entry >> POSBITS)) : rk[entry & POSMASK];
+        };
+        const uint32_t base = static_cast<uint32_t>(tid) * kBucketEPT;
+        uint32_t ent[kBucketEPT];
+#pragma unroll
+        for (int c = 0; c < kBucketEPT / 4; ++c) {
+            const uint4 v = *reinterpret_cast<const uint4*>(srt + base + 4 * c);
+            ent[4 * c + 0] = v.x; ent[4 * c + 1] = v.y; ent[4 * c + 2] = v.z; ent[4 * c + 3] = v.w;
+        }
+        uint32_t hr[kBucketEPT + 1];
+        float hw[kBucketEPT + 1];
+        uint32_t flags = 0;                             // bit j: slot j holds a finished group
+        uint32_t cur = (base > 0 && base < P) ? rank_of(srt[base - 1]) : 0xffffffffu;
+        float W = 0.0f;
+        bool open = false;                              // the group being accumulated is this thread's
 #pragma unroll
         for (int j = 0; j < kBucketEPT; ++j) {
-            const uint32_t i = j * THREADS + tid;
-            uint32_t r = 0xffffffffu;
-            float W = 0.0f;
-            if (i < P) {
-                const uint32_t pos = srt[i] & POSMASK;
-                r = rk[pos];
-                W = wt[pos];
-            }
-            uint32_t prev = __shfl_up_sync(0xffffffffu, r, 1);
-            if (lane == 0) prev = (i > 0 && i < P) ? rk[srt[i - 1] & POSMASK] : 0xfffffffeu;
-            bool head = (i < P) && (r != prev);
-            if (head) {
-                for (uint32_t u = i + 1; u < P; ++u) {
-                    const uint32_t pu = srt[u] & POSMASK;
-                    if (rk[pu] != r) break;
-                    W = __fadd_rn(W, wt[pu]);
+            hr[j] = 0u;
+            hw[j] = 0.0f;
+            if (base + j < P) {
+                const uint32_t r = rank_of(ent[j]);
+                const float w = wt[ent[j] & POSMASK];
+                if (r != cur) {
+                    if (open && W != 0.0f) { hr[j] = cur; hw[j] = W; flags |= 1u << j; }   // utils.py:55-57
+                    cur = r;
+                    W = w;
+                    open = true;
+                } else if (open) {
+                    W = __fadd_rn(W, w);
                 }
-                head = W != 0.0f;                       // utils.py:55-57
             }
-            hr[j] = r;
-            hw[j] = W;
-            votes[j] = __ballot_sync(0xffffffffu, head);
-            if (lane == 0) s_part[j * NW + warp] = __popc(votes[j]);
         }
+        hr[kBucketEPT] = 0u;
+        hw[kBucketEPT] = 0.0f;
+        if (open) {
+            for (uint32_t u = base + kBucketEPT; u < P; ++u) {
+                const uint32_t en = srt[u];
+                if (rank_of(en) != cur) break;
+                W = __fadd_rn(W, wt[en & POSMASK]);
+            }
+            if (W != 0.0f) { hr[kBucketEPT] = cur; hw[kBucketEPT] = W; flags |= 1u << kBucketEPT; }
+        }
+        // compaction: exclusive scan of the per-thread group counts (blocked order = rank order)
+        const uint32_t mine = __popc(flags);
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += u;
+        }
+        if (lane == 31) s_red[warp] = incl;
         __syncthreads();                                // every read of rk / wt / srt is done
-        if (warp == 0) {                                // exclusive scan of the EPT * NW partial counts
-            uint32_t carry = 0;
-            for (int base = 0; base < kBucketEPT * NW; base += 32) {
-                const uint32_t v = s_part[base + lane];
-                uint32_t incl = v;
+        uint32_t c = incl - mine;
+        uint32_t total = 0;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += u;
-                }
-                s_part[base + lane] = carry + incl - v;
-                carry += __shfl_sync(0xffffffffu, incl, 31);
-            }
-            if (lane == 0) s_m = static_cast<int>(carry);
+        for (int w = 0; w < NW; ++w) {
+            const uint32_t v = s_red[w];
+            c += (w < warp) ? v : 0u;
+            total += v;
         }
-        __syncthreads();
+        if (tid == 0) s_m = static_cast<int>(total);
 #pragma unroll
-        for (int j = 0; j < kBucketEPT; ++j) {
-            if (votes[j] & (1u << lane)) {
-                const uint32_t c = s_part[j * NW + warp] + __popc(votes[j] & ((1u << lane) - 1u));
+        for (int j = 0; j <= kBucketEPT; ++j) {
+            if (flags & (1u << j)) {
                 rk[c] = hr[j];
                 wt[c] = hw[j];
+                ++c;
             }
         }
     }
