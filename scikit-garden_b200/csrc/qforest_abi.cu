@@ -11,6 +11,7 @@
 #include "apply_kernel.cuh"
 #include "qf_internal.h"
 #include "quantile_kernel.cuh"
+#include "select_kernel.cuh"
 
 namespace qf {
 
@@ -322,12 +323,37 @@ int launch_bucket_kernel(int threads, unsigned grid, const qf::QuantileParams& q
     }
 }
 
+// QF_MODE_FAST: the selection kernel (select_kernel.cuh) in place of the sorting one
+int launch_select_kernel(int threads, unsigned grid, const qf::QuantileParams& qp, const qf::QuantileList& ql,
+                         int T, cudaStream_t st) {
+    const size_t smem = qf::select_kernel_smem(threads, T);
+    if (smem > 220 * 1024)
+        return qf::fail(QF_ERR_LIMIT, "predict_quantiles: n_estimators too large for shared memory");
+    int k = 0;                                          // weights of a row sum to <= T < 2^k
+    while ((int64_t(1) << k) < int64_t(T) + 1) ++k;
+    const float fx_scale = static_cast<float>(int64_t(1) << (31 - k));
+    auto run = [&](auto kernel) -> int {
+        int rc = set_smem(kernel, smem);
+        if (rc != QF_OK) return rc;
+        kernel<<<grid, threads, smem, st>>>(qp, ql, fx_scale);
+        return QF_OK;
+    };
+    switch (threads) {
+        case 64: return run(qf::quantile_select_kernel<64>);
+        case 128: return run(qf::quantile_select_kernel<128>);
+        case 256: return run(qf::quantile_select_kernel<256>);
+        default: return run(qf::quantile_select_kernel<512>);
+    }
+}
+
 // `pl` is the caller's carve-up of `ws` (made once for the largest chunk, so that the
 // zeroed dense scratch stays where the kernels expect it for every chunk).
 int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, const double* q_host,
                         int nq, double* out, int mode, const Plan& pl, void* ws, int64_t ws_bytes,
                         cudaStream_t st) {
-    (void)mode;  // QF_MODE_FAST currently runs the exact kernels (a superset of its contract)
+    // QF_MODE_FAST swaps the shared-memory sorting stages for histogram selection; the warp
+    // kernel (small member sets) and the dense fallback are exact in both modes
+    const bool select = mode == QF_MODE_FAST && nq <= qf::kSelectMaxQ;
     if (ws_bytes < pl.total || (!ws && pl.total > 0))
         return qf::fail(QF_ERR_WORKSPACE, "predict_quantiles: workspace too small");
     unsigned char* base = static_cast<unsigned char*>(ws);
@@ -400,7 +426,8 @@ int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, co
                                                   : static_cast<unsigned>(rows);
                 {
                     SpanTimer span(f, SPAN_QUANTILE, st);
-                    rc = launch_bucket_kernel(bucket_threads[b], grid, qp, ql, f->T, st);
+                    rc = select ? launch_select_kernel(bucket_threads[b], grid, qp, ql, f->T, st)
+                                : launch_bucket_kernel(bucket_threads[b], grid, qp, ql, f->T, st);
                 }
                 if (rc != QF_OK) return rc;
                 QF_CUDA_TRY(cudaGetLastError());

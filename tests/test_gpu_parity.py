@@ -218,6 +218,50 @@ def test_random_forests_bit_exact_vs_oracle(kind, bootstrap, msl, ties, depth):
     assert got.min() >= y32.min() and got.max() <= y32.max()
 
 
+@pytest.mark.parametrize("name", _golden.CASES)
+@pytest.mark.parametrize("warp_elems", [-1, 0])
+def test_fast_mode_against_reference_outputs(name, warp_elems):
+    # QF_MODE_FAST (histogram selection instead of the sort) against the reference's own
+    # outputs: 1e-4 relative (BASELINE.json north_star, float32 arithmetic), order
+    # statistics (q = 0 and q = 100) bit-exact
+    from skgarden_b200 import _native
+    g = _golden.load(name)
+    flat = _golden.flat_from_golden(g)
+    dev = _dev(flat, warp_elems=warp_elems)
+    X = _cuda(g.X_test)
+    scale = np.abs(g.y_train).max()
+    for lo in range(0, len(g.q), 7):                    # batches of <= 16 percentiles take the selection kernel
+        qs = g.q[lo:lo + 7]
+        got = dev.predict_quantiles(X, qs, mode=_native.QF_MODE_FAST).cpu().numpy().T
+        want = g.pred[lo:lo + 7]
+        assert_allclose(got, want, rtol=1e-4, atol=1e-4 * scale)
+        for k, q in enumerate(qs):
+            if q in (0.0, 100.0):
+                assert_array_equal(got[k], want[k])
+    dev.close()
+
+
+@pytest.mark.parametrize("kind,msl,depth,T", [("et", 20, None, 100), ("rf", 1, 7, 60), ("et", 5, None, 300)])
+def test_fast_mode_large_member_sets(kind, msl, depth, T):
+    # rows with thousands of members: the 128/256/512-thread selection kernels against the
+    # bit-exact sorting kernels on the same forest
+    import skgarden_b200 as sg
+    cls = sg.RandomForestQuantileRegressor if kind == "rf" else sg.ExtraTreesQuantileRegressor
+    rng = np.random.RandomState(11)
+    N, n, F = 20000, 3000, 10
+    X = rng.randn(N + n, F).astype(np.float32)
+    y = 3 * X[:, 0] + 2 * np.sin(3 * X[:, 1]) + X[:, 2] * X[:, 3] + rng.randn(N + n)
+    est = cls(n_estimators=T, random_state=2, min_samples_leaf=msl, max_depth=depth, n_jobs=-1).fit(X[:N], y[:N])
+    qs = [0, 1, 5, 25, 50, 75, 95, 99, 100]
+    exact = est.predict(X[N:], quantile=qs)
+    est.mode = "fast"
+    fast = est.predict(X[N:], quantile=qs)
+    assert_allclose(fast, exact, rtol=1e-4, atol=1e-4 * np.abs(y).max())
+    assert_array_equal(fast[:, [0, -1]], exact[:, [0, -1]])
+    print("fast vs exact: max abs diff %.3g (|y| max %.3g), members/row %.0f" % (
+        np.abs(fast - exact).max(), np.abs(y).max(), est._flat.expected_row_members))
+
+
 def test_fast_mode_within_tolerance():
     import skgarden_b200 as sg
     rng = np.random.RandomState(5)

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--rows", type=int, default=0, help="test rows (default: the config's)")
     ap.add_argument("--grid", default="default", help="default | json list of option dicts")
+    ap.add_argument("--mode", default="exact", choices=["exact", "fast"])
     args = ap.parse_args()
     import torch
     import skgarden_b200 as sg
@@ -50,6 +51,8 @@ def main():
         grid += [dict(warp_elems=w) for w in (0, 4, 8)]
     else:
         grid = json.loads(args.grid)
+    from skgarden_b200 import _native
+    mode = _native.QF_MODE_FAST if args.mode == "fast" else _native.QF_MODE_EXACT
     ref_out = None
     results = []
     for opts in grid:
@@ -65,7 +68,7 @@ def main():
                 flush.zero_()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                out = dev.predict_quantiles(X, qs, out=out)
+                out = dev.predict_quantiles(X, qs, mode=mode, out=out)
                 e1.record()
                 a, q = dev.last_timings()
                 torch.cuda.synchronize()
@@ -77,7 +80,7 @@ def main():
                 flush.zero_()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                out = dev.predict_quantiles(X, qs, out=out)
+                out = dev.predict_quantiles(X, qs, mode=mode, out=out)
                 e1.record()
                 torch.cuda.synchronize()
                 t_ms.append(e0.elapsed_time(e1))
@@ -86,6 +89,14 @@ def main():
             continue
         if ref_out is None:
             ref_out = out.clone()
+            if args.mode == "fast":                      # deviation of the selection kernel from the sorting one
+                for k, v in full.items():
+                    dev.set_option(k, v)
+                ex = dev.predict_quantiles(X, qs, mode=_native.QF_MODE_EXACT)
+                torch.cuda.synchronize()
+                diff = (ex - ref_out).abs()
+                print("fast vs exact: max abs diff %.3g, max rel diff %.3g, |value| max %.3g" % (
+                    float(diff.max()), float((diff / ex.abs().clamp_min(1e-3)).max()), float(ex.abs().max())), flush=True)
         ok = bool(torch.equal(out, ref_out))
         r = dict(opts=opts, apply_ms=float(np.median(a_ms[1:])), quantile_ms=float(np.median(q_ms[1:])),
                  total_ms=float(np.median(t_ms[1:])), same=ok)
