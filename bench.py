@@ -207,45 +207,6 @@ def load_traffic(config):
     return {}
 
 
-def broadcast_flat(flat, rank, device):
-    """Rank 0 -> all: the flattened forest over NCCL (NVLink), as raw device buffers."""
-    import torch
-    import torch.distributed as dist
-    from skgarden_b200.flatten import FlatForest
-    names = ["nodes", "tree_offsets", "node_ids", "members", "member_offsets", "y_sorted",
-             "leaf_values", "sorter"]
-    meta = [None]
-    if rank == 0:
-        meta[0] = dict(
-            scalars=dict(n_trees=flat.n_trees, n_features=flat.n_features, feature_bits=flat.feature_bits,
-                         n_train=flat.n_train, max_row_members=flat.max_row_members,
-                         expected_row_members=flat.expected_row_members, max_depth=flat.max_depth),
-            arrays={k: (None if getattr(flat, k) is None else (getattr(flat, k).dtype.str, getattr(flat, k).shape))
-                    for k in names})
-    dist.broadcast_object_list(meta, src=0)
-    meta = meta[0]
-    out = {}
-    for k in names:
-        spec = meta["arrays"][k]
-        if spec is None:
-            out[k] = None
-            continue
-        dtype, shape = np.dtype(spec[0]), tuple(spec[1])
-        nbytes = int(np.prod(shape)) * dtype.itemsize
-        if rank == 0:
-            buf = torch.from_numpy(np.ascontiguousarray(getattr(flat, k)).view(np.uint8).reshape(-1)).to(device)
-        else:
-            buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        dist.broadcast(buf, src=0)
-        out[k] = getattr(flat, k) if rank == 0 else buf.cpu().numpy().view(dtype).reshape(shape)
-        del buf
-    if rank == 0:
-        return flat
-    return FlatForest(nodes=out["nodes"], tree_offsets=out["tree_offsets"], node_ids=out["node_ids"],
-                      members=out["members"], member_offsets=out["member_offsets"], y_sorted=out["y_sorted"],
-                      leaf_values=out["leaf_values"], sorter=out["sorter"], **meta["scalars"])
-
-
 def run_b200(args, rank, world, local_rank):
     from skgarden_b200.datasets import CONFIGS, make_test
     cfg = CONFIGS[args.config]
@@ -273,6 +234,7 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
+        from skgarden_b200.sharding import broadcast_flat
         flat = broadcast_flat(flat, rank, device)
     import skgarden_b200 as sg
     from skgarden_b200 import _native
@@ -356,7 +318,7 @@ def run_b200(args, rank, world, local_rank):
         peak, peak_src = load_peaks()
         traffic = load_traffic(args.config)
         Q = len(qs)
-        bytes_k2 = float(8 * T * n + 8 * P_rows.sum() + 16 * Q * n)        # DESIGN.md: K2 bytes/row
+        bytes_k2 = float(8 * T * n + 8 * P_rows.sum() + 16 * Q * n)        # DESIGN.md section 5: K2 bytes/row
         bytes_k1 = float(4 * n * F + 8 * n * T + 8 * flat.n_nodes)         # K1 bytes/launch
         k1_ms, k2_ms = apply_ms / args.steps, quant_ms / args.steps
 
@@ -366,8 +328,12 @@ def run_b200(args, rank, world, local_rank):
                     "frac": round(ach / peak, 4), "traffic": traffic.get(name), "peak_source": peak_src,
                     "algorithmic_bytes": nbytes, "ms_per_launch": round(ms, 4)}
 
+        plan = dev.plan(n)                                                  # which kernels the library ran
+        k2_name = ("quantile_warp_kernel<%d>" % plan["warp_elems"]) if plan["warp_elems"] else (
+            "%s<%d>" % ("quantile_select_kernel" if (args.mode == "fast" and Q <= 16) else "quantile_bucket_kernel",
+                        plan["s1_threads"]))
         r1 = roof("apply_kernel", bytes_k1, k1_ms)
-        r2 = roof("quantile_cta_kernel", bytes_k2, k2_ms)
+        r2 = roof(k2_name, bytes_k2, k2_ms)
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
@@ -382,8 +348,9 @@ def run_b200(args, rank, world, local_rank):
                     "api": "qf_forest_predict_quantiles_host (pinned host X -> host result)"},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": r1 if k1_ms >= k2_ms else r2,
-            "roofline_kernels": {"apply_kernel": r1, "quantile_cta_kernel": r2},
-            "kernel_ms": {"apply": round(k1_ms, 4), "quantile": round(k2_ms, 4)},
+            "roofline_kernels": {"apply_kernel": r1, k2_name: r2},
+            "kernel_ms": {"apply": round(k1_ms, 4), "quantile": round(k2_ms, 4),
+                          "locality_order_and_gaps": round(max(0.0, ms_per_step - k1_ms - k2_ms), 4)},
             "clocks": clock_info,
         }
         if cpu_baseline is not None:

@@ -163,6 +163,13 @@ int qf_forest_predict_quantiles_host(qf_forest* f, const float* X_host, int64_t 
                                      int64_t ldx, const double* q_host, int32_t n_quantiles,
                                      double* out_host, int32_t mode, int64_t chunk_rows);
 
+/* Which kernels qf_forest_predict_quantiles runs for a call over n_rows rows (for bench
+ * accounting and tests).  out[8] = {rows per chunk, keys per lane of the warp kernel (0 =
+ * not used), threads of the first shared-memory stage (0 = not used), its member limit,
+ * member limit of the 512-thread stage (0 = not used), dense fallback present (0/1), rows
+ * walked in locality order (0/1), 0}. */
+int qf_forest_plan(const qf_forest* f, int64_t n_rows, int32_t* out);
+
 /* Per-call counters of the most recent predict/apply call on this handle (for bench
  * accounting): number of kernel launches issued and rows that overflowed the
  * in-shared-memory path into the dense fallback (valid after the stream is synced). */

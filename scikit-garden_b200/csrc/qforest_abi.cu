@@ -2,6 +2,7 @@
 // host-buffer end-to-end path.  All compute is in the kernels of apply_kernel.cuh and
 // quantile_kernel.cuh; there is no CPU fallback anywhere in this file.
 #include <algorithm>
+#include <climits>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -559,6 +560,20 @@ int64_t qf_forest_workspace_bytes(const qf_forest* f, int64_t n_rows, int32_t n_
     (void)n_quantiles;
     if (!f || n_rows < 0) return 0;
     return make_plan(f, n_rows).total;
+}
+
+int qf_forest_plan(const qf_forest* f, int64_t n_rows, int32_t* out) {
+    if (!f || !out || n_rows < 0) return qf::fail(QF_ERR_INVALID, "qf_forest_plan: bad argument");
+    const Plan pl = make_plan(f, n_rows);
+    out[0] = static_cast<int32_t>(std::min<int64_t>(pl.chunk_rows, INT32_MAX));
+    out[1] = pl.warp_elems;
+    out[2] = pl.s1_threads;
+    out[3] = pl.s1_limit;
+    out[4] = pl.s2_limit;
+    out[5] = pl.dense_needed ? 1 : 0;
+    out[6] = pl.sort_rows ? 1 : 0;
+    out[7] = 0;
+    return QF_OK;
 }
 
 int qf_forest_last_launches(const qf_forest* f) { return f ? f->launches : 0; }

@@ -87,6 +87,13 @@ class DeviceForest:
     def last_launches(self) -> int:
         return int(self._lib.qf_forest_last_launches(self._h))
 
+    def plan(self, n_rows: int) -> dict:
+        """Which kernels a call over ``n_rows`` rows runs (qf_forest_plan)."""
+        vals = (C.c_int32 * 8)()
+        _native.check(self._lib.qf_forest_plan(self._h, int(n_rows), vals))
+        keys = ("chunk_rows", "warp_elems", "s1_threads", "s1_limit", "s2_limit", "dense", "sort_rows", "reserved")
+        return dict(zip(keys, [int(v) for v in vals]))
+
     def last_timings(self):
         """(apply_ms, quantile_ms) of the most recent call; needs set_option("profile", 1)."""
         a, q = C.c_double(0.0), C.c_double(0.0)
