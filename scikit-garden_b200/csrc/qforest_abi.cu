@@ -71,6 +71,7 @@ struct qf_forest {
     uint32_t root0 = 0;
     int64_t rows_per_chunk = 131072;
     int cta_capacity = 0;         // cap on the members per row of the first bucket stage (0 = its capacity)
+    int select_bits = qf::kSelectL2Bits;   // log2 refinement slots of the selection kernel (tests lower it)
     int cta2_capacity = 8192;     // same for the 512-thread overflow stage (0 = stage not used)
     int warp_elems = -1;          // warp kernel: keys per lane (2, 4, 8), 0 = never, -1 = auto
     int dense_ctas = 0;           // 0 = auto
@@ -326,7 +327,7 @@ int launch_bucket_kernel(int threads, unsigned grid, const qf::QuantileParams& q
 
 // QF_MODE_FAST: the selection kernel (select_kernel.cuh) in place of the sorting one
 int launch_select_kernel(int threads, unsigned grid, const qf::QuantileParams& qp, const qf::QuantileList& ql,
-                         int T, cudaStream_t st) {
+                         int T, int sel_bits, cudaStream_t st) {
     const size_t smem = qf::select_kernel_smem(threads, T);
     if (smem > 220 * 1024)
         return qf::fail(QF_ERR_LIMIT, "predict_quantiles: n_estimators too large for shared memory");
@@ -336,7 +337,7 @@ int launch_select_kernel(int threads, unsigned grid, const qf::QuantileParams& q
     auto run = [&](auto kernel) -> int {
         int rc = set_smem(kernel, smem);
         if (rc != QF_OK) return rc;
-        kernel<<<grid, threads, smem, st>>>(qp, ql, fx_scale);
+        kernel<<<grid, threads, smem, st>>>(qp, ql, fx_scale, sel_bits);
         return QF_OK;
     };
     switch (threads) {
@@ -427,7 +428,7 @@ int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, co
                                                   : static_cast<unsigned>(rows);
                 {
                     SpanTimer span(f, SPAN_QUANTILE, st);
-                    rc = select ? launch_select_kernel(bucket_threads[b], grid, qp, ql, f->T, st)
+                    rc = select ? launch_select_kernel(bucket_threads[b], grid, qp, ql, f->T, f->select_bits, st)
                                 : launch_bucket_kernel(bucket_threads[b], grid, qp, ql, f->T, st);
                 }
                 if (rc != QF_OK) return rc;
@@ -616,6 +617,10 @@ int qf_forest_set_option(qf_forest* f, const char* key, int64_t value) {
     } else if (k == "cta2_capacity") {
         if (value < 0 || value > 8192) return qf::fail(QF_ERR_INVALID, "cta2_capacity must be in [0, 8192]");
         f->cta2_capacity = static_cast<int>(value);
+    } else if (k == "select_bits") {
+        if (value < 1 || value > qf::kSelectL2Bits)
+            return qf::fail(QF_ERR_INVALID, "select_bits must be in [1, 10]");
+        f->select_bits = static_cast<int>(value);
     } else if (k == "warp_elems") {
         if (value != -1 && value != 0 && value != 2 && value != 4 && value != 8)
             return qf::fail(QF_ERR_INVALID, "warp_elems must be -1 (auto), 0 (off), 2, 4 or 8");

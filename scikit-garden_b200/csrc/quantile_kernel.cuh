@@ -289,6 +289,94 @@ quantile_warp_kernel(const QuantileParams p, const __grid_constant__ QuantileLis
 }
 
 // ---------------------------------------------------------------------------------------
+// Shared by the CTA-per-row kernels: exclusive offsets of the row's T leaf lists and the
+// gather of their members into shared memory in tree order.
+// ---------------------------------------------------------------------------------------
+// offs[0..T] <- exclusive prefix of the member counts, starts[t] <- first member of leaf t.
+// Contains block barriers; returns the number of members of the row.
+template <int THREADS>
+__device__ __forceinline__ uint32_t row_leaf_offsets(const uint2* __restrict__ seg, int T, uint32_t* offs,
+                                                     uint32_t* starts) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int t = tid; t < T; t += THREADS) {
+        const uint2 s = seg[t];
+        starts[t] = s.x;
+        offs[t + 1] = s.y;
+    }
+    if (tid == 0) offs[0] = 0;
+    __syncthreads();
+    if (tid < 32) {
+        uint32_t carry = 0;
+        for (int base = 0; base < T; base += 32) {
+            const int t = base + lane;
+            uint32_t v = (t < T) ? offs[t + 1] : 0u;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, v, d);
+                if (lane >= d) v += u;
+            }
+            v += carry;
+            if (t < T) offs[t + 1] = v;
+            carry = __shfl_sync(0xffffffffu, v, 31);
+        }
+    }
+    __syncthreads();
+    return offs[T];
+}
+
+// 4 lanes per leaf, two 8-byte entries per lane and two leaves in flight (4 loads
+// outstanding per lane); store(pos, rank, weight bits) is called once per member, pos =
+// position in tree order.  lo / hi: running min / max of the ranks this thread saw.
+template <int THREADS, typename Store>
+__device__ __forceinline__ void gather_members(const uint2* __restrict__ members, int T,
+                                               const uint32_t* __restrict__ offs,
+                                               const uint32_t* __restrict__ starts, uint32_t& lo,
+                                               uint32_t& hi, Store store) {
+    constexpr int GROUPS = THREADS / 4;
+    const int group = threadIdx.x >> 2;
+    const uint32_t sub = threadIdx.x & 3;
+    for (int t0 = group; t0 < T; t0 += 2 * GROUPS) {
+        uint32_t o[2], len[2];
+        uint2 e0[2], e1[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int t = t0 + k * GROUPS;
+            o[k] = 0u;
+            len[k] = 0u;
+            if (t < T) {
+                o[k] = offs[t];
+                len[k] = offs[t + 1] - o[k];
+                const uint2* __restrict__ src = members + starts[t];
+                if (sub < len[k]) e0[k] = __ldg(src + sub);
+                if (sub + 4 < len[k]) e1[k] = __ldg(src + sub + 4);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (sub < len[k]) {
+                store(o[k] + sub, e0[k].x, e0[k].y);
+                lo = min(lo, e0[k].x);
+                hi = max(hi, e0[k].x);
+            }
+            if (sub + 4 < len[k]) {
+                store(o[k] + sub + 4, e1[k].x, e1[k].y);
+                lo = min(lo, e1[k].x);
+                hi = max(hi, e1[k].x);
+            }
+            if (len[k] > 8) {                           // long leaf lists: the rest, 4 entries per step
+                const uint2* __restrict__ src = members + starts[t0 + k * GROUPS];
+                for (uint32_t i = sub + 8; i < len[k]; i += 4) {
+                    const uint2 x = __ldg(src + i);
+                    store(o[k] + i, x.x, x.y);
+                    lo = min(lo, x.x);
+                    hi = max(hi, x.x);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // CTA-per-row kernel for larger member sets (P <= 16 * THREADS): bucket sort in shared
 // memory, no O(P log^2 P) network.
 //
@@ -349,31 +437,8 @@ quantile_bucket_kernel(const QuantileParams p, const __grid_constant__ QuantileL
     __syncthreads();                                    // shared memory reused from the previous row
 
     // 0. member counts of the row's leaves -> exclusive offsets (tree order)
-    for (int t = tid; t < p.T; t += THREADS) {
-        const uint2 s = seg[t];
-        starts[t] = s.x;
-        offs[t + 1] = s.y;
-    }
-    if (tid == 0) offs[0] = 0;
     for (int i = tid; i < NB + 8; i += THREADS) cnt[i] = 0u;
-    __syncthreads();
-    if (tid < 32) {
-        uint32_t carry = 0;
-        for (int base = 0; base < p.T; base += 32) {
-            const int t = base + lane;
-            uint32_t v = (t < p.T) ? offs[t + 1] : 0u;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t u = __shfl_up_sync(0xffffffffu, v, d);
-                if (lane >= d) v += u;
-            }
-            v += carry;
-            if (t < p.T) offs[t + 1] = v;
-            carry = __shfl_sync(0xffffffffu, v, 31);
-        }
-    }
-    __syncthreads();
-    const uint32_t P = offs[p.T];
+    const uint32_t P = row_leaf_offsets<THREADS>(seg, p.T, offs, starts);
     if (P > static_cast<uint32_t>(min(p.cap, CAP))) {   // too many members for this kernel
         if (tid == 0) p.overflow_rows[atomicAdd(p.overflow_count, 1)] = static_cast<int>(row);
         continue;
@@ -384,47 +449,16 @@ quantile_bucket_kernel(const QuantileParams p, const __grid_constant__ QuantileL
         continue;
     }
 
-    // 1. gather: 8 lanes per leaf, 4 leaves in flight per lane group; rank window of the row
+    // 1. gather (tree order); rank window of the row
     uint32_t rmin, shift;
     bool full;                                          // an entry holds the whole (rank - rmin)
     {
         uint32_t lo = 0xffffffffu, hi = 0u;
-        const int group = tid >> 3, sub = tid & 7;
-        constexpr int GROUPS = THREADS / 8;
-        for (int t0 = group; t0 < p.T; t0 += 4 * GROUPS) {
-            uint32_t o[4], len[4];
-            uint2 e[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int t = t0 + k * GROUPS;
-                o[k] = 0u;
-                len[k] = 0u;
-                if (t < p.T) {
-                    o[k] = offs[t];
-                    len[k] = offs[t + 1] - o[k];
-                    if (sub < len[k]) e[k] = __ldg(p.members + starts[t] + sub);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (sub < len[k]) {
-                    rk[o[k] + sub] = e[k].x;
-                    wt[o[k] + sub] = __uint_as_float(e[k].y);
-                    lo = min(lo, e[k].x);
-                    hi = max(hi, e[k].x);
-                }
-                if (len[k] > 8) {                       // long leaf lists: the rest, 8 entries per step
-                    const uint2* __restrict__ src = p.members + starts[t0 + k * GROUPS];
-                    for (uint32_t i = sub + 8; i < len[k]; i += 8) {
-                        const uint2 x = __ldg(src + i);
-                        rk[o[k] + i] = x.x;
-                        wt[o[k] + i] = __uint_as_float(x.y);
-                        lo = min(lo, x.x);
-                        hi = max(hi, x.x);
-                    }
-                }
-            }
-        }
+        gather_members<THREADS>(p.members, p.T, offs, starts, lo, hi,
+                                [&](uint32_t pos, uint32_t rank, uint32_t wbits) {
+                                    rk[pos] = rank;
+                                    wt[pos] = __uint_as_float(wbits);
+                                });
         lo = __reduce_min_sync(0xffffffffu, lo);
         hi = __reduce_max_sync(0xffffffffu, hi);
         if (lane == 0) { s_red[warp] = lo; s_red[NW + warp] = hi; }

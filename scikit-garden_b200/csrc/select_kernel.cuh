@@ -14,13 +14,16 @@
 //      point (scale 2^31 / next_pow2(T + 1): the weights of one leaf sum to 1, so a row's
 //      total is <= T), which makes every accumulation an exact integer atomic whatever the
 //      order -- duplicates of a training sample merge by landing in the same slot
-//   2. level 1: weight histogram over NB = 8 * THREADS buckets of the row's rank window,
-//      block scan, per q binary search for the bucket that holds e
-//   3. refinement: weight histogram of that bucket alone at 1024 slots per q, repeated until
-//      a slot is a single rank (one level for N <= 2M training rows); the same pass tracks
-//      the nearest ranks on either side of the window
-//   4. e, its neighbours inside the window (else the tracked outside ranks, whose merged
-//      weights one more pass collects) -> utils.py:72-81 in float32
+//   2. level 1: per bucket of the row's rank window (NB <= 2048 buckets) the weight, the
+//      largest and the smallest rank (three integer atomics per member); block scan; per q a
+//      binary search for the bucket that holds e, and the nearest rank in the non-empty
+//      buckets before and after it
+//   3. refinement: weight histogram of that bucket alone at 2^sel_bits slots per q, repeated
+//      until a slot is a single rank (one level when the bucket spans <= 1024 ranks, i.e. for
+//      rank windows up to 2M); the same pass collects the merged weights of the two outside
+//      neighbours.  (More levels: the neighbours are tracked as running max / min of the
+//      ranks outside the final window and their weights collected by one more pass.)
+//   4. e, its neighbours inside the window (else the outside ones) -> utils.py:72-81 in float32
 //
 // Handles up to kSelectQB percentiles per pass over the shared-memory resident members.
 #pragma once
@@ -36,40 +39,51 @@ constexpr int kSelectL2Bits = 10;
 constexpr int kSelectL2Slots = 1 << kSelectL2Bits;      // refinement slots per percentile
 constexpr int kSelectMaxQ = 16;                         // above this the sorting kernel is cheaper
 
-__host__ __device__ inline size_t select_kernel_smem(int threads, int T) {
-    const size_t cap = static_cast<size_t>(bucket_kernel_capacity(threads));
-    return cap * 8 + (cap / 2 + 8) * 4 + static_cast<size_t>(kSelectQB) * kSelectL2Slots * 4 +
-           static_cast<size_t>(2 * T + 1) * 4 + 16;
+__host__ __device__ constexpr int select_kernel_buckets(int threads) {
+    return threads * 8 < 2048 ? threads * 8 : 2048;
 }
 
+__host__ __device__ inline size_t select_kernel_smem(int threads, int T) {
+    const size_t cap = static_cast<size_t>(bucket_kernel_capacity(threads));
+    return cap * 8 + (static_cast<size_t>(select_kernel_buckets(threads)) + 8) * 4 +
+           static_cast<size_t>(kSelectQB) * kSelectL2Slots * 4 + static_cast<size_t>(2 * T + 1) * 4 + 16;
+}
+
+// sel_bits (<= kSelectL2Bits): log2 of the refinement slots actually used; smaller values
+// force several refinement levels on small forests (tests)
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, (THREADS == 64) ? 8 : (THREADS <= 256) ? 768 / THREADS : 1)
-quantile_select_kernel(const QuantileParams p, const __grid_constant__ QuantileList ql, const float fx_scale) {
+quantile_select_kernel(const QuantileParams p, const __grid_constant__ QuantileList ql, const float fx_scale,
+                       const int sel_bits) {
     constexpr int CAP = THREADS * kBucketEPT;
-    constexpr int NB = CAP / 2;                         // level-1 buckets, 8 per thread
+    constexpr int NB = select_kernel_buckets(THREADS);  // level-1 buckets
+    constexpr int BPT = NB / THREADS;                   // buckets scanned per thread (8 or 4)
     constexpr int NW = THREADS / 32;
-    constexpr int LOG2NB = (THREADS == 64) ? 9 : (THREADS == 128) ? 10 : (THREADS == 256) ? 11 : 12;
+    constexpr int LOG2NB = (THREADS == 64) ? 9 : (THREADS == 128) ? 10 : 11;
     constexpr int QB = kSelectQB;
     constexpr int L2S = kSelectL2Slots;
     constexpr int SPT = QB * L2S / THREADS;             // refinement slots scanned per thread
     constexpr uint32_t NONE = 0xffffffffu;
     static_assert(THREADS == 64 || THREADS == 128 || THREADS == 256 || THREADS == 512, "unsupported block size");
-    static_assert((1 << LOG2NB) == NB && L2S % SPT == 0 && SPT % 4 == 0, "layout");
+    static_assert((1 << LOG2NB) == NB && L2S % SPT == 0 && SPT % 4 == 0 && BPT % 4 == 0 && 2 * NB <= QB * L2S, "layout");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* rk = reinterpret_cast<uint32_t*>(smem_raw);          // rank by pos
     uint32_t* wfx = rk + CAP;                                      // fixed-point weight by pos
-    uint32_t* h1 = wfx + CAP;                                      // [NB + 8] level-1 histogram -> inclusive prefix
-    uint32_t* l2 = h1 + NB + 8;                                    // [QB][L2S]
+    uint32_t* h1 = wfx + CAP;                                      // [NB + 8] level-1 weights -> inclusive prefix
+    uint32_t* l2 = h1 + NB + 8;                                    // [QB][L2S]; during level 1: bmx[NB] | bmn[NB]
     uint32_t* offs = l2 + QB * L2S;                                // [T + 1]
     uint32_t* starts = offs + (p.T + 1);                           // [T]
+    uint32_t* bmx = l2;                                            // largest (rank - rmin) + 1 per bucket
+    uint32_t* bmn = l2 + NB;                                       // smallest rank - rmin per bucket
     __shared__ uint32_t s_red[2 * NW];
-    __shared__ uint32_t s_wlo[QB], s_base[QB], s_tau[QB];          // window start (rank - rmin), weight before it, target
-    __shared__ uint32_t s_pout[QB], s_sout[QB];                    // nearest (rank - rmin) + 1 below / rank - rmin above the window
-    __shared__ uint32_t s_e[QB], s_We[QB], s_Ce[QB];               // final slot of e, its merged weight, running weight
-    __shared__ uint32_t s_pin[QB], s_sin[QB];                      // neighbours of e inside the window: slot + 1 / slot
-    __shared__ uint32_t s_Wp[QB], s_Ws[QB];                        // merged weights of the outside neighbours
-    __shared__ uint32_t s_seg[QB];
+    // per percentile of the call: target weight, window start (rank - rmin), weight before the
+    // window, nearest (rank - rmin) + 1 below / rank - rmin above the window
+    __shared__ uint32_t s_tau[kSelectMaxQ], s_wlo[kSelectMaxQ], s_base[kSelectMaxQ];
+    __shared__ uint32_t s_pout[kSelectMaxQ], s_sout[kSelectMaxQ];
+    // per percentile of the batch: final slot of e, its merged weight, running weight;
+    // neighbours of e inside the window (slot + 1 / slot); merged weights of the outside ones
+    __shared__ uint32_t s_e[QB], s_We[QB], s_Ce[QB], s_pin[QB], s_sin[QB], s_Wp[QB], s_Ws[QB], s_seg[QB];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -81,31 +95,9 @@ quantile_select_kernel(const QuantileParams p, const __grid_constant__ QuantileL
     __syncthreads();                                    // shared memory reused from the previous row
 
     // 0. member counts of the row's leaves -> exclusive offsets (tree order)
-    for (int t = tid; t < p.T; t += THREADS) {
-        const uint2 s = seg[t];
-        starts[t] = s.x;
-        offs[t + 1] = s.y;
-    }
-    if (tid == 0) offs[0] = 0;
     for (int i = tid; i < NB + 8; i += THREADS) h1[i] = 0u;
-    __syncthreads();
-    if (tid < 32) {
-        uint32_t carry = 0;
-        for (int base = 0; base < p.T; base += 32) {
-            const int t = base + lane;
-            uint32_t v = (t < p.T) ? offs[t + 1] : 0u;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t u = __shfl_up_sync(0xffffffffu, v, d);
-                if (lane >= d) v += u;
-            }
-            v += carry;
-            if (t < p.T) offs[t + 1] = v;
-            carry = __shfl_sync(0xffffffffu, v, 31);
-        }
-    }
-    __syncthreads();
-    const uint32_t P = offs[p.T];
+    for (int i = tid; i < NB; i += THREADS) { bmx[i] = 0u; bmn[i] = NONE; }
+    const uint32_t P = row_leaf_offsets<THREADS>(seg, p.T, offs, starts);
     if (P > static_cast<uint32_t>(min(p.cap, CAP))) {   // too many members for this kernel
         if (tid == 0) p.overflow_rows[atomicAdd(p.overflow_count, 1)] = static_cast<int>(row);
         continue;
@@ -116,47 +108,16 @@ quantile_select_kernel(const QuantileParams p, const __grid_constant__ QuantileL
         continue;
     }
 
-    // 1. gather: 8 lanes per leaf, 4 leaves in flight per lane group; rank window of the row
+    // 1. gather (tree order), weights to fixed point; rank window of the row
     uint32_t rmin;
     int shift1;
     {
         uint32_t lo = NONE, hi = 0u;
-        const int group = tid >> 3, sub = tid & 7;
-        constexpr int GROUPS = THREADS / 8;
-        for (int t0 = group; t0 < p.T; t0 += 4 * GROUPS) {
-            uint32_t o[4], len[4];
-            uint2 e[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int t = t0 + k * GROUPS;
-                o[k] = 0u;
-                len[k] = 0u;
-                if (t < p.T) {
-                    o[k] = offs[t];
-                    len[k] = offs[t + 1] - o[k];
-                    if (sub < len[k]) e[k] = __ldg(p.members + starts[t] + sub);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (sub < len[k]) {
-                    rk[o[k] + sub] = e[k].x;
-                    wfx[o[k] + sub] = __float2uint_rn(__fmul_rn(__uint_as_float(e[k].y), fx_scale));
-                    lo = min(lo, e[k].x);
-                    hi = max(hi, e[k].x);
-                }
-                if (len[k] > 8) {                       // long leaf lists: the rest, 8 entries per step
-                    const uint2* __restrict__ src = p.members + starts[t0 + k * GROUPS];
-                    for (uint32_t i = sub + 8; i < len[k]; i += 8) {
-                        const uint2 x = __ldg(src + i);
-                        rk[o[k] + i] = x.x;
-                        wfx[o[k] + i] = __float2uint_rn(__fmul_rn(__uint_as_float(x.y), fx_scale));
-                        lo = min(lo, x.x);
-                        hi = max(hi, x.x);
-                    }
-                }
-            }
-        }
+        gather_members<THREADS>(p.members, p.T, offs, starts, lo, hi,
+                                [&](uint32_t pos, uint32_t rank, uint32_t wbits) {
+                                    rk[pos] = rank;
+                                    wfx[pos] = __float2uint_rn(__fmul_rn(__uint_as_float(wbits), fx_scale));
+                                });
         lo = __reduce_min_sync(0xffffffffu, lo);
         hi = __reduce_max_sync(0xffffffffu, hi);
         if (lane == 0) { s_red[warp] = lo; s_red[NW + warp] = hi; }
@@ -169,15 +130,29 @@ quantile_select_kernel(const QuantileParams p, const __grid_constant__ QuantileL
         const int bits = 32 - __clz(hi - lo);           // rank window < 2^bits
         shift1 = max(0, bits - LOG2NB);                 // (window >> shift1) < NB
     }
+    const bool single = shift1 <= sel_bits;             // one refinement level reaches single ranks
 
-    // 2. level 1: weight per bucket, then inclusive prefix in place (8 buckets per thread)
-    for (uint32_t i = tid; i < P; i += THREADS) atomicAdd(&h1[(rk[i] - rmin) >> shift1], wfx[i]);
+    // 2. level 1: weight, largest and smallest rank per bucket; inclusive prefix of the weights
+    for (uint32_t i = tid; i < P; i += THREADS) {
+        const uint32_t w = wfx[i];
+        if (w == 0u) continue;                          // utils.py:55-57
+        const uint32_t d = rk[i] - rmin, b = d >> shift1;
+        atomicAdd(&h1[b], w);
+        atomicMax(&bmx[b], d + 1u);
+        atomicMin(&bmn[b], d);
+    }
     __syncthreads();
     {
-        uint4 c0 = reinterpret_cast<uint4*>(h1)[2 * tid];
-        uint4 c1 = reinterpret_cast<uint4*>(h1)[2 * tid + 1];
-        const uint32_t total = c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w;
-        uint32_t incl = total;
+        uint32_t c[BPT];
+#pragma unroll
+        for (int k = 0; k < BPT / 4; ++k) {
+            const uint4 x = reinterpret_cast<const uint4*>(h1)[tid * (BPT / 4) + k];
+            c[4 * k] = x.x; c[4 * k + 1] = x.y; c[4 * k + 2] = x.z; c[4 * k + 3] = x.w;
+        }
+        uint32_t mine = 0;
+#pragma unroll
+        for (int k = 0; k < BPT; ++k) mine += c[k];
+        uint32_t incl = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
@@ -185,82 +160,109 @@ quantile_select_kernel(const QuantileParams p, const __grid_constant__ QuantileL
         }
         if (lane == 31) s_red[warp] = incl;
         __syncthreads();
-        uint32_t run = incl - total;
+        uint32_t run = incl - mine;
 #pragma unroll
         for (int w = 0; w < NW; ++w) run += (w < warp) ? s_red[w] : 0u;
-        uint4 o0, o1;
-        run += c0.x; o0.x = run; run += c0.y; o0.y = run; run += c0.z; o0.z = run; run += c0.w; o0.w = run;
-        run += c1.x; o1.x = run; run += c1.y; o1.y = run; run += c1.z; o1.z = run; run += c1.w; o1.w = run;
-        reinterpret_cast<uint4*>(h1)[2 * tid] = o0;
-        reinterpret_cast<uint4*>(h1)[2 * tid + 1] = o1;
+#pragma unroll
+        for (int k = 0; k < BPT; ++k) { run += c[k]; c[k] = run; }
+#pragma unroll
+        for (int k = 0; k < BPT / 4; ++k)
+            reinterpret_cast<uint4*>(h1)[tid * (BPT / 4) + k] = make_uint4(c[4 * k], c[4 * k + 1], c[4 * k + 2], c[4 * k + 3]);
     }
     __syncthreads();
     const uint32_t total = h1[NB - 1];
 
-    for (int q0 = 0; q0 < p.Q; q0 += QB) {
-        const int nqb = min(QB, p.Q - q0);
-        // 3a. target weight and level-1 bucket of every percentile of the batch
-        if (tid < QB) {
-            uint32_t tau = 1u, wlo = 0u, base = 0u;
-            if (tid < nqb) {
-                const double t = ceil(ql.q[q0 + tid] * static_cast<double>(total) / 100.0);
-                tau = static_cast<uint32_t>(fmin(fmax(t, 1.0), static_cast<double>(total)));
-                int lo = 0, hi = NB - 1;                // first bucket whose inclusive prefix reaches tau
+    // 3a. every percentile of the call: target weight, level-1 bucket, outside neighbours
+    if (tid < p.Q) {
+        const double t = ceil(ql.q[tid] * static_cast<double>(total) / 100.0);
+        const uint32_t tau = static_cast<uint32_t>(fmin(fmax(t, 1.0), static_cast<double>(total)));
+        int lo = 0, hi = NB - 1;                        // first bucket whose inclusive prefix reaches tau
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (h1[mid] >= tau) hi = mid; else lo = mid + 1;
+        }
+        const int bq = lo;
+        const uint32_t base = bq ? h1[bq - 1] : 0u, upto = h1[bq];
+        uint32_t pout = 0u, sout = NONE;
+        if (single) {
+            if (base != 0u) {                           // last non-empty bucket before bq
+                lo = 0; hi = bq - 1;
                 while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
-                    if (h1[mid] >= tau) hi = mid; else lo = mid + 1;
+                    if (h1[mid] >= base) hi = mid; else lo = mid + 1;
                 }
-                wlo = static_cast<uint32_t>(lo) << shift1;
-                base = lo ? h1[lo - 1] : 0u;
+                pout = bmx[lo];
             }
-            s_tau[tid] = tau;
-            s_wlo[tid] = wlo;
-            s_base[tid] = base;
-            s_pout[tid] = 0u;
-            s_sout[tid] = NONE;
-            s_pin[tid] = 0u;
-            s_sin[tid] = NONE;
-            s_Wp[tid] = 0u;
-            s_Ws[tid] = 0u;
-            s_e[tid] = 0u;
-            s_We[tid] = 0u;
-            s_Ce[tid] = 0u;
+            if (upto != total) {                        // first non-empty bucket after bq
+                lo = bq + 1; hi = NB - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (h1[mid] > upto) hi = mid; else lo = mid + 1;
+                }
+                sout = bmn[lo];
+            }
         }
-        // 3b. refine the window of every percentile down to single ranks
+        s_tau[tid] = tau;
+        s_wlo[tid] = static_cast<uint32_t>(bq) << shift1;
+        s_base[tid] = base;
+        s_pout[tid] = pout;
+        s_sout[tid] = sout;
+    }
+    __syncthreads();
+
+    for (int q0 = 0; q0 < p.Q; q0 += QB) {
+        const int nqb = min(QB, p.Q - q0);
+        if (tid < QB) {
+            s_pin[tid] = 0u; s_sin[tid] = NONE; s_Wp[tid] = 0u; s_Ws[tid] = 0u;
+            s_e[tid] = 0u; s_We[tid] = 0u; s_Ce[tid] = 0u;
+        }
+        // 3b. refine the window of every percentile of the batch down to single ranks
         int wb = shift1;                                // the window of a percentile spans 2^wb ranks
         for (;;) {
-            const int sh = max(0, wb - kSelectL2Bits);  // ranks per slot = 2^sh
+            const int sh = max(0, wb - sel_bits);       // ranks per slot = 2^sh
             const bool final_level = sh == 0;
             for (int i = tid; i < QB * L2S; i += THREADS) l2[i] = 0u;
             __syncthreads();
             {
-                uint32_t wlo[QB], pm[QB], sn[QB];
+                uint32_t wlo[QB], po[QB], so[QB], pm[QB], sn[QB];
 #pragma unroll
-                for (int q = 0; q < QB; ++q) { wlo[q] = s_wlo[q]; pm[q] = 0u; sn[q] = NONE; }
+                for (int q = 0; q < QB; ++q) {
+                    const bool on = q < nqb;
+                    wlo[q] = on ? s_wlo[q0 + q] : 0u;
+                    po[q] = on ? s_pout[q0 + q] : 0u;
+                    so[q] = on ? s_sout[q0 + q] : NONE;
+                    pm[q] = 0u;
+                    sn[q] = NONE;
+                }
                 const uint32_t wsize = 1u << wb;
                 for (uint32_t i = tid; i < P; i += THREADS) {
-                    const uint32_t d = rk[i] - rmin;
                     const uint32_t w = wfx[i];
                     if (w == 0u) continue;              // utils.py:55-57
+                    const uint32_t d = rk[i] - rmin;
 #pragma unroll
                     for (int q = 0; q < QB; ++q) {
                         if (q < nqb) {
                             const uint32_t off = d - wlo[q];
                             if (off < wsize) atomicAdd(&l2[q * L2S + (off >> sh)], w);
-                            else if (d < wlo[q]) pm[q] = max(pm[q], d + 1u);
-                            else sn[q] = min(sn[q], d);
+                            if (single) {               // weights of the outside neighbours, known up front
+                                if (d + 1u == po[q]) atomicAdd(&s_Wp[q], w);
+                                if (d == so[q]) atomicAdd(&s_Ws[q], w);
+                            } else {                    // nearest ranks outside the window
+                                pm[q] = max(pm[q], (d < wlo[q]) ? d + 1u : 0u);
+                                sn[q] = min(sn[q], (off >= wsize && d > wlo[q]) ? d : NONE);
+                            }
                         }
                     }
                 }
-                if (final_level) {
+                if (!single && final_level) {
 #pragma unroll
                     for (int q = 0; q < QB; ++q) {
                         if (q < nqb) {
                             const uint32_t a = __reduce_max_sync(0xffffffffu, pm[q]);
                             const uint32_t b = __reduce_min_sync(0xffffffffu, sn[q]);
                             if (lane == 0) {
-                                if (a) atomicMax(&s_pout[q], a);
-                                if (b != NONE) atomicMin(&s_sout[q], b);
+                                if (a) atomicMax(&s_pout[q0 + q], a);
+                                if (b != NONE) atomicMin(&s_sout[q0 + q], b);
                             }
                         }
                     }
@@ -295,8 +297,8 @@ quantile_select_kernel(const QuantileParams p, const __grid_constant__ QuantileL
                 __syncthreads();
                 uint32_t found = NONE, fw = 0u, fc = 0u;
                 if (q < nqb) {
-                    const uint32_t tau = s_tau[q];
-                    uint32_t run = s_base[q] + (excl - s_seg[q]);
+                    const uint32_t tau = s_tau[q0 + q];
+                    uint32_t run = s_base[q0 + q] + (excl - s_seg[q]);
 #pragma unroll
                     for (int c = 0; c < SPT; ++c) {
                         const uint32_t before = run;
@@ -310,8 +312,8 @@ quantile_select_kernel(const QuantileParams p, const __grid_constant__ QuantileL
                     s_We[q] = fw;
                     s_Ce[q] = fc;
                     if (!final_level) {
-                        s_wlo[q] += found << sh;
-                        s_base[q] = fc - fw;
+                        s_wlo[q0 + q] += found << sh;
+                        s_base[q0 + q] = fc - fw;
                     }
                 }
                 __syncthreads();
@@ -332,8 +334,8 @@ quantile_select_kernel(const QuantileParams p, const __grid_constant__ QuantileL
             if (final_level) break;
             wb = sh;
         }
-        // 3c. merged weights of the neighbours that lie outside the window (if any is needed)
-        {
+        // 3c. several levels only: merged weights of the outside neighbours that are needed
+        if (!single) {
             bool need = false;
             uint32_t pd[QB], sd[QB];
 #pragma unroll
@@ -341,8 +343,8 @@ quantile_select_kernel(const QuantileParams p, const __grid_constant__ QuantileL
                 pd[q] = NONE;
                 sd[q] = NONE;
                 if (q < nqb) {
-                    if (s_pin[q] == 0u && s_pout[q] != 0u) { pd[q] = s_pout[q] - 1u; need = true; }
-                    if (s_sin[q] == NONE && s_sout[q] != NONE) { sd[q] = s_sout[q]; need = true; }
+                    if (s_pin[q] == 0u && s_pout[q0 + q] != 0u) { pd[q] = s_pout[q0 + q] - 1u; need = true; }
+                    if (s_sin[q] == NONE && s_sout[q0 + q] != NONE) { sd[q] = s_sout[q0 + q]; need = true; }
                 }
             }
             if (need) {                                 // block-uniform: computed from shared state
@@ -355,15 +357,15 @@ quantile_select_kernel(const QuantileParams p, const __grid_constant__ QuantileL
                     }
                 }
             }
+            __syncthreads();
         }
-        __syncthreads();
         // 4. utils.py:69-81 on (pred, e, succ), float32
         if (tid < nqb) {
             const int q = tid;
             const double qv = ql.q[q0 + q];
             const float inv = __fdiv_rn(1.0f, fx_scale);
             const float s = __fdiv_rn(100.0f, __fmul_rn(static_cast<float>(total), inv));     // utils.py:69,72
-            const uint32_t wlo = s_wlo[q];              // window of the final level: slot == rank offset
+            const uint32_t wlo = s_wlo[q0 + q];         // window of the final level: slot == rank offset
             const uint32_t de = wlo + s_e[q];
             const uint32_t We = s_We[q], Ce = s_Ce[q];
             const float a_e = __ldg(p.y_sorted + (rmin + de));
@@ -373,7 +375,7 @@ quantile_select_kernel(const QuantileParams p, const __grid_constant__ QuantileL
             if (static_cast<double>(p_e) < qv) {        // interval (e, succ)
                 uint32_t ds = NONE, Ws = 0u;
                 if (s_sin[q] != NONE) { ds = wlo + s_sin[q]; Ws = l2[q * L2S + s_sin[q]]; }
-                else if (s_sout[q] != NONE) { ds = s_sout[q]; Ws = s_Ws[q]; }
+                else if (s_sout[q0 + q] != NONE) { ds = s_sout[q0 + q]; Ws = s_Ws[q]; }
                 if (ds != NONE) {                       // else q lies beyond the last entry: a_last (utils.py:74-75)
                     const float a_s = __ldg(p.y_sorted + (rmin + ds));
                     const float p_s = plotting_position(s, __fmul_rn(static_cast<float>(Ce + Ws), inv),
@@ -384,7 +386,7 @@ quantile_select_kernel(const QuantileParams p, const __grid_constant__ QuantileL
             } else {                                    // interval (pred, e)
                 uint32_t dp = NONE, Wp = 0u;
                 if (s_pin[q] != 0u) { dp = wlo + s_pin[q] - 1u; Wp = l2[q * L2S + s_pin[q] - 1u]; }
-                else if (s_pout[q] != 0u) { dp = s_pout[q] - 1u; Wp = s_Wp[q]; }
+                else if (s_pout[q0 + q] != 0u) { dp = s_pout[q0 + q] - 1u; Wp = s_Wp[q]; }
                 if (dp != NONE) {                       // else q lies before the first entry: a_0 (utils.py:76-77)
                     const float a_p = __ldg(p.y_sorted + (rmin + dp));
                     const float p_p = plotting_position(s, __fmul_rn(static_cast<float>(Ce - We), inv),

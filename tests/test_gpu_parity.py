@@ -219,15 +219,15 @@ def test_random_forests_bit_exact_vs_oracle(kind, bootstrap, msl, ties, depth):
 
 
 @pytest.mark.parametrize("name", _golden.CASES)
-@pytest.mark.parametrize("warp_elems", [-1, 0])
-def test_fast_mode_against_reference_outputs(name, warp_elems):
+@pytest.mark.parametrize("warp_elems,select_bits", [(-1, 10), (0, 10), (0, 3), (0, 1)])
+def test_fast_mode_against_reference_outputs(name, warp_elems, select_bits):
     # QF_MODE_FAST (histogram selection instead of the sort) against the reference's own
     # outputs: 1e-4 relative (BASELINE.json north_star, float32 arithmetic), order
     # statistics (q = 0 and q = 100) bit-exact
     from skgarden_b200 import _native
     g = _golden.load(name)
     flat = _golden.flat_from_golden(g)
-    dev = _dev(flat, warp_elems=warp_elems)
+    dev = _dev(flat, warp_elems=warp_elems, select_bits=select_bits)   # few bits: several refinement levels
     X = _cuda(g.X_test)
     scale = np.abs(g.y_train).max()
     for lo in range(0, len(g.q), 7):                    # batches of <= 16 percentiles take the selection kernel
@@ -258,6 +258,8 @@ def test_fast_mode_large_member_sets(kind, msl, depth, T):
     fast = est.predict(X[N:], quantile=qs)
     assert_allclose(fast, exact, rtol=1e-4, atol=1e-4 * np.abs(y).max())
     assert_array_equal(fast[:, [0, -1]], exact[:, [0, -1]])
+    est._device_forest.set_option("select_bits", 4)              # same through several refinement levels
+    assert_array_equal(est.predict(X[N:], quantile=qs), fast)
     print("fast vs exact: max abs diff %.3g (|y| max %.3g), members/row %.0f" % (
         np.abs(fast - exact).max(), np.abs(y).max(), est._flat.expected_row_members))
 
