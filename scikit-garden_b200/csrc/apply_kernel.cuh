@@ -87,11 +87,18 @@ apply_kernel(const ApplyParams p, void* __restrict__ out) {
     const bool row_ok = pos < p.n;
     int64_t out_row = pos;
     if (EMIT != APPLY_EMIT_SEGMENT && row_ok && p.order) out_row = __ldg(p.order + pos);
-    const float* __restrict__ xcol = xt + r;
+    // shared-memory byte address of this lane's column of the tile; feature f is at
+    // xcol_s + f * 4 * rows_per_cta (32-bit address arithmetic, ld.shared)
+    const uint32_t xcol_s = static_cast<uint32_t>(__cvta_generic_to_shared(xt + r));
+    const uint32_t fstride = static_cast<uint32_t>(rows_per_cta) * 4u;
     const uint32_t fmask = (1u << p.fbits) - 1u;
 
-    // chain k of every lane walks the same tree (warp-uniform tree[k])
+    // chain k of every lane walks the same tree (warp-uniform tree[k]).  The loop body is
+    // branch-free: a lane that reached its leaf keeps the leaf node in nd[k] and simply stops
+    // loading; results are written when the whole warp is done with the chain (uniform branch).
+    const uint2* __restrict__ nodes = p.nodes;
     uint32_t node[ILP];
+    uint2 nd[ILP];
     int tree[ILP];
     uint32_t live = 0;                                  // bit k: this lane is still walking chain k
     uint32_t armed = 0;                                 // bit k: chain k holds a tree (warp-uniform)
@@ -100,6 +107,7 @@ apply_kernel(const ApplyParams p, void* __restrict__ out) {
     for (int k = 0; k < ILP; ++k) {
         tree[k] = next_tree;
         node[k] = 0u;
+        nd[k] = make_uint2(0u, 0u);
         if (next_tree < p.t_end) {
             armed |= 1u << k;
             node[k] = __ldg(p.roots + next_tree);
@@ -109,36 +117,37 @@ apply_kernel(const ApplyParams p, void* __restrict__ out) {
     if (row_ok) live = armed;
 
     while (armed) {
-        uint2 nd[ILP];
 #pragma unroll
         for (int k = 0; k < ILP; ++k)
-            if (live & (1u << k)) nd[k] = __ldg(p.nodes + node[k]);
+            if (live & (1u << k)) nd[k] = __ldg(nodes + node[k]);
 #pragma unroll
         for (int k = 0; k < ILP; ++k) {
-            if (!(live & (1u << k))) continue;
-            if (static_cast<int32_t>(nd[k].y) < 0) {    // leaf
-                if (EMIT == APPLY_EMIT_SEGMENT) {
-                    static_cast<uint2*>(out)[out_row * p.T + tree[k]] =
-                        make_uint2(nd[k].x, nd[k].y & 0x7fffffffu);
-                } else {
-                    static_cast<int32_t*>(out)[out_row * p.T + tree[k]] = static_cast<int32_t>(node[k]);
-                }
-                live &= ~(1u << k);
-            } else {
-                const uint32_t f = nd[k].y & fmask;
-                const uint32_t off = nd[k].y >> p.fbits;
-                const float x = xcol[f * rows_per_cta];
-                // sklearn:tree/_tree.pyx:989  `X[i, feature] <= threshold` -> left
-                node[k] += (x <= __uint_as_float(nd[k].x)) ? 1u : off;
-            }
+            const bool on = (live >> k) & 1u;
+            const bool leaf = static_cast<int32_t>(nd[k].y) < 0;
+            const bool walk = on && !leaf;
+            const uint32_t f = nd[k].y & fmask;
+            const uint32_t off = nd[k].y >> p.fbits;
+            float x = 0.0f;
+            if (walk) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(xcol_s + f * fstride));
+            // sklearn:tree/_tree.pyx:989  `X[i, feature] <= threshold` -> left
+            const uint32_t step = (x <= __uint_as_float(nd[k].x)) ? 1u : off;
+            node[k] += walk ? step : 0u;
+            live &= ~((on && leaf ? 1u : 0u) << k);
         }
-        // re-arm the chains every lane has finished with the warp's next trees
+        // chains every lane has finished: write the results, re-arm with the warp's next trees
         const uint32_t busy = __reduce_or_sync(0xffffffffu, live);
-        uint32_t idle = armed & ~busy;
+        const uint32_t idle = armed & ~busy;
         if (idle) {
 #pragma unroll
             for (int k = 0; k < ILP; ++k) {
                 if (!(idle & (1u << k))) continue;
+                if (row_ok) {
+                    if (EMIT == APPLY_EMIT_SEGMENT)
+                        static_cast<uint2*>(out)[out_row * p.T + tree[k]] =
+                            make_uint2(nd[k].x, nd[k].y & 0x7fffffffu);
+                    else
+                        static_cast<int32_t*>(out)[out_row * p.T + tree[k]] = static_cast<int32_t>(node[k]);
+                }
                 if (next_tree < p.t_end) {
                     tree[k] = next_tree;
                     node[k] = __ldg(p.roots + next_tree);

@@ -325,27 +325,25 @@ int launch_bucket_kernel(int threads, unsigned grid, const qf::QuantileParams& q
     }
 }
 
-// QF_MODE_FAST: the selection kernel (select_kernel.cuh) in place of the sorting one
-int launch_select_kernel(int threads, unsigned grid, const qf::QuantileParams& qp, const qf::QuantileList& ql,
-                         int T, int sel_bits, cudaStream_t st) {
-    const size_t smem = qf::select_kernel_smem(threads, T);
-    if (smem > 220 * 1024)
-        return qf::fail(QF_ERR_LIMIT, "predict_quantiles: n_estimators too large for shared memory");
+// QF_MODE_FAST: the streaming selection kernel (select_kernel.cuh) takes every row the warp
+// kernel does not, whatever its number of members
+int launch_select_kernel(const qf_forest* f, unsigned grid, const qf::QuantileParams& qp,
+                         const qf::QuantileList& ql, cudaStream_t st) {
+    const size_t smem = qf::select_kernel_smem();
     int k = 0;                                          // weights of a row sum to <= T < 2^k
-    while ((int64_t(1) << k) < int64_t(T) + 1) ++k;
+    while ((int64_t(1) << k) < int64_t(f->T) + 1) ++k;
+    if (k > 20) return qf::fail(QF_ERR_LIMIT, "predict_quantiles: too many trees for fixed-point weights");
     const float fx_scale = static_cast<float>(int64_t(1) << (31 - k));
+    int nbits = 0;                                      // ranks are < 2^nbits
+    while ((int64_t(1) << nbits) < f->N) ++nbits;
+    const int threads = f->T <= 128 ? 128 : 256;        // 4 lanes per leaf list
     auto run = [&](auto kernel) -> int {
         int rc = set_smem(kernel, smem);
         if (rc != QF_OK) return rc;
-        kernel<<<grid, threads, smem, st>>>(qp, ql, fx_scale, sel_bits);
+        kernel<<<grid, threads, smem, st>>>(qp, ql, fx_scale, nbits, f->select_bits);
         return QF_OK;
     };
-    switch (threads) {
-        case 64: return run(qf::quantile_select_kernel<64>);
-        case 128: return run(qf::quantile_select_kernel<128>);
-        case 256: return run(qf::quantile_select_kernel<256>);
-        default: return run(qf::quantile_select_kernel<512>);
-    }
+    return threads == 128 ? run(qf::quantile_select_kernel<128>) : run(qf::quantile_select_kernel<256>);
 }
 
 // `pl` is the caller's carve-up of `ws` (made once for the largest chunk, so that the
@@ -417,6 +415,19 @@ int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, co
                 ++f->launches;
                 advance();
             }
+            if (select && (pl.s1_threads || pl.dense_needed)) {   // every remaining row, any member count
+                chain();                                 // (never overflows)
+                const unsigned grid = qp.row_list ? static_cast<unsigned>(std::min<int64_t>(rows, int64_t(f->sm_count) * 8))
+                                                  : static_cast<unsigned>(rows);
+                {
+                    SpanTimer span(f, SPAN_QUANTILE, st);
+                    rc = launch_select_kernel(f, grid, qp, ql, st);
+                }
+                if (rc != QF_OK) return rc;
+                QF_CUDA_TRY(cudaGetLastError());
+                ++f->launches;
+                continue;
+            }
             const int bucket_threads[2] = {pl.s1_threads, pl.s2_limit ? kMaxBucketThreads : 0};
             const int bucket_limit[2] = {pl.s1_limit, pl.s2_limit};
             for (int b = 0; b < 2; ++b) {
@@ -428,8 +439,7 @@ int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, co
                                                   : static_cast<unsigned>(rows);
                 {
                     SpanTimer span(f, SPAN_QUANTILE, st);
-                    rc = select ? launch_select_kernel(bucket_threads[b], grid, qp, ql, f->T, f->select_bits, st)
-                                : launch_bucket_kernel(bucket_threads[b], grid, qp, ql, f->T, st);
+                    rc = launch_bucket_kernel(bucket_threads[b], grid, qp, ql, f->T, st);
                 }
                 if (rc != QF_OK) return rc;
                 QF_CUDA_TRY(cudaGetLastError());
