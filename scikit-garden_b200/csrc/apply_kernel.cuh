@@ -54,11 +54,18 @@ struct ApplyParams {
 enum { APPLY_EMIT_SEGMENT = 0, APPLY_EMIT_NODE = 1 };
 
 constexpr int kApplyThreads = 256;
+constexpr int kApplyLevels = 2;                         // visits per chain between two warp votes
 
 template <int ILP, int EMIT>
 __global__ void __launch_bounds__(kApplyThreads)
 apply_kernel(const ApplyParams p, void* __restrict__ out) {
     extern __shared__ float xt[];                       // [F][ROWS]
+    __shared__ uint64_t s_nodes;
+    __shared__ uint32_t s_fbits;
+    if (threadIdx.x == 0) {
+        s_nodes = reinterpret_cast<uint64_t>(p.nodes);
+        s_fbits = static_cast<uint32_t>(p.fbits);
+    }
     const int rows_per_cta = 32 * p.row_warps;
     const int tree_warps = (kApplyThreads / 32) / p.row_warps;
     const int64_t pos0 = static_cast<int64_t>(blockIdx.x) * rows_per_cta;
@@ -84,7 +91,7 @@ apply_kernel(const ApplyParams p, void* __restrict__ out) {
     const int tw = warp / p.row_warps;
     const int r = rw * 32 + lane;
     const int64_t pos = pos0 + r;
-    const bool row_ok = pos < p.n;
+    const bool row_ok = pos < p.n;                      // lanes past the end walk a zero row and write nothing
     int64_t out_row = pos;
     if (EMIT != APPLY_EMIT_SEGMENT && row_ok && p.order) out_row = __ldg(p.order + pos);
     // shared-memory byte address of this lane's column of the tile; feature f is at
@@ -93,54 +100,59 @@ apply_kernel(const ApplyParams p, void* __restrict__ out) {
     const uint32_t fstride = static_cast<uint32_t>(rows_per_cta) * 4u;
     const uint32_t fmask = (1u << p.fbits) - 1u;
 
-    // chain k of every lane walks the same tree (warp-uniform tree[k]).  The loop body is
-    // branch-free: a lane that reached its leaf keeps the leaf node in nd[k] and simply stops
-    // loading; results are written when the whole warp is done with the chain (uniform branch).
-    const uint2* __restrict__ nodes = p.nodes;
+    // chain k of every lane walks the same tree (warp-uniform tree[k]).  Per visit and chain:
+    // one predicated 8-byte node load, one predicated shared-memory load, compare, select, add.
+    // The sign bit of nd[k].y is the chain's state: a lane that reached its leaf keeps the leaf
+    // node in nd[k] and its loads are predicated off.  Every kApplyLevels visits the sign bits of
+    // all chains are AND-reduced over the warp (one REDUX); a chain whose 32 lanes all sit on a
+    // leaf writes its results and is re-armed with the warp's next tree.
+    // fbits and the node base take a round trip through shared memory: that makes them opaque
+    // to the compiler, which keeps them in registers instead of re-reading the constant bank
+    // in front of every shift / address computation of the loop below.
+    const uint32_t fbits = s_fbits;
+    const uint2* __restrict__ nodes = reinterpret_cast<const uint2*>(s_nodes);
     uint32_t node[ILP];
     uint2 nd[ILP];
     int tree[ILP];
-    uint32_t live = 0;                                  // bit k: this lane is still walking chain k
     uint32_t armed = 0;                                 // bit k: chain k holds a tree (warp-uniform)
     int next_tree = p.t_begin + tw;
 #pragma unroll
     for (int k = 0; k < ILP; ++k) {
         tree[k] = next_tree;
         node[k] = 0u;
-        nd[k] = make_uint2(0u, 0u);
+        nd[k] = make_uint2(0u, 0x80000000u);
         if (next_tree < p.t_end) {
             armed |= 1u << k;
             node[k] = __ldg(p.roots + next_tree);
+            nd[k].y = 0u;
         }
         next_tree += tree_warps;
     }
-    if (row_ok) live = armed;
 
     while (armed) {
 #pragma unroll
-        for (int k = 0; k < ILP; ++k)
-            if (live & (1u << k)) nd[k] = __ldg(nodes + node[k]);
+        for (int lvl = 0; lvl < kApplyLevels; ++lvl) {
 #pragma unroll
-        for (int k = 0; k < ILP; ++k) {
-            const bool on = (live >> k) & 1u;
-            const bool leaf = static_cast<int32_t>(nd[k].y) < 0;
-            const bool walk = on && !leaf;
-            const uint32_t f = nd[k].y & fmask;
-            const uint32_t off = nd[k].y >> p.fbits;
-            float x = 0.0f;
-            if (walk) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(xcol_s + f * fstride));
-            // sklearn:tree/_tree.pyx:989  `X[i, feature] <= threshold` -> left
-            const uint32_t step = (x <= __uint_as_float(nd[k].x)) ? 1u : off;
-            node[k] += walk ? step : 0u;
-            live &= ~((on && leaf ? 1u : 0u) << k);
-        }
-        // chains every lane has finished: write the results, re-arm with the warp's next trees
-        const uint32_t busy = __reduce_or_sync(0xffffffffu, live);
-        const uint32_t idle = armed & ~busy;
-        if (idle) {
+            for (int k = 0; k < ILP; ++k)
+                if (static_cast<int32_t>(nd[k].y) >= 0) nd[k] = __ldg(nodes + node[k]);
 #pragma unroll
             for (int k = 0; k < ILP; ++k) {
-                if (!(idle & (1u << k))) continue;
+                if (static_cast<int32_t>(nd[k].y) >= 0) {
+                    float x;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(xcol_s + (nd[k].y & fmask) * fstride));
+                    // sklearn:tree/_tree.pyx:989  `X[i, feature] <= threshold` -> left (= node + 1)
+                    node[k] += (x <= __uint_as_float(nd[k].x)) ? 1u : (nd[k].y >> fbits);
+                }
+            }
+        }
+        uint32_t signs = 0;                             // bit k: this lane's chain k sits on a leaf
+#pragma unroll
+        for (int k = ILP - 1; k >= 0; --k) signs = __funnelshift_l(nd[k].y, signs, 1);
+        const uint32_t done = __reduce_and_sync(0xffffffffu, signs) & armed;
+        if (done) {                                     // warp-uniform
+#pragma unroll
+            for (int k = 0; k < ILP; ++k) {
+                if (!(done & (1u << k))) continue;
                 if (row_ok) {
                     if (EMIT == APPLY_EMIT_SEGMENT)
                         static_cast<uint2*>(out)[out_row * p.T + tree[k]] =
@@ -151,7 +163,7 @@ apply_kernel(const ApplyParams p, void* __restrict__ out) {
                 if (next_tree < p.t_end) {
                     tree[k] = next_tree;
                     node[k] = __ldg(p.roots + next_tree);
-                    if (row_ok) live |= 1u << k;
+                    nd[k].y = 0u;
                 } else {
                     armed &= ~(1u << k);
                 }

@@ -13,6 +13,7 @@
 #include "qf_internal.h"
 #include "quantile_kernel.cuh"
 #include "select_kernel.cuh"
+#include "select2_kernel.cuh"
 
 namespace qf {
 
@@ -72,6 +73,7 @@ struct qf_forest {
     int64_t rows_per_chunk = 131072;
     int cta_capacity = 0;         // cap on the members per row of the first bucket stage (0 = its capacity)
     int select_bits = qf::kSelectL2Bits;   // log2 refinement slots of the selection kernel (tests lower it)
+    int select_impl = 0;                   // 0: single-refinement kernel when the training set allows; 1: always the multi-level one
     int cta2_capacity = 8192;     // same for the 512-thread overflow stage (0 = stage not used)
     int warp_elems = -1;          // warp kernel: keys per lane (2, 4, 8), 0 = never, -1 = auto
     int dense_ctas = 0;           // 0 = auto
@@ -195,9 +197,9 @@ Plan make_plan(const qf_forest* f, int64_t n_rows) {
 
 int pick_row_warps(const qf_forest* f) {
     if (f->apply_row_warps > 0) return f->apply_row_warps;
-    // 2 row-warps x 4 tree-warps measured best at config 2; fewer trees than tree-warps
-    // would leave warps idle
-    int rw = 2;
+    // 1 row-warp x 8 tree-warps measured best at configs 2 and 3 (32 rows per CTA: the most
+    // CTAs, the smallest tile); fewer trees than tree-warps would leave warps idle
+    int rw = 1;
     while (rw < 8 && (8 / rw) > f->T) rw <<= 1;
     return rw;
 }
@@ -336,6 +338,20 @@ int launch_select_kernel(const qf_forest* f, unsigned grid, const qf::QuantilePa
     const float fx_scale = static_cast<float>(int64_t(1) << (31 - k));
     int nbits = 0;                                      // ranks are < 2^nbits
     while ((int64_t(1) << nbits) < f->N) ++nbits;
+    // training sets of up to 2M samples: one refinement level is enough (select2_kernel.cuh)
+    if (f->select_impl == 0 && f->select_bits == qf::kSelectL2Bits && nbits <= 12 + qf::kSelect2SlotBits) {
+        const int log2nb = nbits <= 11 + qf::kSelect2SlotBits ? 11 : 12;
+        const int shift1 = std::max(0, nbits - log2nb);
+        const size_t smem2 = qf::select2_kernel_smem(log2nb, shift1, f->T);
+        const unsigned ctas = static_cast<unsigned>(f->sm_count) * (log2nb == 11 ? qf::kSelect2CtasPerSm : 4);
+        auto run2 = [&](auto kernel) -> int {
+            int rc = set_smem(kernel, smem2);
+            if (rc != QF_OK) return rc;
+            kernel<<<std::min(grid, ctas), qf::kSelect2Threads, smem2, st>>>(qp, ql, fx_scale, shift1);
+            return QF_OK;
+        };
+        return log2nb == 11 ? run2(qf::quantile_select2_kernel<11>) : run2(qf::quantile_select2_kernel<12>);
+    }
     const int threads = f->T <= 128 ? 128 : 256;        // 4 lanes per leaf list
     auto run = [&](auto kernel) -> int {
         int rc = set_smem(kernel, smem);
@@ -522,7 +538,9 @@ int qf_forest_create(const qf_forest_desc* d, qf_forest** out) {
     for (int t = 0; t < d->n_trees; ++t) roots[t] = static_cast<uint32_t>(d->tree_offsets[t]);
 
     auto upload = [&](void** dst, const void* src, int64_t bytes) -> int {
-        QF_CUDA_TRY(cudaMalloc(dst, static_cast<size_t>(bytes)));
+        // + 16: kernels read members in aligned 128-bit pairs, the last pair may straddle the end
+        QF_CUDA_TRY(cudaMalloc(dst, static_cast<size_t>(bytes) + 16));
+        QF_CUDA_TRY(cudaMemset(static_cast<unsigned char*>(*dst) + bytes, 0, 16));
         // cudaMemcpyDefault: the source may be host memory or (UVA) device memory, e.g. a
         // buffer that was just broadcast to this rank over NCCL
         QF_CUDA_TRY(cudaMemcpy(*dst, src, static_cast<size_t>(bytes), cudaMemcpyDefault));
@@ -627,6 +645,9 @@ int qf_forest_set_option(qf_forest* f, const char* key, int64_t value) {
     } else if (k == "cta2_capacity") {
         if (value < 0 || value > 8192) return qf::fail(QF_ERR_INVALID, "cta2_capacity must be in [0, 8192]");
         f->cta2_capacity = static_cast<int>(value);
+    } else if (k == "select_impl") {
+        if (value != 0 && value != 1) return qf::fail(QF_ERR_INVALID, "select_impl must be 0 or 1");
+        f->select_impl = static_cast<int>(value);
     } else if (k == "select_bits") {
         if (value < 1 || value > qf::kSelectL2Bits)
             return qf::fail(QF_ERR_INVALID, "select_bits must be in [1, 10]");
@@ -732,7 +753,11 @@ int qf_forest_predict_quantiles_host(qf_forest* f, const float* X_host, int64_t 
     reset_call_counters(f);
     if (n == 0) return QF_OK;
     DeviceGuard guard(f->device);
-    if (chunk_rows <= 0) chunk_rows = f->rows_per_chunk;
+    if (chunk_rows <= 0) {
+        // at least four pipeline slots' worth of chunks, so that the copies of one chunk overlap
+        // the kernels of its neighbours; not below 16k rows (launch overhead, kernel tails)
+        chunk_rows = std::min<int64_t>(f->rows_per_chunk, std::max<int64_t>(16384, ((n + 3) / 4 + 31) / 32 * 32));
+    }
     chunk_rows = std::min(chunk_rows, n);
     const int64_t saved_chunk = f->rows_per_chunk;
     f->rows_per_chunk = chunk_rows;                       // one kernel chunk per pipeline slot

@@ -56,12 +56,15 @@ template <typename RankOf, typename WeightOf, typename CumOf>
 __device__ __forceinline__ double select_percentile(double q, int m, float s, RankOf rankOf,
                                                     WeightOf weightOf, CumOf cumOf,
                                                     const float* __restrict__ y_sorted) {
-    // numpy's binary search, side='left', float32 element promoted to float64 for the compare
+    // numpy's binary search, side='left', float32 element promoted to float64 for the compare.
+    // p < q in float64  <=>  p < (smallest float32 >= q) in float32: no float64 instruction in
+    // the loop (the FP64 pipe of sm_100 is narrow)
+    const float qc = __double2float_ru(q);
     int lo = 0, hi = m;
     while (lo < hi) {
         const int mid = lo + ((hi - lo) >> 1);
         const float pm = plotting_position(s, cumOf(mid), weightOf(mid));
-        if (static_cast<double>(pm) < q) lo = mid + 1; else hi = mid;
+        if (pm < qc) lo = mid + 1; else hi = mid;
     }
     const int start = lo - 1;
     if (start == m - 1) return static_cast<double>(__ldg(y_sorted + rankOf(m - 1)));   // utils.py:74-75

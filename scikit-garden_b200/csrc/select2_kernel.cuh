@@ -1,0 +1,445 @@
+// K2, QF_MODE_FAST, single-refinement form -- weighted percentile by histogram selection for
+// training sets of up to 2^(LOG2NB + 9) samples (2M with LOG2NB = 12).  Larger training sets
+// take the multi-level kernel of select_kernel.cuh.
+//
+// Same arithmetic contract as select_kernel.cuh: weights as 32-bit fixed point (exact sums
+// whatever the order; duplicates of a training sample merge by landing in the same slot),
+// utils.py:72-81 in float32 on the three entries (pred, e, succ) around the crossing.
+//
+// What changes is the amount of work per member and the number of block barriers per row:
+//
+//   pass 1   ONE shared-memory atomic per member: weight histogram over NB buckets of the
+//            rank axis (bucket = rank >> shift1).
+//   scan     block scan of the bucket weights, kept in registers (BPT per thread).  Every
+//            thread then looks for the requested percentiles among its own buckets -- no
+//            binary searches, no dependent shared-memory chains:
+//              bq = bucket where the running weight reaches tau = ceil(q/100 * total)
+//              bp = last non-empty bucket before bq, bn = first non-empty bucket after bq
+//            (bp / bn hold the neighbours of the crossing entry when it is the first / last
+//            entry of bq).  A 16-bit table entry per bucket says which slot arrays it feeds.
+//   pass 2   members are streamed again (L1 / L2 hits); a member whose bucket feeds nothing
+//            costs a shift, a 16-bit shared load and a test.  The few others are added to
+//            the slot arrays [bp | bq | bn] of their percentile(s) at single-rank resolution.
+//   select   one WARP per percentile scans its bq slots (<= 512, four 128-bit loads per
+//            lane), finds the crossing entry e, its neighbours inside bq or, failing that,
+//            the largest rank of bp / the smallest rank of bn; lane 0 interpolates.  The other
+//            warps are already in pass 1 of the CTA's next row.
+//
+// Six block barriers per row; histogram, table and slots are returned to zero by the
+// threads that read them, so there is no clearing phase.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "quantile_kernel.cuh"
+#include "select_kernel.cuh"
+
+namespace qf {
+
+constexpr int kSelect2QB = 4;                           // percentiles per pass 2
+constexpr int kSelect2SlotBits = 9;                     // a bucket spans <= 512 ranks
+constexpr int kSelect2Threads = 256;
+constexpr int kSelect2CtasPerSm = 5;
+
+__host__ __device__ constexpr int select2_slots(int shift1) { return (1 << shift1) < 4 ? 4 : (1 << shift1); }
+
+__host__ __device__ inline int select2_seg_stride(int T) { return (T + 1) & ~1; }   // pairs per seg buffer (16-byte multiple)
+
+__host__ __device__ inline size_t select2_kernel_smem(int log2nb, int shift1, int T) {
+    const size_t nb = static_cast<size_t>(1) << log2nb;
+    return nb * 4 + nb * 2 + static_cast<size_t>(kSelect2QB) * 3 * select2_slots(shift1) * 4 +
+           2 * static_cast<size_t>(select2_seg_stride(T)) * 8;
+}
+
+// shared-memory accesses by 32-bit shared address (no generic -> shared conversion in the loops)
+__device__ __forceinline__ void red_add_shared(uint32_t addr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared_u16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 ld_shared_v2(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+
+// f(rank, weight bits, valid) for every member of the row; seg_s = shared address of the row's
+// T (member start, member count) pairs.  4 lanes per leaf list, each lane one aligned 128-bit
+// load = two members, i.e. 8 members per leaf and load instruction (the window starts at the
+// even index at or below the list's first member; entries outside the list come with
+// valid == false).  Two lists in flight per lane.  No barriers.
+template <int THREADS, typename F>
+__device__ __forceinline__ void for_each_member_pair(uint32_t seg_s, const uint2* __restrict__ members, int T, F f) {
+    constexpr int GROUPS = THREADS / 4;
+    const int group = threadIdx.x >> 2;
+    const uint32_t sub2 = (threadIdx.x & 3) * 2;
+    for (int t0 = group; t0 < T; t0 += 2 * GROUPS) {
+        const int t1 = t0 + GROUPS;
+        const uint2 s0 = ld_shared_v2(seg_s + t0 * 8);
+        const uint2 s1 = (t1 < T) ? ld_shared_v2(seg_s + t1 * 8) : make_uint2(0u, 0u);
+        const uint32_t end0 = s0.x + s0.y, end1 = s1.x + s1.y;
+        uint32_t i0 = (s0.x & ~1u) + sub2, i1 = (s1.x & ~1u) + sub2;
+        uint4 a = make_uint4(0u, 0u, 0u, 0u), b = make_uint4(0u, 0u, 0u, 0u);
+        if (i0 < end0) a = __ldg(reinterpret_cast<const uint4*>(members + i0));
+        if (i1 < end1) b = __ldg(reinterpret_cast<const uint4*>(members + i1));
+        f(a.x, a.y, i0 >= s0.x && i0 < end0);
+        f(a.z, a.w, i0 + 1 < end0);
+        f(b.x, b.y, i1 >= s1.x && i1 < end1);
+        f(b.z, b.w, i1 + 1 < end1);
+        for (i0 += 8; i0 < end0; i0 += 8) {             // long lists: the rest
+            const uint4 c = __ldg(reinterpret_cast<const uint4*>(members + i0));
+            f(c.x, c.y, true);
+            f(c.z, c.w, i0 + 1 < end0);
+        }
+        for (i1 += 8; i1 < end1; i1 += 8) {
+            const uint4 c = __ldg(reinterpret_cast<const uint4*>(members + i1));
+            f(c.x, c.y, true);
+            f(c.z, c.w, i1 + 1 < end1);
+        }
+    }
+}
+
+template <int LOG2NB>
+__global__ void __launch_bounds__(kSelect2Threads, (LOG2NB == 11) ? kSelect2CtasPerSm : 4)
+quantile_select2_kernel(const QuantileParams p, const __grid_constant__ QuantileList ql, const float fx_scale,
+                        const int shift1) {
+    constexpr int THREADS = kSelect2Threads;
+    constexpr int NB = 1 << LOG2NB;
+    constexpr int BPT = NB / THREADS;                   // buckets scanned per thread
+    constexpr int NW = THREADS / 32;
+    constexpr int QB = kSelect2QB;
+    constexpr uint32_t NONE = 0xffffffffu;
+    static_assert(BPT % 4 == 0 && QB <= NW && 3 * QB <= 16, "layout");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* h1 = reinterpret_cast<uint32_t*>(smem_raw);          // [NB] bucket weights (zero between rows)
+    uint32_t* tbl32 = h1 + NB;                                     // [NB] x 16 bits: slot arrays a bucket feeds (zero between passes)
+    uint32_t* l2 = tbl32 + NB / 2;                                 // [QB][3][SL] slots: bp | bq | bn (zero between passes)
+    __shared__ uint32_t s_red[NW];
+    __shared__ uint32_t s_total;
+    // per percentile of the call
+    __shared__ uint32_t s_tau[kSelectMaxQ];             // target running weight
+    __shared__ uint32_t s_b[kSelectMaxQ][3];            // buckets bp, bq, bn (NONE: no such bucket)
+    __shared__ uint32_t s_base[kSelectMaxQ], s_upto[kSelectMaxQ];   // running weight before / after bq
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int SL = select2_slots(shift1);               // slots per bucket (padded to one 128-bit chunk)
+    const uint32_t slot_mask = (1u << shift1) - 1u;
+    const int nch = SL >> 2;                            // 128-bit chunks per slot array
+
+    const int seg_stride = select2_seg_stride(p.T);
+    uint2* segbuf = reinterpret_cast<uint2*>(l2 + QB * 3 * SL);    // [2][seg_stride] (start, count) of this row / the next
+    // 32-bit shared addresses of the arrays, passed through shared memory once: the compiler
+    // then keeps them in registers instead of re-deriving them in front of every access
+    __shared__ uint32_t s_addr[4];
+    if (tid == 0) {
+        s_addr[0] = static_cast<uint32_t>(__cvta_generic_to_shared(h1));
+        s_addr[1] = static_cast<uint32_t>(__cvta_generic_to_shared(tbl32));
+        s_addr[2] = static_cast<uint32_t>(__cvta_generic_to_shared(l2));
+        s_addr[3] = static_cast<uint32_t>(__cvta_generic_to_shared(segbuf));
+    }
+    __syncthreads();
+    const uint32_t h1_s = s_addr[0], tbl_s = s_addr[1], l2_s = s_addr[2], seg_s = s_addr[3];
+
+    auto mark = [&](int q, int which, uint32_t b) {     // bucket b feeds slot array 3 * (q % QB) + which
+        atomicOr(&tbl32[b >> 1], (1u << (3 * (q % QB) + which)) << (16 * (b & 1)));
+    };
+
+    // shared state starts at zero and every row leaves it at zero
+    for (int i = tid; i < NB + NB / 2 + QB * 3 * SL; i += THREADS) h1[i] = 0u;
+    const int64_t n_work = p.row_list ? static_cast<int64_t>(*p.row_count) : p.n;
+    auto row_of = [&](int64_t work) -> int64_t {
+        return p.row_list ? static_cast<int64_t>(p.row_list[work]) : work;
+    };
+    if (blockIdx.x < n_work) {                          // leaf lists of the CTA's first row
+        const uint2* __restrict__ seg = p.seg + row_of(blockIdx.x) * p.T;
+        for (int t = tid; t < p.T; t += THREADS) segbuf[t] = seg[t];
+    }
+    __syncthreads();
+
+    int par = 0;                                        // seg buffer of the current row
+    for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x, par ^= 1) {
+        const int64_t row = row_of(work);
+        const uint32_t seg_cur = seg_s + par * seg_stride * 8;
+        // the next row's leaf lists are fetched now and parked in the other buffer after B1
+        // (that buffer was last read before the previous row's B6)
+        const int64_t work_next = work + gridDim.x;
+        const uint2* __restrict__ seg_next = p.seg + (work_next < n_work ? row_of(work_next) : row) * p.T;
+        uint2 pre[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int t = tid + k * THREADS;
+            pre[k] = (t < p.T) ? seg_next[t] : make_uint2(0u, 0u);
+        }
+
+        // pass 1: bucket weights
+        for_each_member_pair<THREADS>(seg_cur, p.members, p.T, [&](uint32_t rank, uint32_t wbits, bool valid) {
+            const uint32_t w = __float2uint_rn(__fmul_rn(__uint_as_float(wbits), fx_scale));
+            if (valid) red_add_shared(h1_s + (rank >> shift1) * 4, w);      // w == 0 (utils.py:55-57) changes nothing
+        });
+        __syncthreads();                                // B1
+        {
+            uint2* nxt = segbuf + (par ^ 1) * seg_stride;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int t = tid + k * THREADS;
+                if (t < p.T) nxt[t] = pre[k];
+            }
+            for (int t = tid + 2 * THREADS; t < p.T; t += THREADS) nxt[t] = seg_next[t];   // T > 512
+        }
+
+        // inclusive prefix of this thread's BPT consecutive buckets, in registers; the
+        // histogram goes back to zero
+        uint32_t c[BPT];
+#pragma unroll
+        for (int k = 0; k < BPT / 4; ++k) {
+            const uint4 x = reinterpret_cast<const uint4*>(h1)[tid * (BPT / 4) + k];
+            c[4 * k] = x.x; c[4 * k + 1] = x.y; c[4 * k + 2] = x.z; c[4 * k + 3] = x.w;
+            reinterpret_cast<uint4*>(h1)[tid * (BPT / 4) + k] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        uint32_t mine = 0;
+#pragma unroll
+        for (int k = 0; k < BPT; ++k) mine += c[k];
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += u;
+        }
+        if (lane == 31) s_red[warp] = incl;
+        __syncthreads();                                // B2
+        uint32_t run0 = incl - mine;                    // running weight before this thread's buckets
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const uint32_t v = s_red[w];
+            run0 += (w < warp) ? v : 0u;
+            total += v;
+        }
+        if (total == 0u) {                              // no member with a non-zero weight: cannot happen for a fitted forest
+            double* __restrict__ out = p.out + (p.order ? static_cast<int64_t>(__ldg(p.order + row)) : row) * p.ldo;
+            for (int qi = tid; qi < p.Q; qi += THREADS) out[qi] = __longlong_as_double(0x7ff8000000000000LL);
+            __syncthreads();                            // s_red is rewritten by the next row
+            continue;
+        }
+        {
+            uint32_t run = run0;
+#pragma unroll
+            for (int k = 0; k < BPT; ++k) { run += c[k]; c[k] = run; }
+        }
+        if (tid < p.Q) {
+            const double t = ceil(ql.q[tid] * static_cast<double>(total) / 100.0);
+            s_tau[tid] = static_cast<uint32_t>(fmin(fmax(t, 1.0), static_cast<double>(total)));
+            s_b[tid][0] = NONE;
+            s_b[tid][2] = NONE;
+        }
+        if (tid == 0) s_total = total;
+        __syncthreads();                                // B3
+
+        // bq: the bucket in which the running weight reaches tau
+        for (int q = 0; q < p.Q; ++q) {
+            const uint32_t tau = s_tau[q];
+            if (run0 < tau && tau <= c[BPT - 1]) {      // exactly one thread
+                int k = 0;
+                uint32_t before = run0;
+#pragma unroll
+                for (int j = 0; j < BPT - 1; ++j)
+                    if (c[j] < tau) { k = j + 1; before = c[j]; }
+                uint32_t upto = c[0];
+#pragma unroll
+                for (int j = 1; j < BPT; ++j)
+                    if (j == k) upto = c[j];
+                const uint32_t b = static_cast<uint32_t>(tid * BPT + k);
+                s_b[q][1] = b;
+                s_base[q] = before;
+                s_upto[q] = upto;
+                if (q < QB) mark(q, 1, b);              // first batch: marked here, later ones below
+            }
+        }
+        __syncthreads();                                // B4
+
+        // bp: last non-empty bucket before bq; bn: first non-empty bucket after bq
+        for (int q = 0; q < p.Q; ++q) {
+            const uint32_t base = s_base[q], upto = s_upto[q];
+            if (base != 0u && run0 < base && base <= c[BPT - 1]) {      // first bucket whose prefix reaches base
+                int k = 0;
+#pragma unroll
+                for (int j = 0; j < BPT - 1; ++j)
+                    if (c[j] < base) k = j + 1;
+                const uint32_t b = static_cast<uint32_t>(tid * BPT + k);
+                s_b[q][0] = b;
+                if (q < QB) mark(q, 0, b);
+            }
+            if (upto != total && run0 <= upto && upto < c[BPT - 1]) {   // first bucket whose prefix exceeds upto
+                int k = 0;
+#pragma unroll
+                for (int j = 0; j < BPT - 1; ++j)
+                    if (c[j] <= upto) k = j + 1;
+                const uint32_t b = static_cast<uint32_t>(tid * BPT + k);
+                s_b[q][2] = b;
+                if (q < QB) mark(q, 2, b);
+            }
+        }
+        __syncthreads();                                // B5
+
+        for (int q0 = 0; q0 < p.Q; q0 += QB) {
+            const int nqb = min(QB, p.Q - q0);
+            if (q0 > 0) {                               // later batches: mark their buckets now
+                __syncthreads();                        //   (the previous batch is done with table and slots)
+                if (tid < 3 * nqb) {
+                    const uint32_t b = s_b[q0 + tid / 3][tid % 3];
+                    if (b != NONE) mark(tid / 3, tid % 3, b);
+                }
+                __syncthreads();
+            }
+
+            // pass 2: members of marked buckets -> slot arrays at single-rank resolution
+            for_each_member_pair<THREADS>(seg_cur, p.members, p.T, [&](uint32_t rank, uint32_t wbits, bool valid) {
+                uint32_t code = valid ? ld_shared_u16(tbl_s + (rank >> shift1) * 2) : 0u;
+                if (code) {
+                    const uint32_t w = __float2uint_rn(__fmul_rn(__uint_as_float(wbits), fx_scale));
+                    const uint32_t dst = l2_s + (rank & slot_mask) * 4;
+                    do {
+                        const int a = __ffs(code) - 1;
+                        code &= code - 1u;
+                        red_add_shared(dst + a * SL * 4, w);
+                    } while (code);
+                }
+            });
+            __syncthreads();                            // B6
+            if (tid < 3 * nqb) {                        // table back to zero (next marks: after the next row's B3)
+                const uint32_t b = s_b[q0 + tid / 3][tid % 3];
+                if (b != NONE) atomicAnd(&tbl32[b >> 1], ~(0xffffu << (16 * (b & 1))));
+            }
+
+            // select: warp w takes percentile q0 + w
+            if (warp < nqb) {
+                const int q = q0 + warp;
+                uint32_t* L = l2 + warp * 3 * SL;
+                uint4* M4 = reinterpret_cast<uint4*>(L + SL);
+                const uint32_t tau = s_tau[q];
+                const uint32_t bp = s_b[q][0], bq = s_b[q][1], bn = s_b[q][2];
+                uint32_t run = s_base[q];
+                uint4 v[4];
+                uint32_t e_loc = NONE, We = 0u, Ce = 0u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int ch = j * 32 + lane;
+                    v[j] = make_uint4(0u, 0u, 0u, 0u);
+                    if (j * 32 < nch) {                  // warp-uniform
+                        if (ch < nch) v[j] = M4[ch];
+                        const uint32_t s4 = v[j].x + v[j].y + v[j].z + v[j].w;
+                        uint32_t in = s4;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const uint32_t u = __shfl_up_sync(0xffffffffu, in, d);
+                            if (lane >= d) in += u;
+                        }
+                        uint32_t before = run + in - s4;
+                        if (before < tau && before + s4 >= tau) {           // the crossing is in this chunk
+                            const uint32_t vv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                            bool got = false;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const uint32_t after = before + vv[i];
+                                if (!got && after >= tau) { got = true; e_loc = static_cast<uint32_t>(4 * ch + i); We = vv[i]; Ce = after; }
+                                before = after;
+                            }
+                        }
+                        run += __shfl_sync(0xffffffffu, in, 31);
+                    }
+                }
+                const uint32_t who = __ballot_sync(0xffffffffu, e_loc != NONE);
+                const int src = __ffs(who) - 1;         // exactly one lane (base < tau <= weight up to bq)
+                const uint32_t e = __shfl_sync(0xffffffffu, e_loc, src);
+                We = __shfl_sync(0xffffffffu, We, src);
+                Ce = __shfl_sync(0xffffffffu, Ce, src);
+                // neighbours of e inside bq: last non-empty slot before (as slot + 1), first after
+                uint32_t pin = 0u, sin = NONE;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t s0 = static_cast<uint32_t>(4 * (j * 32 + lane));
+                    const uint32_t vv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (vv[i] != 0u && s0 + i < e) pin = max(pin, s0 + i + 1u);
+                        if (vv[i] != 0u && s0 + i > e) sin = min(sin, s0 + i);
+                    }
+                }
+                pin = __reduce_max_sync(0xffffffffu, pin);
+                sin = __reduce_min_sync(0xffffffffu, sin);
+                uint32_t rp = NONE, rs = NONE, Wp = 0u, Ws = 0u;            // ranks and merged weights of pred / succ
+                if (pin != 0u) {
+                    rp = (bq << shift1) + pin - 1u;
+                    Wp = L[SL + pin - 1u];
+                } else if (bp != NONE) {                // largest rank of bp
+                    uint32_t mx = 0u;
+                    for (int ch = lane; ch < nch; ch += 32) {
+                        const uint4 x = reinterpret_cast<const uint4*>(L)[ch];
+                        if (x.x) mx = max(mx, 4u * ch + 1u);
+                        if (x.y) mx = max(mx, 4u * ch + 2u);
+                        if (x.z) mx = max(mx, 4u * ch + 3u);
+                        if (x.w) mx = max(mx, 4u * ch + 4u);
+                    }
+                    mx = __reduce_max_sync(0xffffffffu, mx);
+                    rp = (bp << shift1) + mx - 1u;
+                    Wp = L[mx - 1u];
+                }
+                if (sin != NONE) {
+                    rs = (bq << shift1) + sin;
+                    Ws = L[SL + sin];
+                } else if (bn != NONE) {                // smallest rank of bn
+                    uint32_t mn = NONE;
+                    for (int ch = lane; ch < nch; ch += 32) {
+                        const uint4 x = reinterpret_cast<const uint4*>(L + 2 * SL)[ch];
+                        if (x.w) mn = min(mn, 4u * ch + 3u);
+                        if (x.z) mn = min(mn, 4u * ch + 2u);
+                        if (x.y) mn = min(mn, 4u * ch + 1u);
+                        if (x.x) mn = min(mn, 4u * ch);
+                    }
+                    mn = __reduce_min_sync(0xffffffffu, mn);
+                    rs = (bn << shift1) + mn;
+                    Ws = L[2 * SL + mn];
+                }
+                __syncwarp();
+                for (int ch = lane; ch < 3 * nch; ch += 32)                  // slots back to zero
+                    reinterpret_cast<uint4*>(L)[ch] = make_uint4(0u, 0u, 0u, 0u);
+                if (lane == 0) {                        // utils.py:69-81 on (pred, e, succ), float32
+                    const double qv = ql.q[q];
+                    const uint32_t total_w = s_total;
+                    const float inv = __fdiv_rn(1.0f, fx_scale);
+                    const float s = __fdiv_rn(100.0f, __fmul_rn(static_cast<float>(total_w), inv));   // utils.py:69,72
+                    const uint32_t re = (bq << shift1) + e;
+                    const float a_e = __ldg(p.y_sorted + re);
+                    const float p_e = plotting_position(s, __fmul_rn(static_cast<float>(Ce), inv),
+                                                        __fmul_rn(static_cast<float>(We), inv));
+                    float result = a_e;
+                    if (static_cast<double>(p_e) < qv) {                    // interval (e, succ)
+                        if (rs != NONE) {               // else q lies beyond the last entry: a_last (utils.py:74-75)
+                            const float a_s = __ldg(p.y_sorted + rs);
+                            const float p_s = plotting_position(s, __fmul_rn(static_cast<float>(Ce + Ws), inv),
+                                                                __fmul_rn(static_cast<float>(Ws), inv));
+                            const float frac = __fdiv_rn(__fsub_rn(static_cast<float>(qv), p_e), __fsub_rn(p_s, p_e));
+                            result = __fadd_rn(a_e, __fmul_rn(frac, __fsub_rn(a_s, a_e)));
+                        }
+                    } else if (rp != NONE) {            // interval (pred, e); else before the first entry: a_0 (utils.py:76-77)
+                        const float a_p = __ldg(p.y_sorted + rp);
+                        const float p_p = plotting_position(s, __fmul_rn(static_cast<float>(Ce - We), inv),
+                                                            __fmul_rn(static_cast<float>(Wp), inv));
+                        const float frac = __fdiv_rn(__fsub_rn(static_cast<float>(qv), p_p), __fsub_rn(p_e, p_p));
+                        result = __fadd_rn(a_p, __fmul_rn(frac, __fsub_rn(a_e, a_p)));
+                    }
+                    double* __restrict__ out = p.out + (p.order ? static_cast<int64_t>(__ldg(p.order + row)) : row) * p.ldo;
+                    out[q] = static_cast<double>(result);
+                }
+            }
+        }   // percentile batches
+    }   // rows
+}
+
+}  // namespace qf

@@ -259,7 +259,11 @@ def test_fast_mode_large_member_sets(kind, msl, depth, T):
     assert_allclose(fast, exact, rtol=1e-4, atol=1e-4 * np.abs(y).max())
     assert_array_equal(fast[:, [0, -1]], exact[:, [0, -1]])
     est._device_forest.set_option("select_bits", 4)              # same through several refinement levels
+    assert_array_equal(est.predict(X[N:], quantile=qs), fast)    #   (multi-level kernel, select_kernel.cuh)
+    est._device_forest.set_option("select_bits", 10)
+    est._device_forest.set_option("select_impl", 1)              # multi-level kernel, one level
     assert_array_equal(est.predict(X[N:], quantile=qs), fast)
+    est._device_forest.set_option("select_impl", 0)
     print("fast vs exact: max abs diff %.3g (|y| max %.3g), members/row %.0f" % (
         np.abs(fast - exact).max(), np.abs(y).max(), est._flat.expected_row_members))
 
