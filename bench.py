@@ -329,9 +329,14 @@ def run_b200(args, rank, world, local_rank):
                     "algorithmic_bytes": nbytes, "ms_per_launch": round(ms, 4)}
 
         plan = dev.plan(n)                                                  # which kernels the library ran
-        k2_name = ("quantile_warp_kernel<%d>" % plan["warp_elems"]) if plan["warp_elems"] else (
-            "%s<%d>" % ("quantile_select_kernel" if (args.mode == "fast" and Q <= 16) else "quantile_bucket_kernel",
-                        plan["s1_threads"]))
+        if plan["warp_elems"]:
+            k2_name = "quantile_warp_kernel<%d>" % plan["warp_elems"]
+        elif args.mode == "fast" and Q <= 16:
+            nbits = max(1, int(flat.n_train - 1).bit_length())
+            k2_name = ("quantile_select2_kernel<%d>" % (11 if nbits <= 20 else 12)) if (
+                nbits <= 21 and T <= 1024) else ("quantile_select_kernel<%d>" % plan["s1_threads"])
+        else:
+            k2_name = "quantile_bucket_kernel<%d>" % plan["s1_threads"]
         r1 = roof("apply_kernel", bytes_k1, k1_ms)
         r2 = roof(k2_name, bytes_k2, k2_ms)
         line = {

@@ -156,7 +156,7 @@ int qf_forest_predict_mean(qf_forest* f, const float* X_dev, int64_t n_rows, int
 
 /* End-to-end variant of qf_forest_predict_quantiles on HOST buffers: chunks the rows,
  * copies each chunk host->device, runs the kernels and copies the result back,
- * double-buffered on two internal streams.  X_host / out_host should be pinned for
+ * pipelined over three internal streams (H2D, kernels, D2H) and a ring of chunk buffers.  X_host / out_host should be pinned for
  * full PCIe bandwidth (pageable memory works, slower).  Synchronous: returns when
  * out_host is complete.  chunk_rows <= 0 picks a default. */
 int qf_forest_predict_quantiles_host(qf_forest* f, const float* X_host, int64_t n_rows,

@@ -2,17 +2,20 @@
 
 Import as ``skgarden_b200`` (the shim ``skgarden_b200.py`` at the repo root maps the
 name to this directory).  Public surface = the reference's for this path
-(skgarden/quantile/__init__.py:1-10, forests only):
+(skgarden/quantile/__init__.py:1-10):
 
-    RandomForestQuantileRegressor, ExtraTreesQuantileRegressor
+    RandomForestQuantileRegressor, ExtraTreesQuantileRegressor,
+    DecisionTreeQuantileRegressor, ExtraTreeQuantileRegressor
 
 plus the lower-level pieces the estimators are made of: ``flatten_forest`` /
 ``FlatForest`` (host layout), ``DeviceForest`` (HBM-resident forest + kernel calls).
 """
 from .ensemble import ExtraTreesQuantileRegressor, RandomForestQuantileRegressor
 from .flatten import FlatForest, bootstrap_counts, flatten_forest
+from .tree import DecisionTreeQuantileRegressor, ExtraTreeQuantileRegressor
 
-__all__ = ["RandomForestQuantileRegressor", "ExtraTreesQuantileRegressor", "FlatForest",
+__all__ = ["RandomForestQuantileRegressor", "ExtraTreesQuantileRegressor",
+           "DecisionTreeQuantileRegressor", "ExtraTreeQuantileRegressor", "FlatForest",
            "flatten_forest", "bootstrap_counts", "DeviceForest"]
 
 

@@ -41,12 +41,18 @@ struct DeviceGuard {
     }
 };
 
-struct HostPipe {                 // per-slot buffers of the host-buffer path
-    cudaStream_t stream = nullptr;
-    float* x = nullptr;
-    double* out = nullptr;
+// Host-buffer path: three streams (H2D, kernels, D2H) over a ring of kPipeSlots chunk buffers.
+// The copies of one chunk run while the kernels of its neighbours do; the kernels themselves
+// stay on ONE stream, chunk after chunk, and share one workspace.
+constexpr int kPipeSlots = 4;
+struct HostPipe {
+    cudaStream_t h2d = nullptr, compute = nullptr, d2h = nullptr;
+    float* x[kPipeSlots] = {};
+    double* out[kPipeSlots] = {};
+    cudaEvent_t x_ready[kPipeSlots] = {}, computed[kPipeSlots] = {}, out_free[kPipeSlots] = {};
+    int64_t x_bytes = 0, out_bytes = 0;     // per slot
     void* ws = nullptr;
-    int64_t x_bytes = 0, out_bytes = 0, ws_bytes = 0;
+    int64_t ws_bytes = 0;
 };
 
 }  // namespace
@@ -63,6 +69,7 @@ struct qf_forest {
     float* d_y_sorted = nullptr;
     double* d_values = nullptr;
     int64_t device_bytes = 0;
+    std::vector<uint32_t> tree_max_leaf;   // members of the largest leaf of every tree
     int sm_count = 148;
     // options (0 = auto where noted)
     int apply_row_warps = 0;      // warps along rows per CTA (0 auto)
@@ -79,7 +86,7 @@ struct qf_forest {
     int dense_ctas = 0;           // 0 = auto
     // counters
     int launches = 0;
-    HostPipe pipe[2];
+    HostPipe pipe;
     // per-kernel CUDA-event timing of the most recent call (option "profile")
     int profile = 0;
     std::vector<cudaEvent_t> event_pool;
@@ -339,18 +346,33 @@ int launch_select_kernel(const qf_forest* f, unsigned grid, const qf::QuantilePa
     int nbits = 0;                                      // ranks are < 2^nbits
     while ((int64_t(1) << nbits) < f->N) ++nbits;
     // training sets of up to 2M samples: one refinement level is enough (select2_kernel.cuh)
-    if (f->select_impl == 0 && f->select_bits == qf::kSelectL2Bits && nbits <= 12 + qf::kSelect2SlotBits) {
-        const int log2nb = nbits <= 11 + qf::kSelect2SlotBits ? 11 : 12;
-        const int shift1 = std::max(0, nbits - log2nb);
-        const size_t smem2 = qf::select2_kernel_smem(log2nb, shift1, f->T);
-        const unsigned ctas = static_cast<unsigned>(f->sm_count) * (log2nb == 11 ? qf::kSelect2CtasPerSm : 4);
-        auto run2 = [&](auto kernel) -> int {
-            int rc = set_smem(kernel, smem2);
-            if (rc != QF_OK) return rc;
-            kernel<<<std::min(grid, ctas), qf::kSelect2Threads, smem2, st>>>(qp, ql, fx_scale, shift1);
-            return QF_OK;
-        };
-        return log2nb == 11 ? run2(qf::quantile_select2_kernel<11>) : run2(qf::quantile_select2_kernel<12>);
+    if (f->select_impl == 0 && f->select_bits == qf::kSelectL2Bits && nbits <= 12 + qf::kSelect2SlotBits &&
+        f->T <= qf::kSelect2MaxIPT * qf::kSelect2Threads && f->n_members < (int64_t(1) << 31) &&
+        static_cast<int>(f->tree_max_leaf.size()) == f->T) {
+        // pair-table segment of every warp: its leaves are 32 * ipt consecutive trees, a leaf of c
+        // members spans at most c / 2 + 1 aligned pairs
+        qf::Select2Layout lay;
+        const int ipt = (f->T + qf::kSelect2Threads - 1) / qf::kSelect2Threads;
+        uint64_t pairs = 0;
+        for (int w = 0; w < qf::kSelect2Warps; ++w) {
+            lay.warp_off[w] = static_cast<uint32_t>(pairs);
+            for (int t = w * 32 * ipt; t < std::min(f->T, (w + 1) * 32 * ipt); ++t)
+                pairs += f->tree_max_leaf[t] / 2 + 1;
+        }
+        lay.warp_off[qf::kSelect2Warps] = static_cast<uint32_t>(pairs);
+        if (pairs <= static_cast<uint64_t>(qf::kSelect2MaxPairs)) {
+            const int log2nb = nbits <= 11 + qf::kSelect2SlotBits ? 11 : 12;
+            const int shift1 = std::max(0, nbits - log2nb);
+            const size_t smem2 = qf::select2_kernel_smem(log2nb, shift1, static_cast<uint32_t>(pairs));
+            const unsigned ctas = static_cast<unsigned>(f->sm_count) * 4;
+            auto run2 = [&](auto kernel) -> int {
+                int rc = set_smem(kernel, smem2);
+                if (rc != QF_OK) return rc;
+                kernel<<<std::min(grid, ctas), qf::kSelect2Threads, smem2, st>>>(qp, ql, lay, fx_scale, shift1);
+                return QF_OK;
+            };
+            return log2nb == 11 ? run2(qf::quantile_select2_kernel<11>) : run2(qf::quantile_select2_kernel<12>);
+        }
     }
     const int threads = f->T <= 128 ? 128 : 256;        // 4 lanes per leaf list
     auto run = [&](auto kernel) -> int {
@@ -555,6 +577,17 @@ int qf_forest_create(const qf_forest_desc* d, qf_forest** out) {
     if (rc == QF_OK) rc = upload(reinterpret_cast<void**>(&f->d_y_sorted), d->y_sorted, d->n_train * 4);
     if (rc == QF_OK && d->leaf_values)
         rc = upload(reinterpret_cast<void**>(&f->d_values), d->leaf_values, d->n_nodes * 8);
+    if (rc == QF_OK) {                                  // largest leaf of every tree (sizes the pair table of select2)
+        uint32_t* d_max = nullptr;
+        cudaError_t e = cudaMalloc(&d_max, static_cast<size_t>(d->n_trees) * 4);
+        if (e == cudaSuccess) {
+            qf::tree_max_leaf_kernel<<<d->n_trees, 256>>>(f->d_nodes, f->d_roots, f->n_nodes, f->T, d_max);
+            f->tree_max_leaf.resize(d->n_trees);
+            e = cudaMemcpy(f->tree_max_leaf.data(), d_max, static_cast<size_t>(d->n_trees) * 4, cudaMemcpyDeviceToHost);
+            cudaFree(d_max);
+        }
+        if (e != cudaSuccess) rc = qf::fail(QF_ERR_CUDA, std::string("qf_forest_create: ") + cudaGetErrorString(e));
+    }
     if (rc != QF_OK) {
         const std::string keep = qf::last_error_slot();
         qf_forest_destroy(f);
@@ -574,11 +607,19 @@ void qf_forest_destroy(qf_forest* f) {
     cudaFree(f->d_y_sorted);
     cudaFree(f->d_values);
     for (cudaEvent_t e : f->event_pool) cudaEventDestroy(e);
-    for (HostPipe& hp : f->pipe) {
-        cudaFree(hp.x);
-        cudaFree(hp.out);
+    {
+        HostPipe& hp = f->pipe;
+        for (int s = 0; s < kPipeSlots; ++s) {
+            cudaFree(hp.x[s]);
+            cudaFree(hp.out[s]);
+            if (hp.x_ready[s]) cudaEventDestroy(hp.x_ready[s]);
+            if (hp.computed[s]) cudaEventDestroy(hp.computed[s]);
+            if (hp.out_free[s]) cudaEventDestroy(hp.out_free[s]);
+        }
         cudaFree(hp.ws);
-        if (hp.stream) cudaStreamDestroy(hp.stream);
+        if (hp.h2d) cudaStreamDestroy(hp.h2d);
+        if (hp.compute) cudaStreamDestroy(hp.compute);
+        if (hp.d2h) cudaStreamDestroy(hp.d2h);
     }
     delete f;
 }
@@ -753,55 +794,75 @@ int qf_forest_predict_quantiles_host(qf_forest* f, const float* X_host, int64_t 
     reset_call_counters(f);
     if (n == 0) return QF_OK;
     DeviceGuard guard(f->device);
-    if (chunk_rows <= 0) {
-        // at least four pipeline slots' worth of chunks, so that the copies of one chunk overlap
-        // the kernels of its neighbours; not below 16k rows (launch overhead, kernel tails)
-        chunk_rows = std::min<int64_t>(f->rows_per_chunk, std::max<int64_t>(16384, ((n + 3) / 4 + 31) / 32 * 32));
-    }
+    // measured at 100k x 20 rows: splitting below rows_per_chunk only adds per-chunk launches
+    // (1 chunk 0.74 ms, 2 chunks 0.76 ms, 4 chunks 0.91 ms); the copies overlap the kernels of
+    // neighbouring chunks once there are several full-size chunks
+    if (chunk_rows <= 0) chunk_rows = f->rows_per_chunk;
     chunk_rows = std::min(chunk_rows, n);
     const int64_t saved_chunk = f->rows_per_chunk;
     f->rows_per_chunk = chunk_rows;                       // one kernel chunk per pipeline slot
     const Plan pl = make_plan(f, chunk_rows);
     f->rows_per_chunk = saved_chunk;
     const int64_t x_bytes = chunk_rows * f->F * 4, out_bytes = chunk_rows * nq * 8;
-    const int slots = n > chunk_rows ? 2 : 1;
-    for (int s = 0; s < slots; ++s) {
-        HostPipe& hp = f->pipe[s];
-        if (!hp.stream) QF_CUDA_TRY(cudaStreamCreateWithFlags(&hp.stream, cudaStreamNonBlocking));
-        if (hp.x_bytes < x_bytes) {
-            cudaFree(hp.x); hp.x = nullptr; hp.x_bytes = 0;
-            QF_CUDA_TRY(cudaMalloc(&hp.x, x_bytes)); hp.x_bytes = x_bytes;
+    HostPipe& hp = f->pipe;
+    if (!hp.h2d) {
+        QF_CUDA_TRY(cudaStreamCreateWithFlags(&hp.h2d, cudaStreamNonBlocking));
+        QF_CUDA_TRY(cudaStreamCreateWithFlags(&hp.compute, cudaStreamNonBlocking));
+        QF_CUDA_TRY(cudaStreamCreateWithFlags(&hp.d2h, cudaStreamNonBlocking));
+        for (int s = 0; s < kPipeSlots; ++s) {
+            QF_CUDA_TRY(cudaEventCreateWithFlags(&hp.x_ready[s], cudaEventDisableTiming));
+            QF_CUDA_TRY(cudaEventCreateWithFlags(&hp.computed[s], cudaEventDisableTiming));
+            QF_CUDA_TRY(cudaEventCreateWithFlags(&hp.out_free[s], cudaEventDisableTiming));
         }
-        if (hp.out_bytes < out_bytes) {
-            cudaFree(hp.out); hp.out = nullptr; hp.out_bytes = 0;
-            QF_CUDA_TRY(cudaMalloc(&hp.out, out_bytes)); hp.out_bytes = out_bytes;
-        }
-        if (hp.ws_bytes < pl.total) {
-            cudaFree(hp.ws); hp.ws = nullptr; hp.ws_bytes = 0;
-            QF_CUDA_TRY(cudaMalloc(&hp.ws, pl.total)); hp.ws_bytes = pl.total;
-        }
-        rc = zero_dense_scratch(f, pl, hp.ws, hp.stream);
-        if (rc != QF_OK) return rc;
     }
+    if (hp.x_bytes < x_bytes) {
+        for (int s = 0; s < kPipeSlots; ++s) { cudaFree(hp.x[s]); hp.x[s] = nullptr; }
+        hp.x_bytes = 0;
+        for (int s = 0; s < kPipeSlots; ++s) QF_CUDA_TRY(cudaMalloc(&hp.x[s], x_bytes));
+        hp.x_bytes = x_bytes;
+    }
+    if (hp.out_bytes < out_bytes) {
+        for (int s = 0; s < kPipeSlots; ++s) { cudaFree(hp.out[s]); hp.out[s] = nullptr; }
+        hp.out_bytes = 0;
+        for (int s = 0; s < kPipeSlots; ++s) QF_CUDA_TRY(cudaMalloc(&hp.out[s], out_bytes));
+        hp.out_bytes = out_bytes;
+    }
+    if (hp.ws_bytes < pl.total) {
+        cudaFree(hp.ws); hp.ws = nullptr; hp.ws_bytes = 0;
+        QF_CUDA_TRY(cudaMalloc(&hp.ws, pl.total)); hp.ws_bytes = pl.total;
+    }
+    rc = zero_dense_scratch(f, pl, hp.ws, hp.compute);
+    if (rc != QF_OK) return rc;
     int total_launches = 0;
-    int slot = 0;
-    for (int64_t r0 = 0; r0 < n; r0 += chunk_rows, slot ^= 1) {
+    int64_t chunk = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += chunk_rows, ++chunk) {
         const int64_t rows = std::min(chunk_rows, n - r0);
-        HostPipe& hp = f->pipe[slots == 2 ? slot : 0];
-        // rows of X are compacted to F columns on the device (ldx may exceed F on the host)
+        const int s = static_cast<int>(chunk % kPipeSlots);
+        // H2D: the slot's X buffer is free once the kernels of the chunk that used it are done.
+        // Rows of X are compacted to F columns on the device (ldx may exceed F on the host).
+        if (chunk >= kPipeSlots) QF_CUDA_TRY(cudaStreamWaitEvent(hp.h2d, hp.computed[s], 0));
         if (ldx == f->F) {
-            QF_CUDA_TRY(cudaMemcpyAsync(hp.x, X_host + r0 * ldx, rows * f->F * 4, cudaMemcpyHostToDevice, hp.stream));
+            QF_CUDA_TRY(cudaMemcpyAsync(hp.x[s], X_host + r0 * ldx, rows * f->F * 4, cudaMemcpyHostToDevice, hp.h2d));
         } else {
-            QF_CUDA_TRY(cudaMemcpy2DAsync(hp.x, f->F * 4, X_host + r0 * ldx, ldx * 4, f->F * 4, rows,
-                                          cudaMemcpyHostToDevice, hp.stream));
+            QF_CUDA_TRY(cudaMemcpy2DAsync(hp.x[s], f->F * 4, X_host + r0 * ldx, ldx * 4, f->F * 4, rows,
+                                          cudaMemcpyHostToDevice, hp.h2d));
         }
+        QF_CUDA_TRY(cudaEventRecord(hp.x_ready[s], hp.h2d));
+        // kernels: one stream, chunk after chunk
+        QF_CUDA_TRY(cudaStreamWaitEvent(hp.compute, hp.x_ready[s], 0));
+        if (chunk >= kPipeSlots) QF_CUDA_TRY(cudaStreamWaitEvent(hp.compute, hp.out_free[s], 0));
         f->launches = 0;
-        rc = quantiles_on_stream(f, hp.x, rows, f->F, q_host, nq, hp.out, mode, pl, hp.ws, hp.ws_bytes, hp.stream);
+        rc = quantiles_on_stream(f, hp.x[s], rows, f->F, q_host, nq, hp.out[s], mode, pl, hp.ws, hp.ws_bytes, hp.compute);
         if (rc != QF_OK) return rc;
         total_launches += f->launches;
-        QF_CUDA_TRY(cudaMemcpyAsync(out_host + r0 * nq, hp.out, rows * nq * 8, cudaMemcpyDeviceToHost, hp.stream));
+        QF_CUDA_TRY(cudaEventRecord(hp.computed[s], hp.compute));
+        // D2H
+        QF_CUDA_TRY(cudaStreamWaitEvent(hp.d2h, hp.computed[s], 0));
+        QF_CUDA_TRY(cudaMemcpyAsync(out_host + r0 * nq, hp.out[s], rows * nq * 8, cudaMemcpyDeviceToHost, hp.d2h));
+        QF_CUDA_TRY(cudaEventRecord(hp.out_free[s], hp.d2h));
     }
-    for (int s = 0; s < slots; ++s) QF_CUDA_TRY(cudaStreamSynchronize(f->pipe[s].stream));
+    QF_CUDA_TRY(cudaStreamSynchronize(hp.d2h));
+    QF_CUDA_TRY(cudaStreamSynchronize(hp.compute));
     f->launches = total_launches;
     return QF_OK;
 }

@@ -8,8 +8,13 @@
 //
 // What changes is the amount of work per member and the number of block barriers per row:
 //
-//   pass 1   ONE shared-memory atomic per member: weight histogram over NB buckets of the
-//            rank axis (bucket = rank >> shift1).
+//   table    every warp owns T/8 consecutive leaves of the row.  It turns their (start, count)
+//            pairs -- fetched one row ahead into registers -- into a flat table of aligned
+//            128-bit member PAIRS (entry = even member index | "first slot is outside the
+//            list" | "second slot is outside the list"), so that both passes below run with all
+//            32 lanes busy whatever the leaf sizes (4 lanes per leaf wasted half of them).
+//   pass 1   one 128-bit load per lane and pair; ONE shared-memory atomic per member: weight
+//            histogram over NB buckets of the rank axis (bucket = rank >> shift1).
 //   scan     block scan of the bucket weights, kept in registers (BPT per thread).  Every
 //            thread then looks for the requested percentiles among its own buckets -- no
 //            binary searches, no dependent shared-memory chains:
@@ -39,16 +44,21 @@ namespace qf {
 constexpr int kSelect2QB = 4;                           // percentiles per pass 2
 constexpr int kSelect2SlotBits = 9;                     // a bucket spans <= 512 ranks
 constexpr int kSelect2Threads = 256;
-constexpr int kSelect2CtasPerSm = 5;
+constexpr int kSelect2Warps = kSelect2Threads / 32;
+constexpr int kSelect2MaxIPT = 4;                       // leaves per lane: T <= 4 * 256
+constexpr int kSelect2MaxPairs = 6144;                  // pair-table entries per CTA (24 KB)
+
+// first pair-table entry of every warp (exact upper bounds from the largest leaf of each tree)
+struct Select2Layout {
+    uint32_t warp_off[kSelect2Warps + 1];
+};
 
 __host__ __device__ constexpr int select2_slots(int shift1) { return (1 << shift1) < 4 ? 4 : (1 << shift1); }
 
-__host__ __device__ inline int select2_seg_stride(int T) { return (T + 1) & ~1; }   // pairs per seg buffer (16-byte multiple)
-
-__host__ __device__ inline size_t select2_kernel_smem(int log2nb, int shift1, int T) {
+__host__ __device__ inline size_t select2_kernel_smem(int log2nb, int shift1, uint32_t pairs) {
     const size_t nb = static_cast<size_t>(1) << log2nb;
     return nb * 4 + nb * 2 + static_cast<size_t>(kSelect2QB) * 3 * select2_slots(shift1) * 4 +
-           2 * static_cast<size_t>(select2_seg_stride(T)) * 8;
+           ((static_cast<size_t>(pairs) + 3) & ~size_t(3)) * 4;
 }
 
 // shared-memory accesses by 32-bit shared address (no generic -> shared conversion in the loops)
@@ -60,57 +70,43 @@ __device__ __forceinline__ uint32_t ld_shared_u16(uint32_t addr) {
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
     return v;
 }
-__device__ __forceinline__ uint2 ld_shared_v2(uint32_t addr) {
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 
-// f(rank, weight bits, valid) for every member of the row; seg_s = shared address of the row's
-// T (member start, member count) pairs.  4 lanes per leaf list, each lane one aligned 128-bit
-// load = two members, i.e. 8 members per leaf and load instruction (the window starts at the
-// even index at or below the list's first member; entries outside the list come with
-// valid == false).  Two lists in flight per lane.  No barriers.
-template <int THREADS, typename F>
-__device__ __forceinline__ void for_each_member_pair(uint32_t seg_s, const uint2* __restrict__ members, int T, F f) {
-    constexpr int GROUPS = THREADS / 4;
-    const int group = threadIdx.x >> 2;
-    const uint32_t sub2 = (threadIdx.x & 3) * 2;
-    for (int t0 = group; t0 < T; t0 += 2 * GROUPS) {
-        const int t1 = t0 + GROUPS;
-        const uint2 s0 = ld_shared_v2(seg_s + t0 * 8);
-        const uint2 s1 = (t1 < T) ? ld_shared_v2(seg_s + t1 * 8) : make_uint2(0u, 0u);
-        const uint32_t end0 = s0.x + s0.y, end1 = s1.x + s1.y;
-        uint32_t i0 = (s0.x & ~1u) + sub2, i1 = (s1.x & ~1u) + sub2;
-        uint4 a = make_uint4(0u, 0u, 0u, 0u), b = make_uint4(0u, 0u, 0u, 0u);
-        if (i0 < end0) a = __ldg(reinterpret_cast<const uint4*>(members + i0));
-        if (i1 < end1) b = __ldg(reinterpret_cast<const uint4*>(members + i1));
-        f(a.x, a.y, i0 >= s0.x && i0 < end0);
-        f(a.z, a.w, i0 + 1 < end0);
-        f(b.x, b.y, i1 >= s1.x && i1 < end1);
-        f(b.z, b.w, i1 + 1 < end1);
-        for (i0 += 8; i0 < end0; i0 += 8) {             // long lists: the rest
-            const uint4 c = __ldg(reinterpret_cast<const uint4*>(members + i0));
-            f(c.x, c.y, true);
-            f(c.z, c.w, i0 + 1 < end0);
-        }
-        for (i1 += 8; i1 < end1; i1 += 8) {
-            const uint4 c = __ldg(reinterpret_cast<const uint4*>(members + i1));
-            f(c.x, c.y, true);
-            f(c.z, c.w, i1 + 1 < end1);
-        }
+// f(rank, weight bits, valid) for every member behind the warp's pair table [tab_s, tab_s + 4 n):
+// two 128-bit loads in flight per lane, all lanes busy.  No barriers.
+template <typename F>
+__device__ __forceinline__ void for_each_pair(uint32_t tab_s, uint32_t n, const uint2* __restrict__ members, int lane, F f) {
+    for (uint32_t j = lane; j < n; j += 64) {
+        const uint32_t e0 = ld_shared_u32(tab_s + j * 4);
+        const bool two = j + 32 < n;
+        const uint32_t e1 = two ? ld_shared_u32(tab_s + (j + 32) * 4) : 0x80000001u;
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(members + (e0 & 0x7ffffffeu)));
+        uint4 b = make_uint4(0u, 0u, 0u, 0u);
+        if (two) b = __ldg(reinterpret_cast<const uint4*>(members + (e1 & 0x7ffffffeu)));
+        f(a.x, a.y, (e0 & 1u) == 0u);
+        f(a.z, a.w, static_cast<int32_t>(e0) >= 0);
+        f(b.x, b.y, (e1 & 1u) == 0u);
+        f(b.z, b.w, static_cast<int32_t>(e1) >= 0);
     }
 }
 
 template <int LOG2NB>
-__global__ void __launch_bounds__(kSelect2Threads, (LOG2NB == 11) ? kSelect2CtasPerSm : 4)
-quantile_select2_kernel(const QuantileParams p, const __grid_constant__ QuantileList ql, const float fx_scale,
-                        const int shift1) {
+__global__ void __launch_bounds__(kSelect2Threads, 4)
+quantile_select2_kernel(const QuantileParams p, const __grid_constant__ QuantileList ql,
+                        const __grid_constant__ Select2Layout lay, const float fx_scale, const int shift1) {
     constexpr int THREADS = kSelect2Threads;
     constexpr int NB = 1 << LOG2NB;
     constexpr int BPT = NB / THREADS;                   // buckets scanned per thread
-    constexpr int NW = THREADS / 32;
+    constexpr int NW = kSelect2Warps;
     constexpr int QB = kSelect2QB;
+    constexpr int MAXIPT = kSelect2MaxIPT;
     constexpr uint32_t NONE = 0xffffffffu;
     static_assert(BPT % 4 == 0 && QB <= NW && 3 * QB <= 16, "layout");
 
@@ -131,9 +127,8 @@ quantile_select2_kernel(const QuantileParams p, const __grid_constant__ Quantile
     const int SL = select2_slots(shift1);               // slots per bucket (padded to one 128-bit chunk)
     const uint32_t slot_mask = (1u << shift1) - 1u;
     const int nch = SL >> 2;                            // 128-bit chunks per slot array
+    uint32_t* pairtab = l2 + QB * 3 * SL;                          // [lay.warp_off[NW]] pair table, one segment per warp
 
-    const int seg_stride = select2_seg_stride(p.T);
-    uint2* segbuf = reinterpret_cast<uint2*>(l2 + QB * 3 * SL);    // [2][seg_stride] (start, count) of this row / the next
     // 32-bit shared addresses of the arrays, passed through shared memory once: the compiler
     // then keeps them in registers instead of re-deriving them in front of every access
     __shared__ uint32_t s_addr[4];
@@ -141,57 +136,80 @@ quantile_select2_kernel(const QuantileParams p, const __grid_constant__ Quantile
         s_addr[0] = static_cast<uint32_t>(__cvta_generic_to_shared(h1));
         s_addr[1] = static_cast<uint32_t>(__cvta_generic_to_shared(tbl32));
         s_addr[2] = static_cast<uint32_t>(__cvta_generic_to_shared(l2));
-        s_addr[3] = static_cast<uint32_t>(__cvta_generic_to_shared(segbuf));
+        s_addr[3] = static_cast<uint32_t>(__cvta_generic_to_shared(pairtab));
     }
+    // shared state starts at zero and every row leaves it at zero
+    for (int i = tid; i < NB + NB / 2 + QB * 3 * SL; i += THREADS) h1[i] = 0u;
     __syncthreads();
-    const uint32_t h1_s = s_addr[0], tbl_s = s_addr[1], l2_s = s_addr[2], seg_s = s_addr[3];
+    const uint32_t h1_s = s_addr[0], tbl_s = s_addr[1], l2_s = s_addr[2];
+    const uint32_t tab_s = s_addr[3] + lay.warp_off[warp] * 4;    // this warp's segment of the pair table
 
     auto mark = [&](int q, int which, uint32_t b) {     // bucket b feeds slot array 3 * (q % QB) + which
         atomicOr(&tbl32[b >> 1], (1u << (3 * (q % QB) + which)) << (16 * (b & 1)));
     };
 
-    // shared state starts at zero and every row leaves it at zero
-    for (int i = tid; i < NB + NB / 2 + QB * 3 * SL; i += THREADS) h1[i] = 0u;
+    // leaves of this lane: ipt consecutive ones; the warp owns 32 * ipt consecutive leaves
+    const int ipt = (p.T + THREADS - 1) / THREADS;
+    const int t_first = (warp * 32 + lane) * ipt;
     const int64_t n_work = p.row_list ? static_cast<int64_t>(*p.row_count) : p.n;
     auto row_of = [&](int64_t work) -> int64_t {
         return p.row_list ? static_cast<int64_t>(p.row_list[work]) : work;
     };
-    if (blockIdx.x < n_work) {                          // leaf lists of the CTA's first row
-        const uint2* __restrict__ seg = p.seg + row_of(blockIdx.x) * p.T;
-        for (int t = tid; t < p.T; t += THREADS) segbuf[t] = seg[t];
-    }
-    __syncthreads();
-
-    int par = 0;                                        // seg buffer of the current row
-    for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x, par ^= 1) {
-        const int64_t row = row_of(work);
-        const uint32_t seg_cur = seg_s + par * seg_stride * 8;
-        // the next row's leaf lists are fetched now and parked in the other buffer after B1
-        // (that buffer was last read before the previous row's B6)
-        const int64_t work_next = work + gridDim.x;
-        const uint2* __restrict__ seg_next = p.seg + (work_next < n_work ? row_of(work_next) : row) * p.T;
-        uint2 pre[2];
+    auto fetch = [&](int64_t work, uint2 (&sg)[MAXIPT]) {          // (start, count) of this lane's leaves
+        const uint2* __restrict__ seg = p.seg + (work < n_work ? row_of(work) : 0) * p.T;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int t = tid + k * THREADS;
-            pre[k] = (t < p.T) ? seg_next[t] : make_uint2(0u, 0u);
+        for (int i = 0; i < MAXIPT; ++i) {
+            const int t = t_first + i;
+            sg[i] = (work < n_work && i < ipt && t < p.T) ? seg[t] : make_uint2(0u, 0u);
         }
+    };
+    uint2 pre[MAXIPT];
+    fetch(blockIdx.x, pre);
+
+    for (int64_t work = blockIdx.x; work < n_work; work += gridDim.x) {
+        const int64_t row = row_of(work);
+
+        // pair table of this warp's leaves (warp-private: no block barrier), then the next
+        // row's leaf lists are requested
+        uint32_t n_pairs;
+        {
+            uint32_t np[MAXIPT], tot = 0;
+#pragma unroll
+            for (int i = 0; i < MAXIPT; ++i) {
+                np[i] = pre[i].y ? (((pre[i].x & 1u) + pre[i].y + 1u) >> 1) : 0u;
+                tot += np[i];
+            }
+            uint32_t incl = tot;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += u;
+            }
+            n_pairs = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t dst = tab_s + (incl - tot) * 4;
+#pragma unroll
+            for (int i = 0; i < MAXIPT; ++i) {
+                if (i < ipt) {                          // block-uniform
+                    const uint32_t end = pre[i].x + pre[i].y;
+                    uint32_t idx = pre[i].x & ~1u;
+                    if (np[i]) {                        // first pair: its first slot may precede the list
+                        st_shared_u32(dst, idx | (pre[i].x & 1u) | (idx + 1u >= end ? 0x80000000u : 0u));
+                        idx += 2, dst += 4;
+                    }
+                    for (uint32_t k = 1; k < np[i]; ++k, idx += 2, dst += 4)
+                        st_shared_u32(dst, idx | (idx + 1u >= end ? 0x80000000u : 0u));
+                }
+            }
+            __syncwarp();
+        }
+        fetch(work + gridDim.x, pre);
 
         // pass 1: bucket weights
-        for_each_member_pair<THREADS>(seg_cur, p.members, p.T, [&](uint32_t rank, uint32_t wbits, bool valid) {
+        for_each_pair(tab_s, n_pairs, p.members, lane, [&](uint32_t rank, uint32_t wbits, bool valid) {
             const uint32_t w = __float2uint_rn(__fmul_rn(__uint_as_float(wbits), fx_scale));
             if (valid) red_add_shared(h1_s + (rank >> shift1) * 4, w);      // w == 0 (utils.py:55-57) changes nothing
         });
         __syncthreads();                                // B1
-        {
-            uint2* nxt = segbuf + (par ^ 1) * seg_stride;
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const int t = tid + k * THREADS;
-                if (t < p.T) nxt[t] = pre[k];
-            }
-            for (int t = tid + 2 * THREADS; t < p.T; t += THREADS) nxt[t] = seg_next[t];   // T > 512
-        }
 
         // inclusive prefix of this thread's BPT consecutive buckets, in registers; the
         // histogram goes back to zero
@@ -299,7 +317,7 @@ quantile_select2_kernel(const QuantileParams p, const __grid_constant__ Quantile
             }
 
             // pass 2: members of marked buckets -> slot arrays at single-rank resolution
-            for_each_member_pair<THREADS>(seg_cur, p.members, p.T, [&](uint32_t rank, uint32_t wbits, bool valid) {
+            for_each_pair(tab_s, n_pairs, p.members, lane, [&](uint32_t rank, uint32_t wbits, bool valid) {
                 uint32_t code = valid ? ld_shared_u16(tbl_s + (rank >> shift1) * 2) : 0u;
                 if (code) {
                     const uint32_t w = __float2uint_rn(__fmul_rn(__uint_as_float(wbits), fx_scale));
@@ -440,6 +458,27 @@ quantile_select2_kernel(const QuantileParams p, const __grid_constant__ Quantile
             }
         }   // percentile batches
     }   // rows
+}
+
+// largest leaf (members) of every tree: block t reduces over the tree's packed nodes
+__global__ void __launch_bounds__(256)
+tree_max_leaf_kernel(const uint2* __restrict__ nodes, const uint32_t* __restrict__ roots, int64_t n_nodes, int T,
+                     uint32_t* __restrict__ out) {
+    __shared__ uint32_t red[8];
+    const int t = blockIdx.x;
+    const int64_t n0 = roots[t], n1 = (t + 1 < T) ? static_cast<int64_t>(roots[t + 1]) : n_nodes;
+    uint32_t m = 0;
+    for (int64_t i = n0 + threadIdx.x; i < n1; i += blockDim.x) {
+        const uint32_t hi = nodes[i].y;
+        if (hi & 0x80000000u) m = max(m, hi & 0x7fffffffu);
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = max(m, red[w]);
+        out[t] = m;
+    }
 }
 
 }  // namespace qf

@@ -107,7 +107,8 @@ def _tree_arrays(tree):
 
 
 def flatten_forest(trees: Sequence, train_leaves, counts, y_train, n_features: int,
-                   sorter: Optional[np.ndarray] = None, n_jobs: Optional[int] = None) -> FlatForest:
+                   sorter: Optional[np.ndarray] = None, n_jobs: Optional[int] = None,
+                   unit_weights: bool = False) -> FlatForest:
     """Flatten ``trees`` (fitted sklearn estimators, ``Tree`` objects, or anything with
     children_left/right, feature, threshold, value).
 
@@ -118,6 +119,9 @@ def flatten_forest(trees: Sequence, train_leaves, counts, y_train, n_features: i
     y_train      : (N,) training targets as given to fit (ensemble.py:83).
     sorter       : np.argsort(y_train) computed by the caller; computed here if None.
                    It is never recomputed on the device (ties are ordered by numpy).
+    unit_weights : every member weighs 1.0 instead of count / leaf count sum: the
+                   tree-level estimators (quantile/tree.py:45-47 call weighted_percentile
+                   without weights, utils.py:40-41).
     """
     L = _native.lib()
     T = len(trees)
@@ -181,6 +185,9 @@ def flatten_forest(trees: Sequence, train_leaves, counts, y_train, n_features: i
         for t in range(T):
             pack(t)
 
+    if unit_weights:
+        members &= np.uint64(0xFFFFFFFF)
+        members |= np.uint64(0x3F800000) << np.uint64(32)          # float32 1.0
     identity = bool(np.array_equal(
         node_ids, np.concatenate([np.arange(c, dtype=np.int32) for c in node_counts])))
     return FlatForest(

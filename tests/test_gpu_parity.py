@@ -78,6 +78,7 @@ def test_dense_fallback_is_identical(name, cta2_capacity):
 @pytest.mark.parametrize("opts", [
     dict(apply_row_warps=1, apply_ilp=1), dict(apply_row_warps=2, apply_ilp=2),
     dict(apply_row_warps=8, apply_ilp=8), dict(rows_per_chunk=37),
+    dict(apply_row_warps=4, apply_ilp=4),
     dict(sort_rows=0), dict(sort_rows=1), dict(sort_rows=1, rows_per_chunk=100, apply_row_warps=4),
     dict(sort_rows=1, warp_elems=0), dict(sort_rows=1, warp_elems=2, cta_capacity=64, dense_ctas=2),
     dict(warp_elems=0), dict(warp_elems=2), dict(warp_elems=4), dict(warp_elems=8),
