@@ -201,7 +201,7 @@ def load_traffic(config):
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(path):
         try:
-            return json.load(open(path)).get(config, {})
+            return {k: v for k, v in json.load(open(path)).get(config, {}).items() if not k.startswith("_")}
         except Exception:
             pass
     return {}

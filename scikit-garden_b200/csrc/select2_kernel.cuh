@@ -79,23 +79,15 @@ __device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-// f(rank, weight bits, valid) for every member behind the warp's pair table [tab_s, tab_s + 4 n):
-// two 128-bit loads in flight per lane, all lanes busy.  No barriers.
-template <typename F>
-__device__ __forceinline__ void for_each_pair(uint32_t tab_s, uint32_t n, const uint2* __restrict__ members, int lane, F f) {
-    for (uint32_t j = lane; j < n; j += 64) {
-        const uint32_t e0 = ld_shared_u32(tab_s + j * 4);
-        const bool two = j + 32 < n;
-        const uint32_t e1 = two ? ld_shared_u32(tab_s + (j + 32) * 4) : 0x80000001u;
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(members + (e0 & 0x7ffffffeu)));
-        uint4 b = make_uint4(0u, 0u, 0u, 0u);
-        if (two) b = __ldg(reinterpret_cast<const uint4*>(members + (e1 & 0x7ffffffeu)));
-        f(a.x, a.y, (e0 & 1u) == 0u);
-        f(a.z, a.w, static_cast<int32_t>(e0) >= 0);
-        f(b.x, b.y, (e1 & 1u) == 0u);
-        f(b.z, b.w, static_cast<int32_t>(e1) >= 0);
-    }
+// red.shared.add.u32 [addr], v  executed only when `skip` is zero (predicated, no branch)
+__device__ __forceinline__ void red_add_shared_unless(uint32_t addr, uint32_t v, uint32_t skip) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}"
+                 ::"r"(addr), "r"(v), "r"(skip) : "memory");
 }
+
+// Pair-table entry: bits 0..29 = index of the aligned 128-bit member pair (member index / 2),
+// bit 30 = the pair's first slot lies outside the leaf list, bit 31 = its second slot does.
+constexpr uint32_t kPairSkip0 = 0x40000000u, kPairSkip1 = 0x80000000u, kPairIndex = 0x3fffffffu;
 
 template <int LOG2NB>
 __global__ void __launch_bounds__(kSelect2Threads, 4)
@@ -132,7 +124,13 @@ quantile_select2_kernel(const QuantileParams p, const __grid_constant__ Quantile
     // 32-bit shared addresses of the arrays, passed through shared memory once: the compiler
     // then keeps them in registers instead of re-deriving them in front of every access
     __shared__ uint32_t s_addr[4];
+    __shared__ uint64_t s_members;
+    __shared__ float s_scale;
+    __shared__ uint32_t s_shift;
     if (tid == 0) {
+        s_members = reinterpret_cast<uint64_t>(p.members);
+        s_scale = fx_scale;
+        s_shift = static_cast<uint32_t>(shift1);
         s_addr[0] = static_cast<uint32_t>(__cvta_generic_to_shared(h1));
         s_addr[1] = static_cast<uint32_t>(__cvta_generic_to_shared(tbl32));
         s_addr[2] = static_cast<uint32_t>(__cvta_generic_to_shared(l2));
@@ -142,6 +140,9 @@ quantile_select2_kernel(const QuantileParams p, const __grid_constant__ Quantile
     for (int i = tid; i < NB + NB / 2 + QB * 3 * SL; i += THREADS) h1[i] = 0u;
     __syncthreads();
     const uint32_t h1_s = s_addr[0], tbl_s = s_addr[1], l2_s = s_addr[2];
+    const uint4* __restrict__ members4 = reinterpret_cast<const uint4*>(s_members);   // member pairs
+    const float scale = s_scale;
+    const uint32_t shift = s_shift;
     const uint32_t tab_s = s_addr[3] + lay.warp_off[warp] * 4;    // this warp's segment of the pair table
 
     auto mark = [&](int q, int which, uint32_t b) {     // bucket b feeds slot array 3 * (q % QB) + which
@@ -190,25 +191,33 @@ quantile_select2_kernel(const QuantileParams p, const __grid_constant__ Quantile
 #pragma unroll
             for (int i = 0; i < MAXIPT; ++i) {
                 if (i < ipt) {                          // block-uniform
-                    const uint32_t end = pre[i].x + pre[i].y;
-                    uint32_t idx = pre[i].x & ~1u;
+                    const uint32_t last = (pre[i].x + pre[i].y - 1u) >> 1;   // pair holding the list's last member
+                    uint32_t pair = pre[i].x >> 1;
                     if (np[i]) {                        // first pair: its first slot may precede the list
-                        st_shared_u32(dst, idx | (pre[i].x & 1u) | (idx + 1u >= end ? 0x80000000u : 0u));
-                        idx += 2, dst += 4;
+                        st_shared_u32(dst, pair | ((pre[i].x & 1u) ? kPairSkip0 : 0u) |
+                                               ((pair == last && ((pre[i].x + pre[i].y) & 1u)) ? kPairSkip1 : 0u));
+                        ++pair, dst += 4;
                     }
-                    for (uint32_t k = 1; k < np[i]; ++k, idx += 2, dst += 4)
-                        st_shared_u32(dst, idx | (idx + 1u >= end ? 0x80000000u : 0u));
+                    for (uint32_t k = 1; k < np[i]; ++k, ++pair, dst += 4)
+                        st_shared_u32(dst, pair | ((pair == last && ((pre[i].x + pre[i].y) & 1u)) ? kPairSkip1 : 0u));
                 }
             }
             __syncwarp();
         }
         fetch(work + gridDim.x, pre);
 
-        // pass 1: bucket weights
-        for_each_pair(tab_s, n_pairs, p.members, lane, [&](uint32_t rank, uint32_t wbits, bool valid) {
-            const uint32_t w = __float2uint_rn(__fmul_rn(__uint_as_float(wbits), fx_scale));
-            if (valid) red_add_shared(h1_s + (rank >> shift1) * 4, w);      // w == 0 (utils.py:55-57) changes nothing
-        });
+        // pass 1: bucket weights.  Two pairs (four members) per lane and iteration, all lanes
+        // busy; w == 0 (utils.py:55-57) changes nothing
+        for (uint32_t j = lane; j < n_pairs; j += 64) {
+            const uint32_t e0 = ld_shared_u32(tab_s + j * 4);
+            const uint32_t e1 = (j + 32 < n_pairs) ? ld_shared_u32(tab_s + (j + 32) * 4) : (kPairSkip0 | kPairSkip1);
+            const uint4 a = __ldg(members4 + (e0 & kPairIndex));
+            const uint4 b = __ldg(members4 + (e1 & kPairIndex));
+            red_add_shared_unless(h1_s + (a.x >> shift) * 4, __float2uint_rn(__fmul_rn(__uint_as_float(a.y), scale)), e0 & kPairSkip0);
+            red_add_shared_unless(h1_s + (a.z >> shift) * 4, __float2uint_rn(__fmul_rn(__uint_as_float(a.w), scale)), e0 & kPairSkip1);
+            red_add_shared_unless(h1_s + (b.x >> shift) * 4, __float2uint_rn(__fmul_rn(__uint_as_float(b.y), scale)), e1 & kPairSkip0);
+            red_add_shared_unless(h1_s + (b.z >> shift) * 4, __float2uint_rn(__fmul_rn(__uint_as_float(b.w), scale)), e1 & kPairSkip1);
+        }
         __syncthreads();                                // B1
 
         // inclusive prefix of this thread's BPT consecutive buckets, in registers; the
@@ -316,19 +325,35 @@ quantile_select2_kernel(const QuantileParams p, const __grid_constant__ Quantile
                 __syncthreads();
             }
 
-            // pass 2: members of marked buckets -> slot arrays at single-rank resolution
-            for_each_pair(tab_s, n_pairs, p.members, lane, [&](uint32_t rank, uint32_t wbits, bool valid) {
-                uint32_t code = valid ? ld_shared_u16(tbl_s + (rank >> shift1) * 2) : 0u;
-                if (code) {
-                    const uint32_t w = __float2uint_rn(__fmul_rn(__uint_as_float(wbits), fx_scale));
-                    const uint32_t dst = l2_s + (rank & slot_mask) * 4;
-                    do {
-                        const int a = __ffs(code) - 1;
-                        code &= code - 1u;
-                        red_add_shared(dst + a * SL * 4, w);
-                    } while (code);
+            // pass 2: members of marked buckets -> slot arrays at single-rank resolution.  The
+            // table is consulted for all four members of an iteration before anything else
+            auto feed = [&](uint32_t code, uint32_t rank, uint32_t wbits) {
+                const uint32_t w = __float2uint_rn(__fmul_rn(__uint_as_float(wbits), scale));
+                const uint32_t dst = l2_s + (rank & slot_mask) * 4;
+                while (code) {
+                    const int a = __ffs(code) - 1;
+                    code &= code - 1u;
+                    red_add_shared(dst + a * SL * 4, w);
                 }
-            });
+            };
+            for (uint32_t j = lane; j < n_pairs; j += 64) {
+                const uint32_t e0 = ld_shared_u32(tab_s + j * 4);
+                const uint32_t e1 = (j + 32 < n_pairs) ? ld_shared_u32(tab_s + (j + 32) * 4) : (kPairSkip0 | kPairSkip1);
+                const uint4 a = __ldg(members4 + (e0 & kPairIndex));
+                const uint4 b = __ldg(members4 + (e1 & kPairIndex));
+                uint32_t c0 = ld_shared_u16(tbl_s + (a.x >> shift) * 2), c1 = ld_shared_u16(tbl_s + (a.z >> shift) * 2);
+                uint32_t c2 = ld_shared_u16(tbl_s + (b.x >> shift) * 2), c3 = ld_shared_u16(tbl_s + (b.z >> shift) * 2);
+                c0 = (e0 & kPairSkip0) ? 0u : c0;
+                c1 = (e0 & kPairSkip1) ? 0u : c1;
+                c2 = (e1 & kPairSkip0) ? 0u : c2;
+                c3 = (e1 & kPairSkip1) ? 0u : c3;
+                if (c0 | c1 | c2 | c3) {
+                    feed(c0, a.x, a.y);
+                    feed(c1, a.z, a.w);
+                    feed(c2, b.x, b.y);
+                    feed(c3, b.z, b.w);
+                }
+            }
             __syncthreads();                            // B6
             if (tid < 3 * nqb) {                        // table back to zero (next marks: after the next row's B3)
                 const uint32_t b = s_b[q0 + tid / 3][tid % 3];
