@@ -367,10 +367,24 @@ def run_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def _memory_bound_workers(cfg):
+    """The dense algorithm materialises a (T,N) bool mask and a masked float32 copy per row
+    (ensemble.py:138-140): ~6 bytes x T x N transient per worker on top of the shared 8 x T x N
+    fit attributes.  Keep the workers inside half of the available host memory."""
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        return 4
+    tn = cfg["n_estimators"] * cfg["n_train"]
+    return max(1, int((avail * 0.5 - 8 * tn) // (6 * tn)))
+
+
 def measure_cpu_baseline(estimators, Xtr, ytr, cfg, budget_s=12.0, workers=None):
     """Dense reference algorithm on a bounded row sample, all host cores."""
     from skgarden_b200.datasets import make_test
     workers = workers or max(1, min(host_cores(), 64))
+    workers = min(workers, _memory_bound_workers(cfg))
     qs = cfg["quantiles"][:3]
     sample = make_test(min(cfg["n_test"], 4096), cfg["n_features"], seed=0)
     cpu_reference_setup(estimators, Xtr, ytr, sample)
@@ -394,7 +408,7 @@ def run_reference(args, rank, world):
     cfg = CONFIGS[args.config]
     qs = cfg["quantiles"][:3] if len(cfg["quantiles"]) > 3 else cfg["quantiles"]
     est, Xtr, ytr = fit_forest(cfg, product=False)
-    workers = max(1, min(host_cores(), 64))
+    workers = max(1, min(host_cores(), 64, _memory_bound_workers(cfg)))
     sample = make_test(min(cfg["n_test"], 4096), cfg["n_features"], seed=0)
     cpu_reference_setup(est.estimators_, Xtr, ytr, sample)
     _, dt1 = cpu_reference_throughput(qs, 1, workers)

@@ -70,6 +70,7 @@ struct qf_forest {
     double* d_values = nullptr;
     int64_t device_bytes = 0;
     std::vector<uint32_t> tree_max_leaf;   // members of the largest leaf of every tree
+    bool unit_leaves = false;              // every leaf of every tree holds exactly one member
     int sm_count = 148;
     // options (0 = auto where noted)
     int apply_row_warps = 0;      // warps along rows per CTA (0 auto)
@@ -83,6 +84,7 @@ struct qf_forest {
     int select_impl = 0;                   // 0: single-refinement kernel when the training set allows; 1: always the multi-level one
     int cta2_capacity = 8192;     // same for the 512-thread overflow stage (0 = stage not used)
     int warp_elems = -1;          // warp kernel: keys per lane (2, 4, 8), 0 = never, -1 = auto
+    int warp_unit = 1;            // 0: never take the one-member-per-leaf gather of the warp kernel
     int dense_ctas = 0;           // 0 = auto
     // counters
     int launches = 0;
@@ -364,7 +366,7 @@ int launch_select_kernel(const qf_forest* f, unsigned grid, const qf::QuantilePa
             const int log2nb = nbits <= 11 + qf::kSelect2SlotBits ? 11 : 12;
             const int shift1 = std::max(0, nbits - log2nb);
             const size_t smem2 = qf::select2_kernel_smem(log2nb, shift1, static_cast<uint32_t>(pairs));
-            const unsigned ctas = static_cast<unsigned>(f->sm_count) * 4;
+            const unsigned ctas = static_cast<unsigned>(f->sm_count) * qf::kSelect2CtasPerSm;
             auto run2 = [&](auto kernel) -> int {
                 int rc = set_smem(kernel, smem2);
                 if (rc != QF_OK) return rc;
@@ -442,12 +444,19 @@ int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, co
                     static_cast<unsigned>((rows + qf::kWarpKernelWarps - 1) / qf::kWarpKernelWarps);
                 {
                     SpanTimer span(f, SPAN_QUANTILE, st);
-                    if (pl.warp_elems == 2)
-                        qf::quantile_warp_kernel<2><<<grid, qf::kWarpKernelWarps * 32, 0, st>>>(qp, ql);
-                    else if (pl.warp_elems == 4)
-                        qf::quantile_warp_kernel<4><<<grid, qf::kWarpKernelWarps * 32, 0, st>>>(qp, ql);
-                    else
-                        qf::quantile_warp_kernel<8><<<grid, qf::kWarpKernelWarps * 32, 0, st>>>(qp, ql);
+                    // unit_leaves (deep bootstrap trees, min_samples_leaf=1): member t of the row is
+                    // the single member of its leaf in tree t -- no offsets to scan
+                    const bool unit = f->unit_leaves && f->warp_unit != 0;
+                    if (pl.warp_elems == 2) {
+                        if (unit) qf::quantile_warp_kernel<2, true><<<grid, qf::kWarpKernelWarps * 32, 0, st>>>(qp, ql);
+                        else qf::quantile_warp_kernel<2, false><<<grid, qf::kWarpKernelWarps * 32, 0, st>>>(qp, ql);
+                    } else if (pl.warp_elems == 4) {
+                        if (unit) qf::quantile_warp_kernel<4, true><<<grid, qf::kWarpKernelWarps * 32, 0, st>>>(qp, ql);
+                        else qf::quantile_warp_kernel<4, false><<<grid, qf::kWarpKernelWarps * 32, 0, st>>>(qp, ql);
+                    } else {
+                        if (unit) qf::quantile_warp_kernel<8, true><<<grid, qf::kWarpKernelWarps * 32, 0, st>>>(qp, ql);
+                        else qf::quantile_warp_kernel<8, false><<<grid, qf::kWarpKernelWarps * 32, 0, st>>>(qp, ql);
+                    }
                 }
                 QF_CUDA_TRY(cudaGetLastError());
                 ++f->launches;
@@ -579,12 +588,16 @@ int qf_forest_create(const qf_forest_desc* d, qf_forest** out) {
         rc = upload(reinterpret_cast<void**>(&f->d_values), d->leaf_values, d->n_nodes * 8);
     if (rc == QF_OK) {                                  // largest leaf of every tree (sizes the pair table of select2)
         uint32_t* d_max = nullptr;
-        cudaError_t e = cudaMalloc(&d_max, static_cast<size_t>(d->n_trees) * 4);
+        cudaError_t e = cudaMalloc(&d_max, static_cast<size_t>(d->n_trees) * 8);
         if (e == cudaSuccess) {
             qf::tree_max_leaf_kernel<<<d->n_trees, 256>>>(f->d_nodes, f->d_roots, f->n_nodes, f->T, d_max);
-            f->tree_max_leaf.resize(d->n_trees);
-            e = cudaMemcpy(f->tree_max_leaf.data(), d_max, static_cast<size_t>(d->n_trees) * 4, cudaMemcpyDeviceToHost);
+            std::vector<uint32_t> both(static_cast<size_t>(d->n_trees) * 2);
+            e = cudaMemcpy(both.data(), d_max, both.size() * 4, cudaMemcpyDeviceToHost);
             cudaFree(d_max);
+            f->tree_max_leaf.assign(both.begin(), both.begin() + d->n_trees);
+            f->unit_leaves = true;
+            for (int t = 0; t < d->n_trees; ++t)
+                f->unit_leaves = f->unit_leaves && both[t] == 1u && both[d->n_trees + t] == 1u;
         }
         if (e != cudaSuccess) rc = qf::fail(QF_ERR_CUDA, std::string("qf_forest_create: ") + cudaGetErrorString(e));
     }
@@ -686,6 +699,9 @@ int qf_forest_set_option(qf_forest* f, const char* key, int64_t value) {
     } else if (k == "cta2_capacity") {
         if (value < 0 || value > 8192) return qf::fail(QF_ERR_INVALID, "cta2_capacity must be in [0, 8192]");
         f->cta2_capacity = static_cast<int>(value);
+    } else if (k == "warp_unit") {
+        if (value != 0 && value != 1) return qf::fail(QF_ERR_INVALID, "warp_unit must be 0 or 1");
+        f->warp_unit = static_cast<int>(value);
     } else if (k == "select_impl") {
         if (value != 0 && value != 1) return qf::fail(QF_ERR_INVALID, "select_impl must be 0 or 1");
         f->select_impl = static_cast<int>(value);

@@ -142,7 +142,7 @@ __device__ __forceinline__ void warp_bitonic_sort(uint32_t (&key)[E], int lane) 
     }
 }
 
-template <int E>
+template <int E, bool UNIT>
 __global__ void __launch_bounds__(kWarpKernelWarps * 32)
 quantile_warp_kernel(const QuantileParams p, const __grid_constant__ QuantileList ql) {
     constexpr int CAP = 32 * E;
@@ -164,25 +164,36 @@ quantile_warp_kernel(const QuantileParams p, const __grid_constant__ QuantileLis
 
     // 1. gather in tree order
     uint32_t P = 0;
-    for (int base = 0; base < p.T; base += 32) {
-        const int t = base + lane;
-        const uint2 s = (t < p.T) ? seg[t] : make_uint2(0u, 0u);
-        uint32_t incl = s.y;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += u;
-        }
-        const uint32_t excl = P + incl - s.y;
-        if (excl + s.y <= CAP) {
-            const uint2* __restrict__ src = p.members + s.x;
-            for (uint32_t i = 0; i < s.y; ++i) {
-                const uint2 e = __ldg(src + i);
-                A[excl + i] = (e.x << POSBITS) | (excl + i);
-                B[excl + i] = __uint_as_float(e.y);
+    if (UNIT) {                                          // every leaf holds exactly one member: position = tree
+        P = static_cast<uint32_t>(p.T);
+        if (P <= CAP) {
+            for (int t = lane; t < p.T; t += 32) {
+                const uint2 e = __ldg(p.members + seg[t].x);
+                A[t] = (e.x << POSBITS) | static_cast<uint32_t>(t);
+                B[t] = __uint_as_float(e.y);
             }
         }
-        P += __shfl_sync(0xffffffffu, incl, 31);
+    } else {
+        for (int base = 0; base < p.T; base += 32) {
+            const int t = base + lane;
+            const uint2 s = (t < p.T) ? seg[t] : make_uint2(0u, 0u);
+            uint32_t incl = s.y;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += u;
+            }
+            const uint32_t excl = P + incl - s.y;
+            if (excl + s.y <= CAP) {
+                const uint2* __restrict__ src = p.members + s.x;
+                for (uint32_t i = 0; i < s.y; ++i) {
+                    const uint2 e = __ldg(src + i);
+                    A[excl + i] = (e.x << POSBITS) | (excl + i);
+                    B[excl + i] = __uint_as_float(e.y);
+                }
+            }
+            P += __shfl_sync(0xffffffffu, incl, 31);
+        }
     }
     if (P > CAP) {
         if (lane == 0) p.overflow_rows[atomicAdd(p.overflow_count, 1)] = static_cast<int>(row);

@@ -41,11 +41,12 @@
 
 namespace qf {
 
-constexpr int kSelect2QB = 4;                           // percentiles per pass 2
+constexpr int kSelect2QB = 3;                           // percentiles per pass 2
 constexpr int kSelect2SlotBits = 9;                     // a bucket spans <= 512 ranks
 constexpr int kSelect2Threads = 256;
 constexpr int kSelect2Warps = kSelect2Threads / 32;
 constexpr int kSelect2MaxIPT = 4;                       // leaves per lane: T <= 4 * 256
+constexpr int kSelect2CtasPerSm = 5;
 constexpr int kSelect2MaxPairs = 6144;                  // pair-table entries per CTA (24 KB)
 
 // first pair-table entry of every warp (exact upper bounds from the largest leaf of each tree)
@@ -90,7 +91,7 @@ __device__ __forceinline__ void red_add_shared_unless(uint32_t addr, uint32_t v,
 constexpr uint32_t kPairSkip0 = 0x40000000u, kPairSkip1 = 0x80000000u, kPairIndex = 0x3fffffffu;
 
 template <int LOG2NB>
-__global__ void __launch_bounds__(kSelect2Threads, 4)
+__global__ void __launch_bounds__(kSelect2Threads, kSelect2CtasPerSm)
 quantile_select2_kernel(const QuantileParams p, const __grid_constant__ QuantileList ql,
                         const __grid_constant__ Select2Layout lay, const float fx_scale, const int shift1) {
     constexpr int THREADS = kSelect2Threads;
@@ -485,24 +486,30 @@ quantile_select2_kernel(const QuantileParams p, const __grid_constant__ Quantile
     }   // rows
 }
 
-// largest leaf (members) of every tree: block t reduces over the tree's packed nodes
+// largest and smallest leaf (members) of every tree: block t reduces over the tree's packed
+// nodes; out[t] = largest, out[T + t] = smallest
 __global__ void __launch_bounds__(256)
 tree_max_leaf_kernel(const uint2* __restrict__ nodes, const uint32_t* __restrict__ roots, int64_t n_nodes, int T,
                      uint32_t* __restrict__ out) {
-    __shared__ uint32_t red[8];
+    __shared__ uint32_t red[16];
     const int t = blockIdx.x;
     const int64_t n0 = roots[t], n1 = (t + 1 < T) ? static_cast<int64_t>(roots[t + 1]) : n_nodes;
-    uint32_t m = 0;
+    uint32_t m = 0, mn = 0xffffffffu;
     for (int64_t i = n0 + threadIdx.x; i < n1; i += blockDim.x) {
         const uint32_t hi = nodes[i].y;
-        if (hi & 0x80000000u) m = max(m, hi & 0x7fffffffu);
+        if (hi & 0x80000000u) {
+            m = max(m, hi & 0x7fffffffu);
+            mn = min(mn, hi & 0x7fffffffu);
+        }
     }
     m = __reduce_max_sync(0xffffffffu, m);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = m; red[8 + (threadIdx.x >> 5)] = mn; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w) m = max(m, red[w]);
+        for (int w = 1; w < 8; ++w) { m = max(m, red[w]); mn = min(mn, red[8 + w]); }
         out[t] = m;
+        out[T + t] = mn;
     }
 }
 

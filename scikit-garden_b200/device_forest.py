@@ -169,7 +169,7 @@ class DeviceForest:
                                out_host: Optional[np.ndarray] = None,
                                mode: int = _native.QF_MODE_EXACT, chunk_rows: int = 0) -> np.ndarray:
         """Host float32 (n,F) in, host float64 (n,Q) out; H2D, kernels and D2H run inside
-        the C call, double-buffered.  Pass pinned arrays for full PCIe bandwidth."""
+        the C call, pipelined on three streams.  Pass pinned arrays for full PCIe bandwidth."""
         if X_host.dtype != np.float32 or X_host.ndim != 2 or X_host.strides[1] != 4:
             raise TypeError("X_host must be a 2-D float32 array with contiguous rows")
         if X_host.shape[1] != self.n_features:
@@ -183,3 +183,33 @@ class DeviceForest:
             q.ctypes.data_as(C.c_void_p), q.shape[0], C.c_void_p(out_host.ctypes.data),
             int(mode), int(chunk_rows)))
         return out_host
+
+    def predict_stream(self, chunks, quantiles: Sequence[float], mode: int = _native.QF_MODE_EXACT,
+                       pinned: bool = True):
+        """Streaming front end (BASELINE.json config 5: test rows that do not fit one host
+        array): ``chunks`` is any iterable of (m_i, F) float32 arrays; yields one (m_i, Q)
+        float64 array per chunk, in order.  Every chunk goes through the pipelined
+        host-buffer call; with ``pinned`` the rows are staged in a reused page-locked buffer
+        so that the H2D copy runs at full PCIe bandwidth."""
+        torch = _torch()
+        q = [float(v) for v in quantiles]
+        stage_x = stage_o = None
+        for X in chunks:
+            X = np.ascontiguousarray(X, dtype=np.float32)
+            if X.ndim != 2 or X.shape[1] != self.n_features:
+                raise ValueError("chunk has shape %r, forest expects (m, %d)" % (X.shape, self.n_features))
+            m = X.shape[0]
+            if m == 0:
+                yield np.empty((0, len(q)), dtype=np.float64)
+                continue
+            if not pinned:
+                yield self.predict_quantiles_host(X, q, mode=mode)
+                continue
+            if stage_x is None or stage_x.shape[0] < m:
+                stage_x = torch.empty((m, self.n_features), dtype=torch.float32).pin_memory()
+                stage_o = torch.empty((m, len(q)), dtype=torch.float64).pin_memory()
+            xs, os_ = stage_x[:m].numpy(), stage_o[:m].numpy()
+            xs[...] = X
+            self.predict_quantiles_host(xs, q, out_host=os_, mode=mode)
+            yield os_.copy()
+

@@ -206,6 +206,20 @@ class _BaseForestQuantileRegressor(RegressorMixin, BaseEstimator):
         out = dev.predict_quantiles_host(X, qs, mode=self._mode())
         return out[:, 0] if scalar else out
 
+    def predict_stream(self, chunks, quantile):
+        """Extension for test sets that do not fit one array (BASELINE.json config 5): an
+        iterable of (m_i, F) chunks in, one ``predict(chunk, quantile)`` result per chunk out
+        (generator), each chunk pipelined H2D / kernels / D2H on the device."""
+        self._check_fitted()
+        qs, scalar = _check_quantiles(quantile)
+        dev = self._on_device()
+
+        def validated():
+            for X in chunks:
+                yield self._validate_X(X)
+        for out in dev.predict_stream(validated(), qs, mode=self._mode()):
+            yield out[:, 0] if scalar else out
+
     def apply(self, X):
         """forest.py:583-604: (n, T) int64 scikit-learn leaf ids."""
         import torch

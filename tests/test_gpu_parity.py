@@ -284,3 +284,51 @@ def test_fast_mode_within_tolerance():
     # tolerance stated by BASELINE.json north_star for float32 arithmetic: 1e-4 relative
     # (relative to the scale of y where the value itself is near zero)
     assert_allclose(fast, exact, rtol=1e-4, atol=1e-4 * np.abs(y).max())
+
+
+def test_streaming_front_end_and_pickle_round_trip():
+    # chunked streaming predict, flattened forest on disk, estimator pickling
+    import pickle
+    import tempfile
+    import skgarden_b200 as sg
+    rng = np.random.RandomState(9)
+    X = rng.randn(3000, 7).astype(np.float32)
+    y = 2 * X[:, 0] + np.sin(X[:, 1]) + rng.randn(3000)
+    est = sg.ExtraTreesQuantileRegressor(n_estimators=12, min_samples_leaf=3, random_state=0, n_jobs=-1)
+    est.fit(X[:2000], y[:2000])
+    Xt = X[2000:]
+    want = est.predict(Xt, quantile=[10, 50, 90])
+    chunks = [Xt[:1], Xt[1:300], Xt[300:300], Xt[300:]]
+    got = np.concatenate(list(est.predict_stream(chunks, [10, 50, 90])))
+    assert_array_equal(got, want)
+    got1 = np.concatenate(list(est.predict_stream(iter(chunks), 50)))
+    assert_array_equal(got1, want[:, 1])
+    est2 = pickle.loads(pickle.dumps(est))                       # the device handle never travels
+    assert_array_equal(est2.predict(Xt, quantile=[10, 50, 90]), want)
+    with tempfile.TemporaryDirectory() as d:                     # serving without sklearn objects
+        path = d + "/forest.npz"
+        est._flat.save(path)
+        dev = sg.DeviceForest(sg.FlatForest.load(path), device=0)
+        assert_array_equal(dev.predict_quantiles_host(Xt, [10, 50, 90]), want)
+        dev.close()
+
+
+def test_one_member_per_leaf_gather_is_identical():
+    # deep bootstrap trees on continuous targets: every leaf holds exactly one in-bag sample
+    # (BASELINE.json configs 2 and 4); the warp kernel then skips the offset scan
+    import skgarden_b200 as sg
+    rng = np.random.RandomState(3)
+    X = rng.randn(900, 6).astype(np.float32)
+    y = 3 * X[:, 0] + np.sin(3 * X[:, 1]) + rng.randn(900)
+    est = sg.RandomForestQuantileRegressor(n_estimators=40, random_state=0, n_jobs=-1).fit(X[:600], y[:600])
+    hi = (est._flat.nodes >> np.uint64(32)).astype(np.uint32)
+    leaf_sizes = hi[(hi & np.uint32(0x80000000)) != 0] & np.uint32(0x7FFFFFFF)
+    assert leaf_sizes.min() == 1 and leaf_sizes.max() == 1
+    qs = [0, 5, 33.3, 50, 95, 100]
+    got = est.predict(X[600:], quantile=qs)
+    leaves = est.apply(X[600:])
+    index = O.SparseIndex(est.y_train_, est.y_train_leaves_, est.y_weights_, est._flat.sorter)
+    assert_array_equal(got, O.predict_sparse(index, leaves, qs))
+    est._device_forest.set_option("warp_unit", 0)
+    assert_array_equal(est.predict(X[600:], quantile=qs), got)
+
