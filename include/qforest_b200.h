@@ -92,6 +92,43 @@ int qf_pack_tree(int64_t n_nodes,
 /* Number of in-bag samples of one tree (size of members_out); counts NULL = n_train. */
 int64_t qf_count_inbag(int64_t n_train, const int64_t* counts);
 
+/* qf_pack_tree with train_leaves == NULL packs the STRUCTURE only (nodes_out, node_id_out,
+ * max_depth_out; n_train / counts / sorter / members_out are ignored): leaves are left empty
+ * (lo32 = 0, hi32 = 0x80000000) for qf_build_csr to fill on the device. */
+
+/* ------------------------------------------------------------------------------------
+ * Device side, fit time: the leaf -> member lists built on the GPU (K4).
+ *
+ * Replaces the same reference code as the member part of qf_pack_tree -- the O(T*L*N) loop
+ * of quantile/ensemble.py:87-101 and tree_.apply(X_train) per tree (tree.py:98-101) -- and
+ * produces bit for bit the same nodes / members arrays: leaf lookup of the training rows
+ * with the predict path's own kernel, per-leaf counts, a scan over the packed nodes, a
+ * scatter of (rank, f32(count / leaf count sum)) entries and a sort of every list by rank.
+ * All "_dev" arrays live on `device`.  counts_dev is laid out [n_train][n_trees] (uint16
+ * bootstrap multiplicities, ensemble.py:88-94) or NULL (every sample once).  Lists longer
+ * than 4096 members fail with QF_ERR_LIMIT (use the host flattener).  Synchronous.
+ */
+typedef struct qf_csr_build_desc {
+    int32_t device;
+    int32_t n_trees;
+    int32_t n_features;
+    int32_t feature_bits;
+    int64_t n_train;
+    int64_t n_nodes;
+    uint64_t* nodes_dev;            /* in: structure-only packed nodes; out: leaves filled  */
+    const int64_t* tree_offsets;    /* host [T+1]                                           */
+    const float* X_train_dev;       /* (n_train, n_features) float32 row-major              */
+    const int32_t* rank_dev;        /* [n_train] rank of each sample in np.argsort(y_train_) */
+    const uint16_t* counts_dev;     /* [n_train][n_trees] or NULL                           */
+    uint64_t* members_dev;          /* out: (rank, weight) entries                          */
+    int64_t members_capacity;       /* entries members_dev can hold                         */
+    int64_t* inbag_out;             /* host [T]: members of each tree                       */
+    int32_t* max_leaf_members_out;  /* host [T]                                             */
+    double* sum_sq_out;             /* host [T]: sum over leaves of members^2               */
+} qf_csr_build_desc;
+
+int qf_build_csr(const qf_csr_build_desc* desc, int64_t* n_members_out);
+
 /* ------------------------------------------------------------------------------------
  * Device side.
  */

@@ -11,12 +11,12 @@ plus the lower-level pieces the estimators are made of: ``flatten_forest`` /
 ``FlatForest`` (host layout), ``DeviceForest`` (HBM-resident forest + kernel calls).
 """
 from .ensemble import ExtraTreesQuantileRegressor, RandomForestQuantileRegressor
-from .flatten import FlatForest, bootstrap_counts, flatten_forest
+from .flatten import FlatForest, bootstrap_counts, flatten_forest, flatten_forest_device
 from .tree import DecisionTreeQuantileRegressor, ExtraTreeQuantileRegressor
 
 __all__ = ["RandomForestQuantileRegressor", "ExtraTreesQuantileRegressor",
            "DecisionTreeQuantileRegressor", "ExtraTreeQuantileRegressor", "FlatForest",
-           "flatten_forest", "bootstrap_counts", "DeviceForest"]
+           "flatten_forest", "flatten_forest_device", "bootstrap_counts", "DeviceForest"]
 
 
 def __getattr__(name):          # DeviceForest pulls in torch; load it on first use

@@ -42,6 +42,19 @@ class ForestDesc(C.Structure):
     ]
 
 
+class CsrBuildDesc(C.Structure):
+    """struct qf_csr_build_desc"""
+    _fields_ = [
+        ("device", C.c_int32), ("n_trees", C.c_int32), ("n_features", C.c_int32),
+        ("feature_bits", C.c_int32),
+        ("n_train", C.c_int64), ("n_nodes", C.c_int64),
+        ("nodes_dev", C.c_void_p), ("tree_offsets", C.c_void_p), ("X_train_dev", C.c_void_p),
+        ("rank_dev", C.c_void_p), ("counts_dev", C.c_void_p), ("members_dev", C.c_void_p),
+        ("members_capacity", C.c_int64),
+        ("inbag_out", C.c_void_p), ("max_leaf_members_out", C.c_void_p), ("sum_sq_out", C.c_void_p),
+    ]
+
+
 # every symbol include/qforest_b200.h declares: name -> (restype, argtypes)
 _P, _I32, _I64, _U64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
 SIGNATURES = {
@@ -50,6 +63,7 @@ SIGNATURES = {
     "qf_pack_tree": (C.c_int, [_I64, _P, _P, _P, _P, _I32, _I64, _P, _P, _P, _U64,
                                _P, _P, _P, _P, _P, _P, _P]),
     "qf_count_inbag": (_I64, [_I64, _P]),
+    "qf_build_csr": (C.c_int, [C.POINTER(CsrBuildDesc), C.POINTER(C.c_int64)]),
     "qf_forest_create": (C.c_int, [C.POINTER(ForestDesc), C.POINTER(C.c_void_p)]),
     "qf_forest_destroy": (None, [_P]),
     "qf_forest_device_bytes": (_I64, [_P]),

@@ -43,12 +43,15 @@ extern "C" int qf_pack_tree(int64_t n_nodes, const int64_t* left, const int64_t*
                             uint64_t* nodes_out, int32_t* node_id_out, uint64_t* members_out,
                             int64_t* n_inbag_out, int32_t* max_leaf_members_out,
                             int32_t* max_depth_out, double* sum_sq_leaf_members_out) {
-    if (n_nodes <= 0 || !left || !right || !feature || !threshold || !train_leaves || !sorter ||
-        !nodes_out || !node_id_out || !members_out || n_train <= 0)
+    // train_leaves == NULL: structure only (nodes, node ids, depth); the leaves stay empty
+    // and the member lists are built on the device (qf_build_csr)
+    const bool structure_only = train_leaves == nullptr;
+    if (n_nodes <= 0 || !left || !right || !feature || !threshold || !nodes_out || !node_id_out ||
+        (!structure_only && (!sorter || !members_out || n_train <= 0)))
         return qf::fail(QF_ERR_INVALID, "qf_pack_tree: null or empty argument");
     if (feature_bits < 1 || feature_bits > 24)
         return qf::fail(QF_ERR_INVALID, "qf_pack_tree: feature_bits must be in [1,24]");
-    if (n_nodes >= (int64_t(1) << 31) || n_train >= (int64_t(1) << 31))
+    if (n_nodes >= (int64_t(1) << 31) || (!structure_only && n_train >= (int64_t(1) << 31)))
         return qf::fail(QF_ERR_LIMIT, "qf_pack_tree: more than 2^31 nodes or training rows");
     const uint32_t max_off = (1u << (31 - feature_bits)) - 1u;
 
@@ -88,7 +91,7 @@ extern "C" int qf_pack_tree(int64_t n_nodes, const int64_t* left, const int64_t*
     std::vector<int64_t> leaf_count_sum(n_nodes, 0);
     std::vector<uint32_t> leaf_members(n_nodes, 0);
     int64_t n_inbag = 0;
-    for (int64_t j = 0; j < n_train; ++j) {
+    for (int64_t j = 0; !structure_only && j < n_train; ++j) {
         const int64_t c = counts ? counts[j] : 1;
         if (c <= 0) continue;                              // out-of-bag: -1 / weight 0 in the reference
         const int64_t lf = train_leaves[j];
@@ -130,7 +133,7 @@ extern "C" int qf_pack_tree(int64_t n_nodes, const int64_t* left, const int64_t*
     }
 
     // pass 4: members in rank order -> every leaf's list ends up sorted by rank
-    for (int64_t k = 0; k < n_train; ++k) {
+    for (int64_t k = 0; !structure_only && k < n_train; ++k) {
         const int64_t j = sorter[k];
         if (j < 0 || j >= n_train)
             return qf::fail(QF_ERR_INVALID, "qf_pack_tree: sorter is not a permutation");

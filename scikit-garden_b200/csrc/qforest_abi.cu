@@ -14,6 +14,7 @@
 #include "quantile_kernel.cuh"
 #include "select_kernel.cuh"
 #include "select2_kernel.cuh"
+#include "csr_builder.cuh"
 
 namespace qf {
 
@@ -880,6 +881,126 @@ int qf_forest_predict_quantiles_host(qf_forest* f, const float* X_host, int64_t 
     QF_CUDA_TRY(cudaStreamSynchronize(hp.d2h));
     QF_CUDA_TRY(cudaStreamSynchronize(hp.compute));
     f->launches = total_launches;
+    return QF_OK;
+}
+
+// K4: leaf -> member lists on the device (csr_builder.cuh).  Synchronous.
+int qf_build_csr(const qf_csr_build_desc* d, int64_t* n_members_out) {
+    if (!d || !n_members_out) return qf::fail(QF_ERR_INVALID, "qf_build_csr: null argument");
+    if (d->n_trees <= 0 || d->n_features <= 0 || d->n_train <= 0 || d->n_nodes <= 0 || !d->nodes_dev ||
+        !d->tree_offsets || !d->X_train_dev || !d->rank_dev || !d->members_dev || !d->inbag_out ||
+        !d->max_leaf_members_out || !d->sum_sq_out)
+        return qf::fail(QF_ERR_INVALID, "qf_build_csr: empty forest or null array");
+    if (d->n_nodes >= (int64_t(1) << 31) || d->n_train >= (int64_t(1) << 31))
+        return qf::fail(QF_ERR_LIMIT, "qf_build_csr: forest exceeds the 32-bit packed layout");
+    int count = 0;
+    QF_CUDA_TRY(cudaGetDeviceCount(&count));
+    if (d->device < 0 || d->device >= count) return qf::fail(QF_ERR_CUDA, "qf_build_csr: no such CUDA device");
+    DeviceGuard guard(d->device);
+    if (!guard.ok) return qf::fail(QF_ERR_CUDA, "qf_build_csr: cudaSetDevice failed");
+    cudaDeviceProp prop;
+    QF_CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
+    if (prop.major != 10)
+        return qf::fail(QF_ERR_CUDA, "qf_build_csr: device is not sm_100 (this library has sm_100a code only)");
+
+    const int T = d->n_trees;
+    const int64_t N = d->n_train, n_nodes = d->n_nodes, total = N * T;
+    const int64_t n_blocks = (n_nodes + qf::kCsrScanBlock - 1) / qf::kCsrScanBlock;
+    // a minimal forest object for the leaf-lookup launcher (no member lists yet)
+    qf_forest f;
+    f.device = d->device;
+    f.T = T;
+    f.F = d->n_features;
+    f.fbits = d->feature_bits;
+    f.N = N;
+    f.n_nodes = n_nodes;
+    f.sm_count = prop.multiProcessorCount;
+    f.d_nodes = reinterpret_cast<uint2*>(d->nodes_dev);
+
+    struct Scratch {
+        void* p[9] = {};
+        ~Scratch() { for (void* q : p) cudaFree(q); }
+    } sc;
+    auto alloc = [&](int k, size_t bytes) -> cudaError_t { return cudaMalloc(&sc.p[k], bytes ? bytes : 16); };
+    QF_CUDA_TRY(alloc(0, static_cast<size_t>(T) * 4));                      // roots
+    QF_CUDA_TRY(alloc(1, static_cast<size_t>(total) * 4));                  // leaf node of every (sample, tree)
+    QF_CUDA_TRY(alloc(2, static_cast<size_t>(n_nodes) * 4));                // leaf_cnt
+    QF_CUDA_TRY(alloc(3, static_cast<size_t>(n_nodes) * 4));                // leaf_sum
+    QF_CUDA_TRY(alloc(4, static_cast<size_t>(n_nodes) * 4));                // start
+    QF_CUDA_TRY(alloc(5, static_cast<size_t>(n_blocks + 1) * 8));           // block sums + total
+    QF_CUDA_TRY(alloc(6, static_cast<size_t>(n_nodes / 2 + 2) * 4 + 16));   // long lists + counters
+    QF_CUDA_TRY(alloc(7, static_cast<size_t>(T + 1) * 8));                  // tree offsets
+    QF_CUDA_TRY(alloc(8, static_cast<size_t>(T) * 24));                     // per-tree stats
+    uint32_t* d_roots = static_cast<uint32_t*>(sc.p[0]);
+    int32_t* d_idx = static_cast<int32_t*>(sc.p[1]);
+    uint32_t* leaf_cnt = static_cast<uint32_t*>(sc.p[2]);
+    uint32_t* leaf_sum = static_cast<uint32_t*>(sc.p[3]);
+    uint32_t* start = static_cast<uint32_t*>(sc.p[4]);
+    uint64_t* block_sum = static_cast<uint64_t*>(sc.p[5]);
+    int* counters = static_cast<int*>(sc.p[6]);                             // [0] long lists, [1] too long
+    int32_t* big = reinterpret_cast<int32_t*>(counters + 4);
+    int64_t* d_offsets = static_cast<int64_t*>(sc.p[7]);
+    unsigned long long* d_inbag = static_cast<unsigned long long*>(sc.p[8]);
+    uint32_t* d_maxleaf = reinterpret_cast<uint32_t*>(d_inbag + T);
+    double* d_sumsq = reinterpret_cast<double*>(d_inbag + 2 * T);
+
+    std::vector<uint32_t> roots(T);
+    for (int t = 0; t < T; ++t) roots[t] = static_cast<uint32_t>(d->tree_offsets[t]);
+    QF_CUDA_TRY(cudaMemcpy(d_roots, roots.data(), static_cast<size_t>(T) * 4, cudaMemcpyHostToDevice));
+    QF_CUDA_TRY(cudaMemcpy(d_offsets, d->tree_offsets, static_cast<size_t>(T + 1) * 8, cudaMemcpyHostToDevice));
+    f.d_roots = d_roots;
+    QF_CUDA_TRY(cudaMemset(leaf_cnt, 0, static_cast<size_t>(n_nodes) * 4));
+    QF_CUDA_TRY(cudaMemset(leaf_sum, 0, static_cast<size_t>(n_nodes) * 4));
+    QF_CUDA_TRY(cudaMemset(counters, 0, 16));
+
+    cudaStream_t st = nullptr;
+    int rc = QF_OK;
+    // tree.py:101 for every tree: leaf of every training row (rows in their own order)
+    const int64_t chunk = 131072;
+    for (int64_t r0 = 0; r0 < N && rc == QF_OK; r0 += chunk) {
+        const int64_t rows = std::min(chunk, N - r0);
+        rc = launch_apply<qf::APPLY_EMIT_NODE>(&f, d->X_train_dev + r0 * d->n_features, rows, d->n_features,
+                                                d_idx + r0 * T, nullptr, 0, T, st);
+    }
+    f.d_nodes = nullptr;                                 // not owned
+    f.d_roots = nullptr;
+    if (rc != QF_OK) return rc;
+    const unsigned grid = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, int64_t(prop.multiProcessorCount) * 32));
+    qf::csr_count_kernel<<<grid, 256, 0, st>>>(d_idx, d->counts_dev, total, leaf_cnt, leaf_sum);
+    qf::csr_block_sum_kernel<<<static_cast<unsigned>(n_blocks), 256, 0, st>>>(leaf_cnt, n_nodes, block_sum);
+    qf::csr_scan_sums_kernel<<<1, 1024, 0, st>>>(block_sum, n_blocks, block_sum + n_blocks);
+    QF_CUDA_TRY(cudaGetLastError());
+    uint64_t n_members = 0;
+    QF_CUDA_TRY(cudaMemcpy(&n_members, block_sum + n_blocks, 8, cudaMemcpyDeviceToHost));
+    if (n_members > 0xFFFFFFFFull)
+        return qf::fail(QF_ERR_LIMIT, "qf_build_csr: more than 2^32-1 member entries in the forest");
+    if (static_cast<int64_t>(n_members) > d->members_capacity)
+        return qf::fail(QF_ERR_INVALID, "qf_build_csr: members_capacity too small");
+    uint2* nodes = reinterpret_cast<uint2*>(d->nodes_dev);
+    uint2* members = reinterpret_cast<uint2*>(d->members_dev);
+    qf::csr_leaf_record_kernel<<<static_cast<unsigned>(n_blocks), 256, 0, st>>>(nodes, leaf_cnt, n_nodes, block_sum, start);
+    qf::csr_scatter_kernel<<<grid, 256, 0, st>>>(d_idx, d->counts_dev, total, T, d->rank_dev, start, leaf_cnt, leaf_sum, members);
+    qf::csr_sort_small_kernel<<<static_cast<unsigned>((n_nodes + 255) / 256), 256, 0, st>>>(nodes, n_nodes, members, big,
+                                                                                          counters, counters + 1);
+    QF_CUDA_TRY(cudaGetLastError());
+    int host_counters[2] = {0, 0};
+    QF_CUDA_TRY(cudaMemcpy(host_counters, counters, 8, cudaMemcpyDeviceToHost));
+    if (host_counters[1])
+        return qf::fail(QF_ERR_LIMIT, "qf_build_csr: a leaf holds more than 4096 members; use the host flattener");
+    if (host_counters[0] > 0)
+        qf::csr_sort_big_kernel<<<static_cast<unsigned>(host_counters[0]), 256, 0, st>>>(nodes, big, members);
+    qf::csr_tree_stats_kernel<<<T, 256, 0, st>>>(nodes, d_offsets, d_inbag, d_maxleaf, d_sumsq);
+    QF_CUDA_TRY(cudaGetLastError());
+    std::vector<unsigned long long> h_inbag(T);
+    std::vector<uint32_t> h_max(T);
+    QF_CUDA_TRY(cudaMemcpy(h_inbag.data(), d_inbag, static_cast<size_t>(T) * 8, cudaMemcpyDeviceToHost));
+    QF_CUDA_TRY(cudaMemcpy(h_max.data(), d_maxleaf, static_cast<size_t>(T) * 4, cudaMemcpyDeviceToHost));
+    QF_CUDA_TRY(cudaMemcpy(d->sum_sq_out, d_sumsq, static_cast<size_t>(T) * 8, cudaMemcpyDeviceToHost));
+    for (int t = 0; t < T; ++t) {
+        d->inbag_out[t] = static_cast<int64_t>(h_inbag[t]);
+        d->max_leaf_members_out[t] = static_cast<int32_t>(h_max[t]);
+    }
+    *n_members_out = static_cast<int64_t>(n_members);
     return QF_OK;
 }
 

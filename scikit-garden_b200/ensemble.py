@@ -23,7 +23,7 @@ from sklearn.exceptions import NotFittedError
 from sklearn.utils import check_array, check_X_y
 
 from . import _native
-from .flatten import FlatForest, bootstrap_counts, flatten_forest
+from .flatten import FlatForest, bootstrap_counts, flatten_forest, flatten_forest_device
 
 __all__ = ["RandomForestQuantileRegressor", "ExtraTreesQuantileRegressor"]
 
@@ -50,7 +50,8 @@ class _BaseForestQuantileRegressor(RegressorMixin, BaseEstimator):
     def __init__(self, n_estimators=10, criterion="mse", max_depth=None, min_samples_split=2,
                  min_samples_leaf=1, min_weight_fraction_leaf=0.0, max_features="auto",
                  max_leaf_nodes=None, bootstrap=True, oob_score=False, n_jobs=1,
-                 random_state=None, verbose=0, warm_start=False, *, device=0, mode="exact"):
+                 random_state=None, verbose=0, warm_start=False, *, device=0, mode="exact",
+                 builder="host"):
         self.n_estimators = n_estimators
         self.criterion = criterion
         self.max_depth = max_depth
@@ -67,6 +68,7 @@ class _BaseForestQuantileRegressor(RegressorMixin, BaseEstimator):
         self.warm_start = warm_start
         self.device = device
         self.mode = mode
+        self.builder = builder        # "host": qf_pack_tree; "device": qf_build_csr (member lists on the GPU)
 
     # -- fit (CPU, scikit-learn builders) -------------------------------------------------
     def _make_forest(self):
@@ -102,6 +104,12 @@ class _BaseForestQuantileRegressor(RegressorMixin, BaseEstimator):
         N = len(y)
         trees = [e.tree_ for e in self.estimators_]
         workers = self._workers()
+        if self.builder not in ("host", "device"):
+            raise ValueError("builder must be 'host' or 'device'")
+        if self.builder == "device":
+            counts = [bootstrap_counts(e.random_state, N) for e in self.estimators_] if self.bootstrap else None
+            return flatten_forest_device(trees, X, counts, y, X.shape[1], sorter=np.argsort(y),
+                                         n_jobs=workers, device=self.device)
 
         def leaves_of(t):                         # tree.py:101 (all N samples, incl. out-of-bag)
             return trees[t].apply(X)
@@ -216,7 +224,10 @@ class _BaseForestQuantileRegressor(RegressorMixin, BaseEstimator):
 
         def validated():
             for X in chunks:
-                yield self._validate_X(X)
+                if np.ndim(X) == 2 and np.shape(X)[0] == 0 and np.shape(X)[1] == self.n_features_:
+                    yield np.empty((0, self.n_features_), dtype=np.float32)     # an empty chunk is fine in a stream
+                else:
+                    yield self._validate_X(X)
         for out in dev.predict_stream(validated(), qs, mode=self._mode()):
             yield out[:, 0] if scalar else out
 

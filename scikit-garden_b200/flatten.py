@@ -197,3 +197,116 @@ def flatten_forest(trees: Sequence, train_leaves, counts, y_train, n_features: i
         leaf_values=leaf_values, max_row_members=int(stats[:, 0].sum()),
         expected_row_members=float((stats[:, 2] / np.maximum(inbag, 1)).sum()),
         max_depth=int(stats[:, 1].max()), sorter=sorter)
+
+
+def flatten_forest_device(trees: Sequence, X_train, counts, y_train, n_features: int,
+                          sorter: Optional[np.ndarray] = None, n_jobs: Optional[int] = None,
+                          unit_weights: bool = False, device: int = 0) -> FlatForest:
+    """Same result as :func:`flatten_forest`, bit for bit, with the member lists built on
+    the GPU (``qf_build_csr``, csrc/csr_builder.cuh): no ``tree_.apply(X_train)`` on the CPU
+    (tree.py:98-101) and no per-sample host loop (ensemble.py:87-101).  Only the tree
+    STRUCTURE is packed on the host.  Raises ``QFError`` (QF_ERR_LIMIT) when a leaf holds
+    more than 4096 members -- use :func:`flatten_forest` for such shallow trees.
+
+    X_train : (N, F) training rows as given to fit (cast to float32 like ensemble.py:79).
+    counts  : as for :func:`flatten_forest` (per-tree multiplicity vectors or None).
+    """
+    import torch
+    L = _native.lib()
+    T = len(trees)
+    if T == 0:
+        raise ValueError("empty forest")
+    y_train = np.asarray(y_train)
+    N = int(y_train.shape[0])
+    if sorter is None:
+        sorter = np.argsort(y_train)                      # ensemble.py:133
+    sorter = np.ascontiguousarray(sorter, dtype=np.int64)
+    y_sorted = np.ascontiguousarray(np.asarray(y_train, dtype=np.float32)[sorter])   # utils.py:46,52
+    feature_bits = max(1, int(n_features - 1).bit_length())
+    arrays = [_tree_arrays(t) for t in trees]
+    node_counts = np.array([a[0].shape[0] for a in arrays], dtype=np.int64)
+    tree_offsets = np.concatenate([[0], np.cumsum(node_counts)]).astype(np.int64)
+    n_nodes = int(tree_offsets[-1])
+    nodes = np.empty(n_nodes, dtype=np.uint64)
+    node_ids = np.empty(n_nodes, dtype=np.int32)
+    leaf_values = np.empty(n_nodes, dtype=np.float64)
+    depths = np.zeros(T, dtype=np.int64)
+
+    def pack(t):                                          # structure only (train_leaves = NULL)
+        left, right, feat, thr, val = arrays[t]
+        n0, n1 = int(tree_offsets[t]), int(tree_offsets[t + 1])
+        depth = C.c_int32(0)
+        nodes_t, ids_t = nodes[n0:n1], node_ids[n0:n1]
+        rc = L.qf_pack_tree(n1 - n0, _ptr(left), _ptr(right), _ptr(feat), _ptr(thr), feature_bits,
+                            0, None, None, None, 0, _ptr(nodes_t), _ptr(ids_t), None,
+                            None, None, C.byref(depth), None)
+        if rc != 0:
+            raise _native.QFError(rc, "tree %d: %s" % (t, _native.last_error()))
+        leaf_values[n0:n1] = val[ids_t]
+        depths[t] = depth.value
+
+    workers = n_jobs if n_jobs and n_jobs > 0 else min(T, os.cpu_count() or 1)
+    if workers > 1:
+        with ThreadPoolExecutor(workers) as ex:
+            list(ex.map(pack, range(T)))
+    else:
+        for t in range(T):
+            pack(t)
+
+    if counts is None or all(c is None for c in counts):
+        counts_nt, capacity = None, N * T
+    else:
+        cm = np.stack([np.ones(N, dtype=np.int64) if c is None else np.asarray(c, dtype=np.int64) for c in counts])
+        if cm.min() < 0 or cm.max() > 65535:
+            raise ValueError("bootstrap multiplicities must be in [0, 65535] for the device builder")
+        capacity = int(np.count_nonzero(cm))
+        counts_nt = np.ascontiguousarray(cm.T.astype(np.uint16))        # [N][T]
+    rank = np.empty(N, dtype=np.int32)
+    rank[sorter] = np.arange(N, dtype=np.int32)
+
+    dev = torch.device("cuda", device)
+    with torch.cuda.device(dev):
+        d_nodes = torch.from_numpy(nodes.view(np.int64)).to(dev)
+        d_X = torch.from_numpy(np.ascontiguousarray(X_train, dtype=np.float32)).to(dev)
+        d_rank = torch.from_numpy(rank).to(dev)
+        d_counts = None if counts_nt is None else torch.from_numpy(counts_nt.view(np.int16)).to(dev)
+        d_members = torch.empty(max(capacity, 1), dtype=torch.int64, device=dev)
+        inbag = np.zeros(T, dtype=np.int64)
+        max_leaf = np.zeros(T, dtype=np.int32)
+        sum_sq = np.zeros(T, dtype=np.float64)
+        desc = _native.CsrBuildDesc()
+        desc.device = device
+        desc.n_trees, desc.n_features, desc.feature_bits = T, int(n_features), feature_bits
+        desc.n_train, desc.n_nodes = N, n_nodes
+        desc.nodes_dev = d_nodes.data_ptr()
+        desc.tree_offsets = tree_offsets.ctypes.data
+        desc.X_train_dev = d_X.data_ptr()
+        desc.rank_dev = d_rank.data_ptr()
+        desc.counts_dev = None if d_counts is None else d_counts.data_ptr()
+        desc.members_dev = d_members.data_ptr()
+        desc.members_capacity = capacity
+        desc.inbag_out = inbag.ctypes.data
+        desc.max_leaf_members_out = max_leaf.ctypes.data
+        desc.sum_sq_out = sum_sq.ctypes.data
+        torch.cuda.synchronize()
+        n_members = C.c_int64(0)
+        _native.check(L.qf_build_csr(C.byref(desc), C.byref(n_members)))
+        if n_members.value != capacity:
+            raise RuntimeError("device builder produced %d members, expected %d" % (n_members.value, capacity))
+        nodes = d_nodes.cpu().numpy().view(np.uint64)
+        members = d_members[:capacity].cpu().numpy().view(np.uint64)
+    if unit_weights:
+        members = members.copy()
+        members &= np.uint64(0xFFFFFFFF)
+        members |= np.uint64(0x3F800000) << np.uint64(32)
+    member_offsets = np.concatenate([[0], np.cumsum(inbag)]).astype(np.int64)
+    identity = bool(np.array_equal(
+        node_ids, np.concatenate([np.arange(c, dtype=np.int32) for c in node_counts])))
+    return FlatForest(
+        n_trees=T, n_features=int(n_features), feature_bits=feature_bits, n_train=N,
+        nodes=nodes, tree_offsets=tree_offsets, node_ids=None if identity else node_ids,
+        members=members, member_offsets=member_offsets, y_sorted=y_sorted,
+        leaf_values=leaf_values, max_row_members=int(max_leaf.sum()),
+        expected_row_members=float((sum_sq / np.maximum(inbag, 1)).sum()),
+        max_depth=int(depths.max()), sorter=sorter)
+
