@@ -191,6 +191,17 @@ int qf_forest_predict_mean(qf_forest* f, const float* X_dev, int64_t n_rows, int
                            double* out_dev, void* workspace_dev, int64_t workspace_bytes,
                            void* stream);
 
+/* Mean and standard deviation of y | x: the reference's `return_std` forests
+ * (skgarden/forest.py:133-178 `_return_std`, :332-362 RandomForestRegressor.predict, :516-548
+ * ExtraTreesRegressor.predict): std = sqrt(max(0, mean_t(max(impurity, min_variance) + value^2)
+ * - mean^2)), float64, trees in increasing order.  qf_forest_set_leaf_impurity uploads
+ * tree_.impurity per PACKED node (host or device pointer, [n_nodes]); it must be called once
+ * before qf_forest_predict_mean_std.  Outputs: (n_rows,) float64 each. */
+int qf_forest_set_leaf_impurity(qf_forest* f, const double* impurity);
+int qf_forest_predict_mean_std(qf_forest* f, const float* X_dev, int64_t n_rows, int64_t ldx,
+                               double min_variance, double* mean_out_dev, double* std_out_dev,
+                               void* workspace_dev, int64_t workspace_bytes, void* stream);
+
 /* End-to-end variant of qf_forest_predict_quantiles on HOST buffers: chunks the rows,
  * copies each chunk host->device, runs the kernels and copies the result back,
  * pipelined over three internal streams (H2D, kernels, D2H) and a ring of chunk buffers.  X_host / out_host should be pinned for

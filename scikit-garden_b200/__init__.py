@@ -6,6 +6,7 @@ name to this directory).  Public surface = the reference's for this path
 
     RandomForestQuantileRegressor, ExtraTreesQuantileRegressor,
     DecisionTreeQuantileRegressor, ExtraTreeQuantileRegressor
+    RandomForestRegressor, ExtraTreesRegressor      (skgarden/forest.py: predict(X, return_std=True))
 
 plus the lower-level pieces the estimators are made of: ``flatten_forest`` /
 ``FlatForest`` (host layout), ``DeviceForest`` (HBM-resident forest + kernel calls).
@@ -13,9 +14,11 @@ plus the lower-level pieces the estimators are made of: ``flatten_forest`` /
 from .ensemble import ExtraTreesQuantileRegressor, RandomForestQuantileRegressor
 from .flatten import FlatForest, bootstrap_counts, flatten_forest, flatten_forest_device
 from .tree import DecisionTreeQuantileRegressor, ExtraTreeQuantileRegressor
+from .forest import ExtraTreesRegressor, RandomForestRegressor
 
 __all__ = ["RandomForestQuantileRegressor", "ExtraTreesQuantileRegressor",
-           "DecisionTreeQuantileRegressor", "ExtraTreeQuantileRegressor", "FlatForest",
+           "DecisionTreeQuantileRegressor", "ExtraTreeQuantileRegressor",
+           "RandomForestRegressor", "ExtraTreesRegressor", "FlatForest",
            "flatten_forest", "flatten_forest_device", "bootstrap_counts", "DeviceForest"]
 
 

@@ -71,6 +71,8 @@ SIGNATURES = {
     "qf_forest_apply": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _I64, _P]),
     "qf_forest_predict_quantiles": (C.c_int, [_P, _P, _I64, _I64, _P, _I32, _P, _I32, _P, _I64, _P]),
     "qf_forest_predict_mean": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _I64, _P]),
+    "qf_forest_set_leaf_impurity": (C.c_int, [_P, _P]),
+    "qf_forest_predict_mean_std": (C.c_int, [_P, _P, _I64, _I64, C.c_double, _P, _P, _P, _I64, _P]),
     "qf_forest_predict_quantiles_host": (C.c_int, [_P, _P, _I64, _I64, _P, _I32, _P, _I32, _I64]),
     "qf_forest_plan": (C.c_int, [_P, _I64, _P]),
     "qf_forest_last_launches": (C.c_int, [_P]),

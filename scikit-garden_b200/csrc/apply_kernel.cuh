@@ -274,4 +274,31 @@ __global__ void mean_kernel(const int32_t* __restrict__ node_idx, int64_t n, int
     out[row] = __ddiv_rn(acc, static_cast<double>(T));  // forest.py:1129
 }
 
+// Mean and standard deviation of y | x -- skgarden/forest.py:133-178 (`_return_std`) on top of
+// ForestRegressor.predict (forest.py:332-362, :516-548).  Per row, float64, trees in
+// increasing order like the reference's loop (forest.py:165-174):
+//   s   += max(impurity[leaf], min_variance) + value[leaf]^2
+//   std  = sqrt(max(0, s / T - mean^2)),   mean = (sum of value[leaf]) / T
+__global__ void mean_std_kernel(const int32_t* __restrict__ node_idx, int64_t n, int T,
+                                const double* __restrict__ values, const double* __restrict__ impurity,
+                                double min_variance, double* __restrict__ mean_out, double* __restrict__ std_out) {
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const int32_t* __restrict__ idx = node_idx + row * T;
+    double acc = 0.0, s = 0.0;
+    for (int t = 0; t < T; ++t) {
+        const double m = __ldg(values + idx[t]);
+        double v = __ldg(impurity + idx[t]);
+        if (v < min_variance) v = min_variance;          // forest.py:170
+        acc = __dadd_rn(acc, m);
+        s = __dadd_rn(s, __dadd_rn(v, __dmul_rn(m, m)));   // forest.py:172
+    }
+    const double mean = __ddiv_rn(acc, static_cast<double>(T));
+    s = __ddiv_rn(s, static_cast<double>(T));           // forest.py:174
+    s = __dsub_rn(s, __dmul_rn(mean, mean));             // forest.py:175
+    if (s < 0.0) s = 0.0;                                // forest.py:176
+    mean_out[row] = mean;
+    std_out[row] = __dsqrt_rn(s);                        // forest.py:177
+}
+
 }  // namespace qf

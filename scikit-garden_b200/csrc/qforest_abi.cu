@@ -69,6 +69,7 @@ struct qf_forest {
     uint2* d_members = nullptr;
     float* d_y_sorted = nullptr;
     double* d_values = nullptr;
+    double* d_impurity = nullptr;          // tree_.impurity per packed node (qf_forest_set_leaf_impurity)
     int64_t device_bytes = 0;
     std::vector<uint32_t> tree_max_leaf;   // members of the largest leaf of every tree
     bool unit_leaves = false;              // every leaf of every tree holds exactly one member
@@ -620,6 +621,7 @@ void qf_forest_destroy(qf_forest* f) {
     cudaFree(f->d_members);
     cudaFree(f->d_y_sorted);
     cudaFree(f->d_values);
+    cudaFree(f->d_impurity);
     for (cudaEvent_t e : f->event_pool) cudaEventDestroy(e);
     {
         HostPipe& hp = f->pipe;
@@ -776,6 +778,47 @@ int qf_forest_predict_mean(qf_forest* f, const float* X, int64_t n, int64_t ldx,
         if (rc != QF_OK) return rc;
         qf::mean_kernel<<<static_cast<unsigned>((rows + 127) / 128), 128, 0, st>>>(idx, rows, f->T, f->d_values,
                                                                                    out + r0);
+        QF_CUDA_TRY(cudaGetLastError());
+        ++f->launches;
+    }
+    return QF_OK;
+}
+
+int qf_forest_set_leaf_impurity(qf_forest* f, const double* impurity) {
+    if (!f || !impurity) return qf::fail(QF_ERR_INVALID, "qf_forest_set_leaf_impurity: null argument");
+    DeviceGuard guard(f->device);
+    if (!f->d_impurity) {
+        QF_CUDA_TRY(cudaMalloc(&f->d_impurity, static_cast<size_t>(f->n_nodes) * 8));
+        f->device_bytes += f->n_nodes * 8;
+    }
+    QF_CUDA_TRY(cudaMemcpy(f->d_impurity, impurity, static_cast<size_t>(f->n_nodes) * 8, cudaMemcpyDefault));
+    return QF_OK;
+}
+
+int qf_forest_predict_mean_std(qf_forest* f, const float* X, int64_t n, int64_t ldx, double min_variance,
+                               double* mean_out, double* std_out, void* ws, int64_t ws_bytes, void* stream) {
+    int rc = check_forest_call(f, X, n, ldx, mean_out, "qf_forest_predict_mean_std");
+    if (rc != QF_OK) return rc;
+    if (!std_out) return qf::fail(QF_ERR_INVALID, "qf_forest_predict_mean_std: null output");
+    if (!f->d_values || !f->d_impurity)
+        return qf::fail(QF_ERR_INVALID, "qf_forest_predict_mean_std: forest has no leaf_values / leaf impurities");
+    reset_call_counters(f);
+    if (n == 0) return QF_OK;
+    DeviceGuard guard(f->device);
+    const Plan pl = make_plan(f, n);
+    if (ws_bytes < pl.total || !ws)
+        return qf::fail(QF_ERR_WORKSPACE, "qf_forest_predict_mean_std: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int32_t* idx = reinterpret_cast<int32_t*>(static_cast<unsigned char*>(ws) + pl.off_seg);
+    for (int64_t r0 = 0; r0 < n; r0 += pl.chunk_rows) {
+        const int64_t rows = std::min(pl.chunk_rows, n - r0);
+        const int* order = nullptr;
+        rc = build_locality_order(f, X + r0 * ldx, rows, ldx, pl, static_cast<unsigned char*>(ws), st, &order);
+        if (rc != QF_OK) return rc;
+        rc = launch_apply<qf::APPLY_EMIT_NODE>(f, X + r0 * ldx, rows, ldx, idx, order, 0, f->T, st);
+        if (rc != QF_OK) return rc;
+        qf::mean_std_kernel<<<static_cast<unsigned>((rows + 127) / 128), 128, 0, st>>>(
+            idx, rows, f->T, f->d_values, f->d_impurity, min_variance, mean_out + r0, std_out + r0);
         QF_CUDA_TRY(cudaGetLastError());
         ++f->launches;
     }

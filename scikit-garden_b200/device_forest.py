@@ -61,6 +61,10 @@ class DeviceForest:
         _native.check(self._lib.qf_forest_create(C.byref(desc), C.byref(handle)))
         self._h = handle
         self._ws = None
+        self.has_impurity = flat.leaf_impurity is not None and with_leaf_values
+        if self.has_impurity:
+            imp = np.ascontiguousarray(flat.leaf_impurity, dtype=np.float64)
+            _native.check(self._lib.qf_forest_set_leaf_impurity(self._h, C.c_void_p(imp.ctypes.data)))
 
     # -- lifetime ---------------------------------------------------------------------
     def close(self):
@@ -163,6 +167,23 @@ class DeviceForest:
             self._h, C.c_void_p(X.data_ptr()), n, X.stride(0), C.c_void_p(out.data_ptr()),
             C.c_void_p(ws.data_ptr()), ws.numel(), self._stream()))
         return out
+
+    def predict_mean_std(self, X, min_variance: float = 0.0):
+        """((n,), (n,)) float64 CUDA tensors: forest mean and std(y | x) of the reference's
+        ``return_std`` forests (forest.py:133-178, :332-362)."""
+        torch = _torch()
+        if not self.has_impurity:
+            raise RuntimeError("this forest was flattened without tree impurities")
+        X = self._check_X(X)
+        n = X.shape[0]
+        mean = torch.empty((n,), dtype=torch.float64, device=X.device)
+        std = torch.empty((n,), dtype=torch.float64, device=X.device)
+        ws, _ = self._workspace(n, 1)
+        _native.check(self._lib.qf_forest_predict_mean_std(
+            self._h, C.c_void_p(X.data_ptr()), n, X.stride(0), float(min_variance),
+            C.c_void_p(mean.data_ptr()), C.c_void_p(std.data_ptr()),
+            C.c_void_p(ws.data_ptr()), ws.numel(), self._stream()))
+        return mean, std
 
     # -- host-buffer end-to-end call ------------------------------------------------------
     def predict_quantiles_host(self, X_host: np.ndarray, quantiles: Sequence[float],

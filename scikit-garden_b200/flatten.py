@@ -56,6 +56,7 @@ class FlatForest:
     expected_row_members: float  # sum over trees of E[leaf size] for a training-like row
     max_depth: int
     sorter: np.ndarray = field(repr=False, default=None)   # int64 [N] np.argsort(y_train_)
+    leaf_impurity: Optional[np.ndarray] = field(repr=False, default=None)   # float64 [n_nodes] tree_.impurity
 
     @property
     def n_nodes(self) -> int:
@@ -80,7 +81,8 @@ class FlatForest:
                  y_sorted=self.y_sorted, leaf_values=self.leaf_values,
                  max_row_members=self.max_row_members,
                  expected_row_members=self.expected_row_members, max_depth=self.max_depth,
-                 sorter=self.sorter)
+                 sorter=self.sorter,
+                 leaf_impurity=np.zeros(0) if self.leaf_impurity is None else self.leaf_impurity)
 
     @classmethod
     def load(cls, path: str) -> "FlatForest":
@@ -91,7 +93,8 @@ class FlatForest:
                    None if node_ids.size == 0 else node_ids, z["members"],
                    z["member_offsets"], z["y_sorted"], z["leaf_values"],
                    int(z["max_row_members"]), float(z["expected_row_members"]),
-                   int(z["max_depth"]), z["sorter"])
+                   int(z["max_depth"]), z["sorter"],
+                   z["leaf_impurity"] if "leaf_impurity" in z.files and z["leaf_impurity"].size else None)
 
 
 def _tree_arrays(tree):
@@ -104,6 +107,13 @@ def _tree_arrays(tree):
     val = np.asarray(t.value, dtype=np.float64)
     val = np.ascontiguousarray(val.reshape(val.shape[0], -1)[:, 0])
     return left, right, feat, thr, val
+
+
+def _tree_impurity(tree):
+    """tree_.impurity (float64 per node) or None for duck-typed trees without it."""
+    t = getattr(tree, "tree_", tree)
+    imp = getattr(t, "impurity", None)
+    return None if imp is None else np.ascontiguousarray(imp, dtype=np.float64)
 
 
 def flatten_forest(trees: Sequence, train_leaves, counts, y_train, n_features: int,
@@ -152,6 +162,8 @@ def flatten_forest(trees: Sequence, train_leaves, counts, y_train, n_features: i
     node_ids = np.empty(int(tree_offsets[-1]), dtype=np.int32)
     members = np.empty(int(member_offsets[-1]), dtype=np.uint64)
     leaf_values = np.empty(int(tree_offsets[-1]), dtype=np.float64)
+    impurities = [_tree_impurity(t) for t in trees]
+    leaf_impurity = None if any(i is None for i in impurities) else np.empty(int(tree_offsets[-1]), dtype=np.float64)
     stats = np.zeros((T, 3), dtype=np.float64)            # max_leaf_members, depth, sum_sq
 
     def pack(t):
@@ -175,6 +187,8 @@ def flatten_forest(trees: Sequence, train_leaves, counts, y_train, n_features: i
         if n_inbag.value != m1 - m0:
             raise RuntimeError("tree %d: in-bag count mismatch" % t)
         leaf_values[n0:n1] = val[ids_t]
+        if leaf_impurity is not None:
+            leaf_impurity[n0:n1] = impurities[t][ids_t]
         stats[t] = (max_members.value, depth.value, sum_sq.value)
 
     workers = n_jobs if n_jobs and n_jobs > 0 else min(T, os.cpu_count() or 1)
@@ -196,7 +210,7 @@ def flatten_forest(trees: Sequence, train_leaves, counts, y_train, n_features: i
         members=members, member_offsets=member_offsets, y_sorted=y_sorted,
         leaf_values=leaf_values, max_row_members=int(stats[:, 0].sum()),
         expected_row_members=float((stats[:, 2] / np.maximum(inbag, 1)).sum()),
-        max_depth=int(stats[:, 1].max()), sorter=sorter)
+        max_depth=int(stats[:, 1].max()), sorter=sorter, leaf_impurity=leaf_impurity)
 
 
 def flatten_forest_device(trees: Sequence, X_train, counts, y_train, n_features: int,
@@ -230,6 +244,8 @@ def flatten_forest_device(trees: Sequence, X_train, counts, y_train, n_features:
     nodes = np.empty(n_nodes, dtype=np.uint64)
     node_ids = np.empty(n_nodes, dtype=np.int32)
     leaf_values = np.empty(n_nodes, dtype=np.float64)
+    impurities = [_tree_impurity(t) for t in trees]
+    leaf_impurity = None if any(i is None for i in impurities) else np.empty(n_nodes, dtype=np.float64)
     depths = np.zeros(T, dtype=np.int64)
 
     def pack(t):                                          # structure only (train_leaves = NULL)
@@ -243,6 +259,8 @@ def flatten_forest_device(trees: Sequence, X_train, counts, y_train, n_features:
         if rc != 0:
             raise _native.QFError(rc, "tree %d: %s" % (t, _native.last_error()))
         leaf_values[n0:n1] = val[ids_t]
+        if leaf_impurity is not None:
+            leaf_impurity[n0:n1] = impurities[t][ids_t]
         depths[t] = depth.value
 
     workers = n_jobs if n_jobs and n_jobs > 0 else min(T, os.cpu_count() or 1)
@@ -256,11 +274,19 @@ def flatten_forest_device(trees: Sequence, X_train, counts, y_train, n_features:
     if counts is None or all(c is None for c in counts):
         counts_nt, capacity = None, N * T
     else:
-        cm = np.stack([np.ones(N, dtype=np.int64) if c is None else np.asarray(c, dtype=np.int64) for c in counts])
-        if cm.min() < 0 or cm.max() > 65535:
-            raise ValueError("bootstrap multiplicities must be in [0, 65535] for the device builder")
-        capacity = int(np.count_nonzero(cm))
-        counts_nt = np.ascontiguousarray(cm.T.astype(np.uint16))        # [N][T]
+        cm = np.empty((T, N), dtype=np.uint16)            # [T][N] here, transposed on the device
+        capacity = 0
+        for t, c in enumerate(counts):
+            if c is None:
+                cm[t] = 1
+                capacity += N
+                continue
+            c = np.asarray(c)
+            if c.min() < 0 or c.max() > 65535:
+                raise ValueError("bootstrap multiplicities must be in [0, 65535] for the device builder")
+            cm[t] = c
+            capacity += int(np.count_nonzero(c))
+        counts_nt = cm
     rank = np.empty(N, dtype=np.int32)
     rank[sorter] = np.arange(N, dtype=np.int32)
 
@@ -269,7 +295,7 @@ def flatten_forest_device(trees: Sequence, X_train, counts, y_train, n_features:
         d_nodes = torch.from_numpy(nodes.view(np.int64)).to(dev)
         d_X = torch.from_numpy(np.ascontiguousarray(X_train, dtype=np.float32)).to(dev)
         d_rank = torch.from_numpy(rank).to(dev)
-        d_counts = None if counts_nt is None else torch.from_numpy(counts_nt.view(np.int16)).to(dev)
+        d_counts = None if counts_nt is None else torch.from_numpy(counts_nt.view(np.int16)).to(dev).t().contiguous()   # [N][T]
         d_members = torch.empty(max(capacity, 1), dtype=torch.int64, device=dev)
         inbag = np.zeros(T, dtype=np.int64)
         max_leaf = np.zeros(T, dtype=np.int32)
@@ -308,5 +334,5 @@ def flatten_forest_device(trees: Sequence, X_train, counts, y_train, n_features:
         members=members, member_offsets=member_offsets, y_sorted=y_sorted,
         leaf_values=leaf_values, max_row_members=int(max_leaf.sum()),
         expected_row_members=float((sum_sq / np.maximum(inbag, 1)).sum()),
-        max_depth=int(depths.max()), sorter=sorter)
+        max_depth=int(depths.max()), sorter=sorter, leaf_impurity=leaf_impurity)
 
