@@ -23,6 +23,12 @@ CONFIGS = {
                      n_features=20, quantiles=[5.0, 50.0, 95.0], label="C2 at 1/5 scale"),
     "c3q": dict(kind="et", n_estimators=500, min_samples_leaf=5, n_train=250_000, n_test=250_000,
                 n_features=50, quantiles=[5.0, 50.0, 95.0], label="C3 with a quarter of the rows (same T, leaf size)"),
+    "c4q": dict(kind="rf", n_estimators=200, min_samples_leaf=1, n_train=250_000, n_test=250_000,
+                n_features=20, quantiles=[float(q) for q in range(1, 100)],
+                label="C4 with a quarter of the rows (RFQR T=200 msl=1, 99-point quantile grid)"),
+    "c5q": dict(kind="et", n_estimators=1000, min_samples_leaf=5, n_train=250_000, n_test=1_000_000,
+                n_features=64, quantiles=[5.0, 50.0, 95.0],
+                label="C5 reduced (ETQR T=1000 msl=5, 250k x 64 train, 1M test rows per GPU through the host pipeline)"),
     "c3_small": dict(kind="et", n_estimators=50, min_samples_leaf=5, n_train=100_000, n_test=50_000,
                      n_features=50, quantiles=[5.0, 50.0, 95.0], label="C3 at 1/10 scale"),
 }
