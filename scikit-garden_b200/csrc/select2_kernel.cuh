@@ -459,20 +459,21 @@ quantile_select2_kernel(const QuantileParams p, const __grid_constant__ Quantile
                     const float inv = __fdiv_rn(1.0f, fx_scale);
                     const float s = __fdiv_rn(100.0f, __fmul_rn(static_cast<float>(total_w), inv));   // utils.py:69,72
                     const uint32_t re = (bq << shift1) + e;
+                    // the three candidate values are requested together (one HBM latency, not two)
                     const float a_e = __ldg(p.y_sorted + re);
+                    const float a_s = __ldg(p.y_sorted + (rs != NONE ? rs : re));
+                    const float a_p = __ldg(p.y_sorted + (rp != NONE ? rp : re));
                     const float p_e = plotting_position(s, __fmul_rn(static_cast<float>(Ce), inv),
                                                         __fmul_rn(static_cast<float>(We), inv));
                     float result = a_e;
                     if (static_cast<double>(p_e) < qv) {                    // interval (e, succ)
                         if (rs != NONE) {               // else q lies beyond the last entry: a_last (utils.py:74-75)
-                            const float a_s = __ldg(p.y_sorted + rs);
                             const float p_s = plotting_position(s, __fmul_rn(static_cast<float>(Ce + Ws), inv),
                                                                 __fmul_rn(static_cast<float>(Ws), inv));
                             const float frac = __fdiv_rn(__fsub_rn(static_cast<float>(qv), p_e), __fsub_rn(p_s, p_e));
                             result = __fadd_rn(a_e, __fmul_rn(frac, __fsub_rn(a_s, a_e)));
                         }
                     } else if (rp != NONE) {            // interval (pred, e); else before the first entry: a_0 (utils.py:76-77)
-                        const float a_p = __ldg(p.y_sorted + rp);
                         const float p_p = plotting_position(s, __fmul_rn(static_cast<float>(Ce - We), inv),
                                                             __fmul_rn(static_cast<float>(Wp), inv));
                         const float frac = __fdiv_rn(__fsub_rn(static_cast<float>(qv), p_p), __fsub_rn(p_e, p_p));
