@@ -278,8 +278,31 @@ quantile_warp_kernel(const QuantileParams p, const __grid_constant__ QuantileLis
         return;
     }
 
-    // 6. lane 0: float32 running sum in rank order (utils.py:68), 4 entries per shared access
-    if (lane == 0) {
+    // 6. float32 running sum in rank order (utils.py:68).
+    //    UNIT: every member weight is f32(c / c) = 1.0, so every merged weight and every partial
+    //    sum is an integer below 2^24 -- float32 addition is exact on those and the sequential
+    //    sum equals a warp scan, bit for bit.  Otherwise lane 0 adds in sequence, 4 entries per
+    //    shared access.
+    if (UNIT) {
+        float wv[E], run = 0.0f;
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            wv[i] = (lane * E + i < m) ? B[lane * E + i] : 0.0f;
+            run = __fadd_rn(run, wv[i]);
+        }
+        float incl_f = run;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float u = __shfl_up_sync(0xffffffffu, incl_f, d);
+            if (lane >= d) incl_f = __fadd_rn(incl_f, u);
+        }
+        float C = __fsub_rn(incl_f, run);
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            C = __fadd_rn(C, wv[i]);
+            if (lane * E + i < m) Cc[lane * E + i] = C;
+        }
+    } else if (lane == 0) {
         float C = 0.0f;
         for (int c = 0; c < m; c += 4) {
             const float4 w4 = *reinterpret_cast<const float4*>(B + c);

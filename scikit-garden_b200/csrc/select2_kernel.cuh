@@ -10,9 +10,9 @@
 //
 //   table    every warp owns T/8 consecutive leaves of the row.  It turns their (start, count)
 //            pairs -- fetched one row ahead into registers -- into a flat table of aligned
-//            128-bit member PAIRS (entry = even member index | "first slot is outside the
-//            list" | "second slot is outside the list"), so that both passes below run with all
-//            32 lanes busy whatever the leaf sizes (4 lanes per leaf wasted half of them).
+//            128-bit member PAIRS (entry = pair index | "first slot is outside the list" |
+//            "second slot is outside the list"), so that both passes below run with all 32
+//            lanes busy whatever the leaf sizes (4 lanes per leaf wasted half of them).
 //   pass 1   one 128-bit load per lane and pair; ONE shared-memory atomic per member: weight
 //            histogram over NB buckets of the rank axis (bucket = rank >> shift1).
 //   scan     block scan of the bucket weights, kept in registers (BPT per thread).  Every
@@ -22,7 +22,7 @@
 //              bp = last non-empty bucket before bq, bn = first non-empty bucket after bq
 //            (bp / bn hold the neighbours of the crossing entry when it is the first / last
 //            entry of bq).  A 16-bit table entry per bucket says which slot arrays it feeds.
-//   pass 2   members are streamed again (L1 / L2 hits); a member whose bucket feeds nothing
+//   pass 2   members are streamed again (L2 hits); a member whose bucket feeds nothing
 //            costs a shift, a 16-bit shared load and a test.  The few others are added to
 //            the slot arrays [bp | bq | bn] of their percentile(s) at single-rank resolution.
 //   select   one WARP per percentile scans its bq slots (<= 512, four 128-bit loads per

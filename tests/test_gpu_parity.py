@@ -332,3 +332,57 @@ def test_one_member_per_leaf_gather_is_identical():
     est._device_forest.set_option("warp_unit", 0)
     assert_array_equal(est.predict(X[600:], quantile=qs), got)
 
+
+@pytest.mark.parametrize("T,msl,bootstrap", [(1, 8, False), (3, 30, True), (600, 12, True), (1030, 6, False)])
+def test_fast_mode_tree_counts_around_the_kernel_limits(T, msl, bootstrap):
+    # select2 keeps T / 256 leaves per lane (1..4): one tree, a handful, more than 512, and more
+    # than the 1024 it supports (-> multi-level kernel); all against the exact kernels
+    import skgarden_b200 as sg
+    rng = np.random.RandomState(T)
+    N, n, F = 6000, 700, 5
+    X = rng.randn(N + n, F).astype(np.float32)
+    y = 2 * X[:, 0] + np.sin(2 * X[:, 1]) + rng.randn(N + n)
+    est = sg.ExtraTreesQuantileRegressor(n_estimators=T, random_state=0, min_samples_leaf=msl,
+                                         bootstrap=bootstrap, max_depth=8, n_jobs=-1).fit(X[:N], y[:N])
+    qs = [0, 10, 50, 90, 100]
+    est._on_device().set_option("warp_elems", 0)
+    exact = est.predict(X[N:], quantile=qs)
+    est.mode = "fast"
+    fast = est.predict(X[N:], quantile=qs)
+    # 1e-4 of the scale of y; the 1030-tree forest gathers 24k members per row (total weight
+    # 1030): there the REFERENCE's float32 running sum has drifted by ~1e-3 of a weight by the
+    # time it reaches the tails, which moves its interpolation point -- fast mode (exact integer
+    # sums) is the more accurate of the two, and the bar is loosened accordingly
+    tol = (1e-3 if T > 1000 else 1e-4) * np.abs(y).max()
+    assert_allclose(fast, exact, rtol=1e-4, atol=tol)
+    assert_array_equal(fast[:, [0, -1]], exact[:, [0, -1]])
+    est._device_forest.set_option("select_impl", 1)
+    assert_array_equal(est.predict(X[N:], quantile=qs), fast)
+
+
+def test_one_member_per_leaf_forest_larger_than_the_warp_kernel():
+    # T = 300 single-member leaves: more than the 256 keys of the warp kernel -> overflow chain
+    import skgarden_b200 as sg
+    rng = np.random.RandomState(8)
+    X = rng.randn(500, 4).astype(np.float32)
+    y = X[:, 0] + rng.randn(500)
+    est = sg.RandomForestQuantileRegressor(n_estimators=300, random_state=0, n_jobs=-1).fit(X[:400], y[:400])
+    qs = [5, 50, 95]
+    got = est.predict(X[400:], quantile=qs)
+    index = O.SparseIndex(est.y_train_, est.y_train_leaves_, est.y_weights_, est._flat.sorter)
+    assert_array_equal(got, O.predict_sparse(index, est.apply(X[400:]), qs))
+
+
+def test_single_row_and_single_feature():
+    import skgarden_b200 as sg
+    rng = np.random.RandomState(2)
+    X = rng.randn(300, 1).astype(np.float32)
+    y = np.round(X[:, 0] + 0.3 * rng.randn(300), 1)
+    est = sg.RandomForestQuantileRegressor(n_estimators=7, random_state=0, min_samples_leaf=4).fit(X, y)
+    index = O.SparseIndex(est.y_train_, est.y_train_leaves_, est.y_weights_, est._flat.sorter)
+    for rows in (X[:1], X[5:6], X[:33]):
+        leaves = est.apply(rows)
+        assert_array_equal(leaves, O.forest_apply(est.estimators_, rows))
+        assert_array_equal(est.predict(rows, quantile=[25, 75]), O.predict_sparse(index, leaves, [25, 75]))
+        assert_array_equal(est.predict(rows), O.predict_mean(est.estimators_, rows, leaves))
+
