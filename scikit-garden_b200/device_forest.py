@@ -22,7 +22,8 @@ def _torch():
 class DeviceForest:
     """A flattened forest uploaded to one GPU (replicated per GPU when row-sharding)."""
 
-    def __init__(self, flat: FlatForest, device: int = 0, with_leaf_values: bool = True):
+    def __init__(self, flat: FlatForest, device: int = 0, with_leaf_values: bool = True,
+                 with_impurity: bool = False):
         torch = _torch()
         if not torch.cuda.is_available():
             raise RuntimeError("DeviceForest needs a CUDA device (sm_100); there is no CPU fallback")
@@ -61,7 +62,8 @@ class DeviceForest:
         _native.check(self._lib.qf_forest_create(C.byref(desc), C.byref(handle)))
         self._h = handle
         self._ws = None
-        self.has_impurity = flat.leaf_impurity is not None and with_leaf_values
+        # tree_.impurity per node is only needed by the return_std forests (predict_mean_std)
+        self.has_impurity = with_impurity and flat.leaf_impurity is not None and with_leaf_values
         if self.has_impurity:
             imp = np.ascontiguousarray(flat.leaf_impurity, dtype=np.float64)
             _native.check(self._lib.qf_forest_set_leaf_impurity(self._h, C.c_void_p(imp.ctypes.data)))
@@ -173,7 +175,8 @@ class DeviceForest:
         ``return_std`` forests (forest.py:133-178, :332-362)."""
         torch = _torch()
         if not self.has_impurity:
-            raise RuntimeError("this forest was flattened without tree impurities")
+            raise RuntimeError("create the DeviceForest with with_impurity=True (and a forest flattened "
+                               "from trees that carry tree_.impurity)")
         X = self._check_X(X)
         n = X.shape[0]
         mean = torch.empty((n,), dtype=torch.float64, device=X.device)

@@ -182,8 +182,10 @@ class _BaseForestQuantileRegressor(RegressorMixin, BaseEstimator):
         flat = self._check_fitted()
         if getattr(self, "_device_forest", None) is None:
             from .device_forest import DeviceForest
-            self._device_forest = DeviceForest(flat, device=self.device)
+            self._device_forest = DeviceForest(flat, device=self.device, with_impurity=self._needs_impurity)
         return self._device_forest
+
+    _needs_impurity = False            # the return_std forests (forest.py) upload tree_.impurity too
 
     def _mode(self):
         if self.mode not in ("exact", "fast"):

@@ -19,6 +19,8 @@ __all__ = ["RandomForestRegressor", "ExtraTreesRegressor"]
 
 
 class _BaseStdForestRegressor(_BaseForestQuantileRegressor):
+    _needs_impurity = True
+
     def __init__(self, n_estimators=10, criterion="mse", max_depth=None, min_samples_split=2,
                  min_samples_leaf=1, min_weight_fraction_leaf=0.0, max_features="auto",
                  max_leaf_nodes=None, bootstrap=True, oob_score=False, n_jobs=1,

@@ -69,7 +69,7 @@ def test_device_return_std_matches_reference(name):
     torch = pytest.importorskip("torch")
     import skgarden_b200 as sg
     g = _load(name)
-    dev = sg.DeviceForest(_flat(g), device=0)
+    dev = sg.DeviceForest(_flat(g), device=0, with_impurity=True)
     X = torch.from_numpy(np.ascontiguousarray(g.X_test)).cuda()
     for k, mv in enumerate(g.min_variance):
         mean, std = dev.predict_mean_std(X, float(mv))
