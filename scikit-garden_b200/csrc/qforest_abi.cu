@@ -3,6 +3,7 @@
 // quantile_kernel.cuh; there is no CPU fallback anywhere in this file.
 #include <algorithm>
 #include <climits>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -73,6 +74,7 @@ struct qf_forest {
     int64_t device_bytes = 0;
     std::vector<uint32_t> tree_max_leaf;   // members of the largest leaf of every tree
     bool unit_leaves = false;              // every leaf of every tree holds exactly one member
+    int64_t row_weight_bound = 0;          // upper bound on the total weight one row can gather (T for normalised leaf weights)
     int sm_count = 148;
     // options (0 = auto where noted)
     int apply_row_warps = 0;      // warps along rows per CTA (0 auto)
@@ -343,9 +345,10 @@ int launch_bucket_kernel(int threads, unsigned grid, const qf::QuantileParams& q
 int launch_select_kernel(const qf_forest* f, unsigned grid, const qf::QuantileParams& qp,
                          const qf::QuantileList& ql, cudaStream_t st) {
     const size_t smem = qf::select_kernel_smem();
-    int k = 0;                                          // weights of a row sum to <= T < 2^k
-    while ((int64_t(1) << k) < int64_t(f->T) + 1) ++k;
-    if (k > 20) return qf::fail(QF_ERR_LIMIT, "predict_quantiles: too many trees for fixed-point weights");
+    int k = 0;                                          // weights of a row sum to <= bound < 2^k
+    const int64_t bound = std::max<int64_t>(f->T, f->row_weight_bound);   // T when every leaf's weights sum to one
+    while ((int64_t(1) << k) < bound + 1) ++k;
+    if (k > 20) return qf::fail(QF_ERR_LIMIT, "predict_quantiles: total weight per row too large for fixed-point weights");
     const float fx_scale = static_cast<float>(int64_t(1) << (31 - k));
     int nbits = 0;                                      // ranks are < 2^nbits
     while ((int64_t(1) << nbits) < f->N) ++nbits;
@@ -601,6 +604,19 @@ int qf_forest_create(const qf_forest_desc* d, qf_forest** out) {
             for (int t = 0; t < d->n_trees; ++t)
                 f->unit_leaves = f->unit_leaves && both[t] == 1u && both[d->n_trees + t] == 1u;
         }
+        // largest total weight a row can gather: scales the fixed-point weights of QF_MODE_FAST
+        uint32_t* d_w = nullptr;
+        if (e == cudaSuccess) e = cudaMalloc(&d_w, static_cast<size_t>(d->n_trees) * 4);
+        if (e == cudaSuccess) e = cudaMemset(d_w, 0, static_cast<size_t>(d->n_trees) * 4);
+        if (e == cudaSuccess) {
+            qf::tree_max_leaf_weight_kernel<<<d->n_trees, 256>>>(f->d_nodes, f->d_roots, f->n_nodes, f->T, f->d_members, d_w);
+            std::vector<float> w(static_cast<size_t>(d->n_trees));
+            e = cudaMemcpy(w.data(), d_w, w.size() * 4, cudaMemcpyDeviceToHost);
+            double bound = 0.0;
+            for (float v : w) bound += v <= 1.0f + 1e-5f ? 1.0 : static_cast<double>(v) * (1.0 + 1e-6);
+            f->row_weight_bound = static_cast<int64_t>(std::ceil(bound));
+        }
+        cudaFree(d_w);
         if (e != cudaSuccess) rc = qf::fail(QF_ERR_CUDA, std::string("qf_forest_create: ") + cudaGetErrorString(e));
     }
     if (rc != QF_OK) {

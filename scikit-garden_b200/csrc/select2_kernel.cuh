@@ -514,4 +514,24 @@ tree_max_leaf_kernel(const uint2* __restrict__ nodes, const uint32_t* __restrict
     }
 }
 
+// largest sum of member weights over the leaves of every tree (float bits, weights are > 0):
+// 1.0 for forests (ensemble.py:94-99 normalises per leaf), the leaf size for unit weights
+__global__ void __launch_bounds__(256)
+tree_max_leaf_weight_kernel(const uint2* __restrict__ nodes, const uint32_t* __restrict__ roots, int64_t n_nodes, int T,
+                            const uint2* __restrict__ members, uint32_t* __restrict__ out) {
+    const int t = blockIdx.x;
+    const int64_t n0 = roots[t], n1 = (t + 1 < T) ? static_cast<int64_t>(roots[t + 1]) : n_nodes;
+    float mx = 0.0f;
+    for (int64_t i = n0 + threadIdx.x; i < n1; i += blockDim.x) {
+        const uint2 nd = nodes[i];
+        if (nd.y & 0x80000000u) {
+            const uint32_t cnt = nd.y & 0x7fffffffu;
+            double s = 0.0;
+            for (uint32_t k = 0; k < cnt; ++k) s += static_cast<double>(__uint_as_float(members[nd.x + k].y));
+            mx = fmaxf(mx, static_cast<float>(s));
+        }
+    }
+    atomicMax(out + t, __float_as_uint(mx));
+}
+
 }  // namespace qf

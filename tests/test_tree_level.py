@@ -2,7 +2,7 @@
 reference's own outputs (CPU), device path against them (GPU, through the C ABI)."""
 import numpy as np
 import pytest
-from numpy.testing import assert_array_almost_equal, assert_array_equal
+from numpy.testing import assert_allclose, assert_array_almost_equal, assert_array_equal
 
 import _golden_tree
 from oracle import qrf_oracle as O
@@ -65,6 +65,14 @@ def test_device_tree_predict_matches_reference(name):
     assert_array_equal(dev.apply(X).cpu().numpy()[:, 0], g.apply)            # leaf ids bit-exact
     assert_array_equal(dev.predict_quantiles(X, g.q).cpu().numpy().T, g.pred)
     assert_array_equal(dev.predict_mean(X).cpu().numpy(), g.mean)
+    # fast mode on unit weights: the total weight of a row is its leaf size (up to ~150 here),
+    # the library scales its fixed-point weights by that bound
+    from skgarden_b200 import _native
+    dev.set_option("warp_elems", 0)
+    scale = np.abs(g.y_train).max()
+    for lo in range(0, len(g.q), 7):
+        fast = dev.predict_quantiles(X, g.q[lo:lo + 7], mode=_native.QF_MODE_FAST).cpu().numpy().T
+        assert_allclose(fast, g.pred[lo:lo + 7], rtol=1e-4, atol=1e-4 * scale)
     dev.close()
 
 
@@ -91,6 +99,11 @@ def test_reference_tree_tests_through_the_drop_in_api():
                 assert_array_almost_equal(est.predict(cur), est.predict(cur, quantile=q), 1)
         with pytest.raises(ValueError):
             est.predict(Xte, quantile=101)
+        exact = est.predict(Xte, quantile=[10, 50, 90])
+        est.mode = "fast"               # unit weights: a leaf's weights sum to its size, not to one
+        est._on_device().set_option("warp_elems", 0)            # selection kernel for every row
+        assert_array_almost_equal(est.predict(Xte, quantile=[10, 50, 90]), exact, 5)
+        est.mode = "exact"
     # test_tree_toy_data: two clusters, depth 1 -> np.percentile of each cluster (3 decimals)
     x1 = rng.randn(1, 10)
     x2 = 20.0 * rng.randn(1, 10)
