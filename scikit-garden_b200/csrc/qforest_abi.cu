@@ -987,7 +987,7 @@ int qf_build_csr(const qf_csr_build_desc* d, int64_t* n_members_out) {
     QF_CUDA_TRY(alloc(3, static_cast<size_t>(n_nodes) * 4));                // leaf_sum
     QF_CUDA_TRY(alloc(4, static_cast<size_t>(n_nodes) * 4));                // start
     QF_CUDA_TRY(alloc(5, static_cast<size_t>(n_blocks + 1) * 8));           // block sums + total
-    QF_CUDA_TRY(alloc(6, static_cast<size_t>(n_nodes / 2 + 2) * 4 + 16));   // long lists + counters
+    QF_CUDA_TRY(alloc(6, static_cast<size_t>((n_nodes + T) / 2 + 2) * 4 + 16));   // long lists (<= one per leaf: a tree of k nodes has (k + 1) / 2) + counters
     QF_CUDA_TRY(alloc(7, static_cast<size_t>(T + 1) * 8));                  // tree offsets
     QF_CUDA_TRY(alloc(8, static_cast<size_t>(T) * 24));                     // per-tree stats
     uint32_t* d_roots = static_cast<uint32_t*>(sc.p[0]);

@@ -16,7 +16,7 @@ def _forest(kind, **kw):
     if kw.pop("ties", False):
         y = np.round(y, 1)
     cls = sg.RandomForestQuantileRegressor if kind == "rf" else sg.ExtraTreesQuantileRegressor
-    return cls(n_estimators=9, random_state=1, n_jobs=-1, **kw), X, y
+    return cls(**{**dict(n_estimators=9, random_state=1, n_jobs=-1), **kw}), X, y
 
 
 def test_structure_only_packing_matches_full_packing():
@@ -45,7 +45,8 @@ def test_structure_only_packing_matches_full_packing():
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,kw", [
     ("rf", dict()), ("et", dict(min_samples_leaf=5)), ("rf", dict(bootstrap=False, min_samples_leaf=3, ties=True)),
-    ("rf", dict(max_leaf_nodes=60)), ("et", dict(max_depth=4)), ("et", dict(min_samples_leaf=40, bootstrap=False))])
+    ("rf", dict(max_leaf_nodes=60)), ("et", dict(max_depth=4)), ("et", dict(min_samples_leaf=40, bootstrap=False)),
+    ("rf", dict(max_depth=3, min_samples_leaf=30, n_estimators=100))])        # every leaf is a long list (found by tools/fuzz_parity.py)
 def test_device_builder_equals_host_flattener(kind, kw):
     pytest.importorskip("torch")
     est, X, y = _forest(kind, **kw)
