@@ -42,7 +42,9 @@ typedef enum qf_status {
 
 /* Arithmetic modes of qf_forest_predict_quantiles. */
 #define QF_MODE_EXACT 0   /* bit-identical to the reference's float32 op order            */
-#define QF_MODE_FAST  1   /* parallel scans; <= 1e-4 relative to the reference             */
+#define QF_MODE_FAST  1   /* histogram selection on fixed-point weights; <= 1e-4 relative to
+                             the reference.  Forests whose leaf weights are too small for 32-bit
+                             fixed point (leaves of hundreds of members) take the exact kernels */
 
 int qf_abi_version(void);
 const char* qf_last_error(void);

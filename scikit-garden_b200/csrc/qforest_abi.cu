@@ -391,6 +391,20 @@ int launch_select_kernel(const qf_forest* f, unsigned grid, const qf::QuantilePa
     return threads == 128 ? run(qf::quantile_select_kernel<128>) : run(qf::quantile_select_kernel<256>);
 }
 
+// QF_MODE_FAST adds weights as 32-bit fixed point with 2^(31-k) units per unit of weight
+// (2^k > total weight of a row).  A member of a leaf of L samples weighs about 1/L, i.e.
+// 2^(31-k) / L units: below ~2^14 units the rounding of each weight (the same direction for a
+// whole leaf) shifts tail percentiles visibly (tools/fuzz_parity.py: 3e-3 at q = 99.9 with
+// leaves of thousands of members).  Such forests take the exact kernels in both modes.
+bool fast_mode_is_precise(const qf_forest* f) {
+    if (f->row_weight_bound > f->T) return true;        // unit weights (tree-level estimators): nothing to round
+    int k = 0;
+    while ((int64_t(1) << k) < int64_t(f->T) + 1) ++k;
+    uint32_t largest = 1;
+    for (uint32_t m : f->tree_max_leaf) largest = std::max(largest, m);
+    return (static_cast<int64_t>(largest) << k) <= (int64_t(1) << 17);
+}
+
 // `pl` is the caller's carve-up of `ws` (made once for the largest chunk, so that the
 // zeroed dense scratch stays where the kernels expect it for every chunk).
 int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, const double* q_host,
@@ -398,7 +412,7 @@ int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, co
                         cudaStream_t st) {
     // QF_MODE_FAST swaps the shared-memory sorting stages for histogram selection; the warp
     // kernel (small member sets) and the dense fallback are exact in both modes
-    const bool select = mode == QF_MODE_FAST && nq <= qf::kSelectMaxQ;
+    const bool select = mode == QF_MODE_FAST && nq <= qf::kSelectMaxQ && fast_mode_is_precise(f);
     if (ws_bytes < pl.total || (!ws && pl.total > 0))
         return qf::fail(QF_ERR_WORKSPACE, "predict_quantiles: workspace too small");
     unsigned char* base = static_cast<unsigned char*>(ws);

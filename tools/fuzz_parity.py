@@ -68,6 +68,7 @@ def main():
         nq = int(rng.choice([1, 3, 4, 9, 16]))
         qs = sorted(set([float(q) for q in rng.choice([0, 0.5, 1, 5, 25, 33.3, 50, 62.5, 75, 95, 99, 99.9, 100], nq)]))
         sample_rows = rng.choice(n, 12, replace=False)
+        mv = float(rng.choice([0.0, 0.01, 1.0]))
         if args.only >= 0 and case != args.only:
             continue
         est = cls(n_estimators=T, random_state=forest_seed, min_samples_leaf=msl, max_depth=depth,
@@ -121,8 +122,24 @@ def main():
             assert np.array_equal(fl.nodes, est._flat.nodes) and np.array_equal(fl.members, est._flat.members), tag + ": K4"
             est.builder = "host"
             built = "ok"
-        print(tag, "| largest leaf %d | K4 %s | ok" % (biggest, built), flush=True)
         dev.close()
+        # tree-level estimator (quantile/tree.py) and return_std forest (forest.py:133-178) on the same data
+        tcls = sg.DecisionTreeQuantileRegressor if kind == "rf" else sg.ExtraTreeQuantileRegressor
+        tq = tcls(random_state=forest_seed, min_samples_leaf=msl, max_depth=depth).fit(X[:N], y[:N])
+        tl = tq.apply(Xt)
+        assert np.array_equal(tl, O.tree_apply(tq.tree_, Xt)), tag + ": tree apply"
+        for q in qs[:3]:
+            qq = int(q) if float(q).is_integer() else q
+            assert np.array_equal(tq.predict(Xt, quantile=qq),
+                                  O.tree_predict_quantile(tq.y_train_, tq.y_train_leaves_, tl, qq)), tag + ": tree quantile %g" % q
+        scls = sg.RandomForestRegressor if kind == "rf" else sg.ExtraTreesRegressor
+        sf = scls(n_estimators=min(T, 20), random_state=forest_seed, min_samples_leaf=msl, max_depth=depth,
+                  bootstrap=bootstrap, min_variance=mv, n_jobs=-1).fit(X[:N], y[:N])
+        mean, std = sf.predict(Xt, return_std=True)
+        sl = sf.apply(Xt)
+        assert np.array_equal(mean, O.predict_mean(sf.estimators_, Xt, sl)), tag + ": forest mean"
+        assert np.array_equal(std, O.forest_return_std(sf.estimators_, sl, mean, mv)), tag + ": return_std"
+        print(tag, "| largest leaf %d | K4 %s | tree + return_std ok | ok" % (biggest, built), flush=True)
     print("all %d cases ok" % args.cases)
 
 
