@@ -69,14 +69,18 @@ def main():
         qs = sorted(set([float(q) for q in rng.choice([0, 0.5, 1, 5, 25, 33.3, 50, 62.5, 75, 95, 99, 99.9, 100], nq)]))
         sample_rows = rng.choice(n, 12, replace=False)
         mv = float(rng.choice([0.0, 0.01, 1.0]))
+        chunk = int(rng.choice([131072, 100, 33]))       # several kernel chunks per call
+        sort_rows = int(rng.choice([-1, 0, 1]))
         if args.only >= 0 and case != args.only:
             continue
         est = cls(n_estimators=T, random_state=forest_seed, min_samples_leaf=msl, max_depth=depth,
                   bootstrap=bootstrap, n_jobs=-1).fit(X[:N], y[:N])
         Xt = X[N:]
         dev = est._on_device()
-        tag = "case %3d %s N=%5d T=%3d F=%2d msl=%2d depth=%s boot=%d ties=%d Q=%d members/row=%.0f" % (
-            case, kind, N, T, F, msl, depth, bootstrap, ties, len(qs), est._flat.expected_row_members)
+        dev.set_option("rows_per_chunk", chunk)
+        dev.set_option("sort_rows", sort_rows)
+        tag = "case %3d %s N=%5d T=%3d F=%2d msl=%2d depth=%s boot=%d ties=%d Q=%d chunk=%d sort=%d members/row=%.0f" % (
+            case, kind, N, T, F, msl, depth, bootstrap, ties, len(qs), chunk, sort_rows, est._flat.expected_row_members)
         leaves = est.apply(Xt)
         assert np.array_equal(leaves, O.forest_apply(est.estimators_, Xt)), tag + ": apply"
         index = O.SparseIndex(est.y_train_, est.y_train_leaves_, est.y_weights_, est._flat.sorter)
