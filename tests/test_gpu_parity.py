@@ -386,3 +386,25 @@ def test_single_row_and_single_feature():
         assert_array_equal(est.predict(rows, quantile=[25, 75]), O.predict_sparse(index, leaves, [25, 75]))
         assert_array_equal(est.predict(rows), O.predict_mean(est.estimators_, rows, leaves))
 
+
+def test_fast_mode_on_more_than_a_million_training_rows():
+    # N in (2^20, 2^21]: the 4096-bucket instantiation of the single-refinement selection kernel
+    # (512 ranks per bucket), against the multi-level kernel (bit for bit) and the exact kernels
+    import skgarden_b200 as sg
+    rng = np.random.RandomState(12)
+    N, n, F = 1_200_000, 1500, 4
+    X = rng.randn(N + n, F).astype(np.float32)
+    y = 3 * X[:, 0] + np.sin(3 * X[:, 1]) + rng.randn(N + n)
+    est = sg.ExtraTreesQuantileRegressor(n_estimators=6, random_state=0, min_samples_leaf=5, n_jobs=-1).fit(X[:N], y[:N])
+    assert est._flat.n_train > (1 << 20)
+    dev = est._on_device()
+    dev.set_option("warp_elems", 0)
+    qs = [0, 5, 50, 95, 100]
+    exact = est.predict(X[N:], quantile=qs)
+    est.mode = "fast"
+    fast = est.predict(X[N:], quantile=qs)
+    assert_allclose(fast, exact, rtol=1e-4, atol=1e-4 * np.abs(y).max())
+    assert_array_equal(fast[:, [0, -1]], exact[:, [0, -1]])
+    dev.set_option("select_impl", 1)
+    assert_array_equal(est.predict(X[N:], quantile=qs), fast)
+
