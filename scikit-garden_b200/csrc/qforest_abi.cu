@@ -219,7 +219,9 @@ int pick_row_warps(const qf_forest* f) {
 
 template <typename Kernel>
 int set_smem(Kernel kernel, size_t smem) {
-    if (smem > 48 * 1024)
+    // static + dynamic shared memory may not exceed 48 KB without the opt-in: leave room for the
+    // kernels' static arrays (a few hundred bytes)
+    if (smem > 40 * 1024)
         QF_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
     return QF_OK;
@@ -376,6 +378,15 @@ int launch_select_kernel(const qf_forest* f, unsigned grid, const qf::QuantilePa
                 int rc = set_smem(kernel, smem2);
                 if (rc != QF_OK) return rc;
                 kernel<<<std::min(grid, ctas), qf::kSelect2Threads, smem2, st>>>(qp, ql, lay, fx_scale, shift1);
+                const cudaError_t e = cudaPeekAtLastError();
+                if (e != cudaSuccess) {
+                    char msg[256];
+                    std::snprintf(msg, sizeof(msg), "quantile_select2_kernel launch failed: %s (grid %u, %zu bytes of "
+                                  "shared memory, %llu pairs)", cudaGetErrorString(e), std::min(grid, ctas), smem2,
+                                  static_cast<unsigned long long>(pairs));
+                    cudaGetLastError();
+                    return qf::fail(QF_ERR_CUDA, msg);
+                }
                 return QF_OK;
             };
             return log2nb == 11 ? run2(qf::quantile_select2_kernel<11>) : run2(qf::quantile_select2_kernel<12>);

@@ -22,9 +22,10 @@
 //              bp = last non-empty bucket before bq, bn = first non-empty bucket after bq
 //            (bp / bn hold the neighbours of the crossing entry when it is the first / last
 //            entry of bq).  A 16-bit table entry per bucket says which slot arrays it feeds.
-//   pass 2   members are streamed again (L2 hits); a member whose bucket feeds nothing
-//            costs a shift, a 16-bit shared load and a test.  The few others are added to
-//            the slot arrays [bp | bq | bn] of their percentile(s) at single-rank resolution.
+//   pass 2   runs over the bucket ids pass 1 left in shared memory (two 16-bit ids per pair): a
+//            pair whose buckets feed nothing costs three shared loads and a test and no
+//            global traffic.  The few others are loaded again (L2 hits) and added to the slot
+//            arrays [bp | bq | bn] of their percentile(s) at single-rank resolution.
 //   select   one WARP per percentile scans its bq slots (<= 512, four 128-bit loads per
 //            lane), finds the crossing entry e, its neighbours inside bq or, failing that,
 //            the largest rank of bp / the smallest rank of bn; lane 0 interpolates.  The other
@@ -46,7 +47,7 @@ constexpr int kSelect2SlotBits = 9;                     // a bucket spans <= 512
 constexpr int kSelect2Threads = 256;
 constexpr int kSelect2Warps = kSelect2Threads / 32;
 constexpr int kSelect2MaxIPT = 4;                       // leaves per lane: T <= 4 * 256
-constexpr int kSelect2CtasPerSm = 5;
+constexpr int kSelect2CtasPerSm = 4;
 constexpr int kSelect2MaxPairs = 6144;                  // pair-table entries per CTA (24 KB)
 
 // first pair-table entry of every warp (exact upper bounds from the largest leaf of each tree)
@@ -58,8 +59,8 @@ __host__ __device__ constexpr int select2_slots(int shift1) { return (1 << shift
 
 __host__ __device__ inline size_t select2_kernel_smem(int log2nb, int shift1, uint32_t pairs) {
     const size_t nb = static_cast<size_t>(1) << log2nb;
-    return nb * 4 + nb * 2 + static_cast<size_t>(kSelect2QB) * 3 * select2_slots(shift1) * 4 +
-           ((static_cast<size_t>(pairs) + 3) & ~size_t(3)) * 4;
+    return nb * 4 + (nb * 2 + 16) + static_cast<size_t>(kSelect2QB) * 3 * select2_slots(shift1) * 4 +
+           2 * ((static_cast<size_t>(pairs) + 3) & ~size_t(3)) * 4;       // pair table + bucket summaries
 }
 
 // shared-memory accesses by 32-bit shared address (no generic -> shared conversion in the loops)
@@ -106,7 +107,8 @@ quantile_select2_kernel(const QuantileParams p, const __grid_constant__ Quantile
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* h1 = reinterpret_cast<uint32_t*>(smem_raw);          // [NB] bucket weights (zero between rows)
     uint32_t* tbl32 = h1 + NB;                                     // [NB] x 16 bits: slot arrays a bucket feeds (zero between passes)
-    uint32_t* l2 = tbl32 + NB / 2;                                 // [QB][3][SL] slots: bp | bq | bn (zero between passes)
+    uint32_t* l2 = tbl32 + NB / 2 + 4;                             // [QB][3][SL] slots: bp | bq | bn (zero between passes);
+                                                                   //   table entries NB.. stay zero ("no bucket")
     __shared__ uint32_t s_red[NW];
     __shared__ uint32_t s_total;
     // per percentile of the call
@@ -138,13 +140,15 @@ quantile_select2_kernel(const QuantileParams p, const __grid_constant__ Quantile
         s_addr[3] = static_cast<uint32_t>(__cvta_generic_to_shared(pairtab));
     }
     // shared state starts at zero and every row leaves it at zero
-    for (int i = tid; i < NB + NB / 2 + QB * 3 * SL; i += THREADS) h1[i] = 0u;
+    for (int i = tid; i < NB + NB / 2 + 4 + QB * 3 * SL; i += THREADS) h1[i] = 0u;
     __syncthreads();
     const uint32_t h1_s = s_addr[0], tbl_s = s_addr[1], l2_s = s_addr[2];
     const uint4* __restrict__ members4 = reinterpret_cast<const uint4*>(s_members);   // member pairs
     const float scale = s_scale;
     const uint32_t shift = s_shift;
     const uint32_t tab_s = s_addr[3] + lay.warp_off[warp] * 4;    // this warp's segment of the pair table
+    // bucket summaries of the same pairs, written by pass 1 and read by pass 2 (second half)
+    const uint32_t sum_s = tab_s + ((lay.warp_off[NW] + 3u) & ~3u) * 4;
 
     auto mark = [&](int q, int which, uint32_t b) {     // bucket b feeds slot array 3 * (q % QB) + which
         atomicOr(&tbl32[b >> 1], (1u << (3 * (q % QB) + which)) << (16 * (b & 1)));
@@ -208,16 +212,22 @@ quantile_select2_kernel(const QuantileParams p, const __grid_constant__ Quantile
         fetch(work + gridDim.x, pre);
 
         // pass 1: bucket weights.  Two pairs (four members) per lane and iteration, all lanes
-        // busy; w == 0 (utils.py:55-57) changes nothing
+        // busy; w == 0 (utils.py:55-57) changes nothing.  The buckets of every pair are kept
+        // (16 bits each, NB = slot outside its leaf list) so that pass 2 need not load it again.
         for (uint32_t j = lane; j < n_pairs; j += 64) {
+            const bool two = j + 32 < n_pairs;
             const uint32_t e0 = ld_shared_u32(tab_s + j * 4);
-            const uint32_t e1 = (j + 32 < n_pairs) ? ld_shared_u32(tab_s + (j + 32) * 4) : (kPairSkip0 | kPairSkip1);
+            const uint32_t e1 = two ? ld_shared_u32(tab_s + (j + 32) * 4) : (kPairSkip0 | kPairSkip1);
             const uint4 a = __ldg(members4 + (e0 & kPairIndex));
             const uint4 b = __ldg(members4 + (e1 & kPairIndex));
-            red_add_shared_unless(h1_s + (a.x >> shift) * 4, __float2uint_rn(__fmul_rn(__uint_as_float(a.y), scale)), e0 & kPairSkip0);
-            red_add_shared_unless(h1_s + (a.z >> shift) * 4, __float2uint_rn(__fmul_rn(__uint_as_float(a.w), scale)), e0 & kPairSkip1);
-            red_add_shared_unless(h1_s + (b.x >> shift) * 4, __float2uint_rn(__fmul_rn(__uint_as_float(b.y), scale)), e1 & kPairSkip0);
-            red_add_shared_unless(h1_s + (b.z >> shift) * 4, __float2uint_rn(__fmul_rn(__uint_as_float(b.w), scale)), e1 & kPairSkip1);
+            const uint32_t a0 = (e0 & kPairSkip0) ? NB : (a.x >> shift), a1 = (e0 & kPairSkip1) ? NB : (a.z >> shift);
+            const uint32_t b0 = (e1 & kPairSkip0) ? NB : (b.x >> shift), b1 = (e1 & kPairSkip1) ? NB : (b.z >> shift);
+            red_add_shared_unless(h1_s + a0 * 4, __float2uint_rn(__fmul_rn(__uint_as_float(a.y), scale)), e0 & kPairSkip0);
+            red_add_shared_unless(h1_s + a1 * 4, __float2uint_rn(__fmul_rn(__uint_as_float(a.w), scale)), e0 & kPairSkip1);
+            red_add_shared_unless(h1_s + b0 * 4, __float2uint_rn(__fmul_rn(__uint_as_float(b.y), scale)), e1 & kPairSkip0);
+            red_add_shared_unless(h1_s + b1 * 4, __float2uint_rn(__fmul_rn(__uint_as_float(b.w), scale)), e1 & kPairSkip1);
+            st_shared_u32(sum_s + j * 4, a0 | (a1 << 16));
+            if (two) st_shared_u32(sum_s + (j + 32) * 4, b0 | (b1 << 16));
         }
         __syncthreads();                                // B1
 
@@ -326,8 +336,9 @@ quantile_select2_kernel(const QuantileParams p, const __grid_constant__ Quantile
                 __syncthreads();
             }
 
-            // pass 2: members of marked buckets -> slot arrays at single-rank resolution.  The
-            // table is consulted for all four members of an iteration before anything else
+            // pass 2: members of marked buckets -> slot arrays at single-rank resolution.  Only the
+            // bucket summaries are read back; the few pairs that touch a marked bucket are
+            // loaded again (L2 hits)
             auto feed = [&](uint32_t code, uint32_t rank, uint32_t wbits) {
                 const uint32_t w = __float2uint_rn(__fmul_rn(__uint_as_float(wbits), scale));
                 const uint32_t dst = l2_s + (rank & slot_mask) * 4;
@@ -337,22 +348,14 @@ quantile_select2_kernel(const QuantileParams p, const __grid_constant__ Quantile
                     red_add_shared(dst + a * SL * 4, w);
                 }
             };
-            for (uint32_t j = lane; j < n_pairs; j += 64) {
-                const uint32_t e0 = ld_shared_u32(tab_s + j * 4);
-                const uint32_t e1 = (j + 32 < n_pairs) ? ld_shared_u32(tab_s + (j + 32) * 4) : (kPairSkip0 | kPairSkip1);
-                const uint4 a = __ldg(members4 + (e0 & kPairIndex));
-                const uint4 b = __ldg(members4 + (e1 & kPairIndex));
-                uint32_t c0 = ld_shared_u16(tbl_s + (a.x >> shift) * 2), c1 = ld_shared_u16(tbl_s + (a.z >> shift) * 2);
-                uint32_t c2 = ld_shared_u16(tbl_s + (b.x >> shift) * 2), c3 = ld_shared_u16(tbl_s + (b.z >> shift) * 2);
-                c0 = (e0 & kPairSkip0) ? 0u : c0;
-                c1 = (e0 & kPairSkip1) ? 0u : c1;
-                c2 = (e1 & kPairSkip0) ? 0u : c2;
-                c3 = (e1 & kPairSkip1) ? 0u : c3;
-                if (c0 | c1 | c2 | c3) {
+            for (uint32_t j = lane; j < n_pairs; j += 32) {
+                const uint32_t sm = ld_shared_u32(sum_s + j * 4);
+                const uint32_t c0 = ld_shared_u16(tbl_s + (sm & 0xffffu) * 2);
+                const uint32_t c1 = ld_shared_u16(tbl_s + (sm >> 16) * 2);
+                if (c0 | c1) {
+                    const uint4 a = __ldg(members4 + (ld_shared_u32(tab_s + j * 4) & kPairIndex));
                     feed(c0, a.x, a.y);
                     feed(c1, a.z, a.w);
-                    feed(c2, b.x, b.y);
-                    feed(c3, b.z, b.w);
                 }
             }
             __syncthreads();                            // B6
