@@ -102,7 +102,7 @@ quantile_select2_kernel(const QuantileParams p, const __grid_constant__ Quantile
     constexpr int QB = kSelect2QB;
     constexpr int MAXIPT = kSelect2MaxIPT;
     constexpr uint32_t NONE = 0xffffffffu;
-    static_assert(BPT % 4 == 0 && QB <= NW && 3 * QB <= 16, "layout");
+    static_assert(BPT % 4 == 0 && QB <= NW && 3 * QB <= 9 && kSelect2MaxPairs <= (1 << 13), "layout");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* h1 = reinterpret_cast<uint32_t*>(smem_raw);          // [NB] bucket weights (zero between rows)
@@ -348,14 +348,43 @@ quantile_select2_kernel(const QuantileParams p, const __grid_constant__ Quantile
                     red_add_shared(dst + a * SL * 4, w);
                 }
             };
-            for (uint32_t j = lane; j < n_pairs; j += 32) {
-                const uint32_t sm = ld_shared_u32(sum_s + j * 4);
-                const uint32_t c0 = ld_shared_u16(tbl_s + (sm & 0xffffu) * 2);
-                const uint32_t c1 = ld_shared_u16(tbl_s + (sm >> 16) * 2);
-                if (c0 | c1) {
-                    const uint4 a = __ldg(members4 + (ld_shared_u32(tab_s + j * 4) & kPairIndex));
-                    feed(c0, a.x, a.y);
-                    feed(c1, a.z, a.w);
+            if (p.Q <= QB) {
+                // one batch: the hits are first compacted (in place, over summaries already read)
+                // and then fed with all lanes busy -- at C3 some 50 of a row's 1900 pairs hit,
+                // spread over most of the 60 warp-iterations of the scan
+                uint32_t n_hits = 0;                     // warp-uniform
+                for (uint32_t j0 = 0; j0 < n_pairs; j0 += 32) {
+                    const uint32_t j = j0 + lane;
+                    uint32_t c0 = 0u, c1 = 0u;
+                    if (j < n_pairs) {
+                        const uint32_t sm = ld_shared_u32(sum_s + j * 4);
+                        c0 = ld_shared_u16(tbl_s + (sm & 0xffffu) * 2);
+                        c1 = ld_shared_u16(tbl_s + (sm >> 16) * 2);
+                    }
+                    const uint32_t mask = __ballot_sync(0xffffffffu, (c0 | c1) != 0u);
+                    if (mask) {                          // warp-uniform; entry = pair | codes (13 + 9 + 9 bits)
+                        if (c0 | c1)
+                            st_shared_u32(sum_s + (n_hits + __popc(mask & ((1u << lane) - 1u))) * 4, j | (c0 << 13) | (c1 << 22));
+                        n_hits += __popc(mask);
+                    }
+                }
+                __syncwarp();
+                for (uint32_t k = lane; k < n_hits; k += 32) {
+                    const uint32_t h = ld_shared_u32(sum_s + k * 4);
+                    const uint4 a = __ldg(members4 + (ld_shared_u32(tab_s + (h & 0x1fffu) * 4) & kPairIndex));
+                    feed((h >> 13) & 0x1ffu, a.x, a.y);
+                    feed(h >> 22, a.z, a.w);
+                }
+            } else {
+                for (uint32_t j = lane; j < n_pairs; j += 32) {
+                    const uint32_t sm = ld_shared_u32(sum_s + j * 4);
+                    const uint32_t c0 = ld_shared_u16(tbl_s + (sm & 0xffffu) * 2);
+                    const uint32_t c1 = ld_shared_u16(tbl_s + (sm >> 16) * 2);
+                    if (c0 | c1) {
+                        const uint4 a = __ldg(members4 + (ld_shared_u32(tab_s + j * 4) & kPairIndex));
+                        feed(c0, a.x, a.y);
+                        feed(c1, a.z, a.w);
+                    }
                 }
             }
             __syncthreads();                            // B6
