@@ -361,7 +361,8 @@ int launch_select_kernel(const qf_forest* f, unsigned grid, const qf::QuantilePa
         // pair-table segment of every warp: its leaves are 32 * ipt consecutive trees, a leaf of c
         // members spans at most c / 2 + 1 aligned pairs
         qf::Select2Layout lay;
-        const int ipt = (f->T + qf::kSelect2Threads - 1) / qf::kSelect2Threads;
+        int ipt = (f->T + qf::kSelect2Threads - 1) / qf::kSelect2Threads;   // leaves per lane: 1, 2 or 4
+        if (ipt == 3) ipt = 4;
         uint64_t pairs = 0;
         for (int w = 0; w < qf::kSelect2Warps; ++w) {
             lay.warp_off[w] = static_cast<uint32_t>(pairs);
@@ -389,7 +390,11 @@ int launch_select_kernel(const qf_forest* f, unsigned grid, const qf::QuantilePa
                 }
                 return QF_OK;
             };
-            return log2nb == 11 ? run2(qf::quantile_select2_kernel<11>) : run2(qf::quantile_select2_kernel<12>);
+            if (log2nb == 11)
+                return ipt == 1 ? run2(qf::quantile_select2_kernel<11, 1>)
+                     : ipt == 2 ? run2(qf::quantile_select2_kernel<11, 2>) : run2(qf::quantile_select2_kernel<11, 4>);
+            return ipt == 1 ? run2(qf::quantile_select2_kernel<12, 1>)
+                 : ipt == 2 ? run2(qf::quantile_select2_kernel<12, 2>) : run2(qf::quantile_select2_kernel<12, 4>);
         }
     }
     const int threads = f->T <= 128 ? 128 : 256;        // 4 lanes per leaf list

@@ -91,7 +91,9 @@ __device__ __forceinline__ void red_add_shared_unless(uint32_t addr, uint32_t v,
 // bit 30 = the pair's first slot lies outside the leaf list, bit 31 = its second slot does.
 constexpr uint32_t kPairSkip0 = 0x40000000u, kPairSkip1 = 0x80000000u, kPairIndex = 0x3fffffffu;
 
-template <int LOG2NB>
+// IPT: leaves per lane (1, 2 or 4): covers T <= IPT * 256 trees; a template parameter so that the
+// per-lane loops over them carry no dead iterations
+template <int LOG2NB, int IPT>
 __global__ void __launch_bounds__(kSelect2Threads, kSelect2CtasPerSm)
 quantile_select2_kernel(const QuantileParams p, const __grid_constant__ QuantileList ql,
                         const __grid_constant__ Select2Layout lay, const float fx_scale, const int shift1) {
@@ -100,7 +102,7 @@ quantile_select2_kernel(const QuantileParams p, const __grid_constant__ Quantile
     constexpr int BPT = NB / THREADS;                   // buckets scanned per thread
     constexpr int NW = kSelect2Warps;
     constexpr int QB = kSelect2QB;
-    constexpr int MAXIPT = kSelect2MaxIPT;
+    constexpr int MAXIPT = IPT;
     constexpr uint32_t NONE = 0xffffffffu;
     static_assert(BPT % 4 == 0 && QB <= NW && 3 * QB <= 9 && kSelect2MaxPairs <= (1 << 13), "layout");
 
@@ -155,7 +157,7 @@ quantile_select2_kernel(const QuantileParams p, const __grid_constant__ Quantile
     };
 
     // leaves of this lane: ipt consecutive ones; the warp owns 32 * ipt consecutive leaves
-    const int ipt = (p.T + THREADS - 1) / THREADS;
+    constexpr int ipt = IPT;
     const int t_first = (warp * 32 + lane) * ipt;
     const int64_t n_work = p.row_list ? static_cast<int64_t>(*p.row_count) : p.n;
     auto row_of = [&](int64_t work) -> int64_t {
