@@ -24,8 +24,10 @@
 //            entry of bq).  A 16-bit table entry per bucket says which slot arrays it feeds.
 //   pass 2   runs over the bucket ids pass 1 left in shared memory (two 16-bit ids per pair): a
 //            pair whose buckets feed nothing costs three shared loads and a test and no
-//            global traffic.  The few others are loaded again (L2 hits) and added to the slot
-//            arrays [bp | bq | bn] of their percentile(s) at single-rank resolution.
+//            global traffic.  The few others (about 50 of 1900 pairs at C3) are first compacted
+//            -- in place, over summaries already read -- then loaded again (L2 hits) with all
+//            lanes busy and added to the slot arrays [bp | bq | bn] of their percentile(s) at
+//            single-rank resolution.
 //   select   one WARP per percentile scans its bq slots (<= 512, four 128-bit loads per
 //            lane), finds the crossing entry e, its neighbours inside bq or, failing that,
 //            the largest rank of bp / the smallest rank of bn; lane 0 interpolates.  The other
@@ -48,7 +50,7 @@ constexpr int kSelect2Threads = 256;
 constexpr int kSelect2Warps = kSelect2Threads / 32;
 constexpr int kSelect2MaxIPT = 4;                       // leaves per lane: T <= 4 * 256
 constexpr int kSelect2CtasPerSm = 4;
-constexpr int kSelect2MaxPairs = 6144;                  // pair-table entries per CTA (24 KB)
+constexpr int kSelect2MaxPairs = 6144;                  // pair-table entries per CTA (24 KB, and as much again for the bucket summaries)
 
 // first pair-table entry of every warp (exact upper bounds from the largest leaf of each tree)
 struct Select2Layout {
