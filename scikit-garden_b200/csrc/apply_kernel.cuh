@@ -56,22 +56,10 @@ enum { APPLY_EMIT_SEGMENT = 0, APPLY_EMIT_NODE = 1 };
 constexpr int kApplyThreads = 256;
 constexpr int kApplyLevels = 2;                         // visits per chain between two warp votes
 
-// STAGE (EMIT_SEGMENT only): a warp walks a CONTIGUOUS block of trees and parks the 32 x 8
-// results of eight consecutive trees in shared memory before writing them, 64 contiguous bytes
-// per row: 8 store wavefronts per eight trees instead of 8 x 32 scattered 8-byte stores (the
-// stores were ~17 % of the kernel's L1TEX wavefronts).
-constexpr int kStageRing = 16;                          // staged trees per warp (two groups of 8)
-constexpr int kStageRowPitch = 33;                      // padded against bank conflicts on the way out
-
-__host__ __device__ inline size_t apply_stage_bytes() {
-    return static_cast<size_t>(kApplyThreads / 32) * kStageRing * kStageRowPitch * sizeof(uint2);
-}
-
-template <int ILP, int EMIT, bool STAGE = false>
-__global__ void __launch_bounds__(kApplyThreads, STAGE ? 5 : 1)     // STAGE: the ring leaves room for 5 CTAs per SM
+template <int ILP, int EMIT>
+__global__ void __launch_bounds__(kApplyThreads)
 apply_kernel(const ApplyParams p, void* __restrict__ out) {
-    static_assert(!STAGE || EMIT == 0, "staged stores are for the (start, count) output");
-    extern __shared__ float xt[];                       // [F][ROWS] (+ STAGE: the warps' staging rings)
+    extern __shared__ float xt[];                       // [F][ROWS]
     __shared__ uint64_t s_nodes;
     __shared__ uint32_t s_fbits;
     if (threadIdx.x == 0) {
@@ -127,42 +115,19 @@ apply_kernel(const ApplyParams p, void* __restrict__ out) {
     uint2 nd[ILP];
     int tree[ILP];
     uint32_t armed = 0;                                 // bit k: chain k holds a tree (warp-uniform)
-    // trees of this warp: tw, tw + tree_warps, ... or (STAGE) one contiguous block
-    const int per_warp = (p.t_end - p.t_begin + tree_warps - 1) / tree_warps;
-    const int my_lo = STAGE ? p.t_begin + tw * per_warp : p.t_begin + tw;
-    const int my_hi = STAGE ? min(p.t_end, my_lo + per_warp) : p.t_end;
-    const int tree_step = STAGE ? 1 : tree_warps;
-    int next_tree = my_lo;
+    int next_tree = p.t_begin + tw;
 #pragma unroll
     for (int k = 0; k < ILP; ++k) {
         tree[k] = next_tree;
         node[k] = 0u;
         nd[k] = make_uint2(0u, 0x80000000u);
-        if (next_tree < my_hi) {
+        if (next_tree < p.t_end) {
             armed |= 1u << k;
             node[k] = __ldg(p.roots + next_tree);
             nd[k].y = 0u;
         }
-        next_tree += tree_step;
+        next_tree += tree_warps;
     }
-    // STAGE: ring of kStageRing tree slots x 32 rows per warp; `group_lo` = first tree (relative to
-    // my_lo) of the oldest group of 8 not yet written, bit b of `staged` = tree group_lo + b is parked
-    uint2* const ring = reinterpret_cast<uint2*>(xt + static_cast<size_t>(rows_per_cta) * p.F) +
-                        static_cast<size_t>(warp) * kStageRing * kStageRowPitch;
-    int group_lo = 0;
-    uint32_t staged = 0;
-    auto flush = [&](int count) {                       // trees group_lo .. group_lo + count - 1, all 32 rows
-        __syncwarp();
-        const int tl = group_lo + (lane & 7);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + (lane >> 3);
-            if ((lane & 7) < count && pos0 + rw * 32 + rr < p.n)
-                static_cast<uint2*>(out)[(pos0 + rw * 32 + rr) * p.T + my_lo + tl] =
-                    ring[(tl % kStageRing) * kStageRowPitch + rr];
-        }
-        __syncwarp();
-    };
 
     while (armed) {
 #pragma unroll
@@ -188,41 +153,22 @@ apply_kernel(const ApplyParams p, void* __restrict__ out) {
 #pragma unroll
             for (int k = 0; k < ILP; ++k) {
                 if (!(done & (1u << k))) continue;
-                if (STAGE) {
-                    const int tl = tree[k] - my_lo;
-                    ring[(tl % kStageRing) * kStageRowPitch + lane] = make_uint2(nd[k].x, nd[k].y & 0x7fffffffu);
-                    staged |= 1u << (tl - group_lo);
-                } else if (row_ok) {
+                if (row_ok) {
                     if (EMIT == APPLY_EMIT_SEGMENT)
                         static_cast<uint2*>(out)[out_row * p.T + tree[k]] =
                             make_uint2(nd[k].x, nd[k].y & 0x7fffffffu);
                     else
                         static_cast<int32_t*>(out)[out_row * p.T + tree[k]] = static_cast<int32_t>(node[k]);
                 }
-                if (next_tree < my_hi) {
+                if (next_tree < p.t_end) {
                     tree[k] = next_tree;
                     node[k] = __ldg(p.roots + next_tree);
                     nd[k].y = 0u;
                 } else {
                     armed &= ~(1u << k);
                 }
-                next_tree += tree_step;
+                next_tree += tree_warps;
             }
-            if (STAGE) {
-                while ((staged & 0xffu) == 0xffu) {     // a whole group of 8 is parked: write it
-                    flush(8);
-                    staged >>= 8;
-                    group_lo += 8;
-                }
-            }
-        }
-    }
-    if (STAGE) {                                        // what is left: fewer than 8 trees (twice at most)
-        while (staged) {
-            const int count = min(8, (my_hi - my_lo) - group_lo);
-            flush(count);
-            staged >>= 8;
-            group_lo += 8;
         }
     }
 }

@@ -79,7 +79,6 @@ struct qf_forest {
     // options (0 = auto where noted)
     int apply_row_warps = 0;      // warps along rows per CTA (0 auto)
     int apply_ilp = 4;
-    int apply_stage = 1;          // leaf lookup for K2: park 8 trees x 32 rows in shared memory and write 64-byte runs
     int sort_rows = -1;           // walk rows in locality order: -1 auto, 0 never, 1 always
     int key_shift = 0, key_bins = 1;   // locality buckets = leaf position in tree 0 >> key_shift
     uint32_t root0 = 0;
@@ -250,14 +249,9 @@ int launch_apply(qf_forest* f, const float* X, int64_t n, int64_t ldx, void* out
     while (ap.row_warps > 1 && static_cast<size_t>(f->F) * 32 * ap.row_warps * sizeof(float) > 200 * 1024)
         ap.row_warps >>= 1;
     const int rows_per_cta = 32 * ap.row_warps;
-    size_t smem = static_cast<size_t>(f->F) * rows_per_cta * sizeof(float);
+    const size_t smem = static_cast<size_t>(f->F) * rows_per_cta * sizeof(float);
     if (smem > 200 * 1024)
         return qf::fail(QF_ERR_LIMIT, "apply: n_features too large for the shared-memory row tile");
-    // staged stores: (start, count) output, at least 8 trees per warp
-    const bool stage = EMIT == qf::APPLY_EMIT_SEGMENT && f->apply_stage != 0 &&
-                       (t_end - t_begin) >= 8 * (qf::kApplyThreads / 32) / ap.row_warps &&
-                       smem + qf::apply_stage_bytes() <= 200 * 1024;
-    if (stage) smem += qf::apply_stage_bytes();
     const int64_t grid = (n + rows_per_cta - 1) / rows_per_cta;
     auto run = [&](auto kernel) -> int {
         int rc = set_smem(kernel, smem);
@@ -270,16 +264,6 @@ int launch_apply(qf_forest* f, const float* X, int64_t n, int64_t ldx, void* out
         ++f->launches;
         return QF_OK;
     };
-    if constexpr (EMIT == qf::APPLY_EMIT_SEGMENT) {
-        if (stage) {
-            switch (f->apply_ilp) {
-                case 1: return run(qf::apply_kernel<1, EMIT, true>);
-                case 2: return run(qf::apply_kernel<2, EMIT, true>);
-                case 8: return run(qf::apply_kernel<8, EMIT, true>);
-                default: return run(qf::apply_kernel<4, EMIT, true>);
-            }
-        }
-    }
     switch (f->apply_ilp) {
         case 1: return run(qf::apply_kernel<1, EMIT>);
         case 2: return run(qf::apply_kernel<2, EMIT>);
@@ -764,9 +748,6 @@ int qf_forest_set_option(qf_forest* f, const char* key, int64_t value) {
     } else if (k == "cta2_capacity") {
         if (value < 0 || value > 8192) return qf::fail(QF_ERR_INVALID, "cta2_capacity must be in [0, 8192]");
         f->cta2_capacity = static_cast<int>(value);
-    } else if (k == "apply_stage") {
-        if (value != 0 && value != 1) return qf::fail(QF_ERR_INVALID, "apply_stage must be 0 or 1");
-        f->apply_stage = static_cast<int>(value);
     } else if (k == "warp_unit") {
         if (value != 0 && value != 1) return qf::fail(QF_ERR_INVALID, "warp_unit must be 0 or 1");
         f->warp_unit = static_cast<int>(value);
