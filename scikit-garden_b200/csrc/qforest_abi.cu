@@ -82,7 +82,7 @@ struct qf_forest {
     int sort_rows = -1;           // walk rows in locality order: -1 auto, 0 never, 1 always
     int key_shift = 0, key_bins = 1;   // locality buckets = leaf position in tree 0 >> key_shift
     uint32_t root0 = 0;
-    int64_t rows_per_chunk = 131072;
+    int64_t rows_per_chunk = 262144;    // rows per kernel chunk (denser chunks = closer neighbours in the locality order: C3-quarter K1 2.66 -> 2.52 ms against 131072)
     int cta_capacity = 0;         // cap on the members per row of the first bucket stage (0 = its capacity)
     int select_bits = qf::kSelectL2Bits;   // log2 refinement slots of the selection kernel (tests lower it)
     int select_impl = 0;                   // 0: single-refinement kernel when the training set allows; 1: always the multi-level one

@@ -42,7 +42,7 @@ def main():
     X = torch.from_numpy(make_test(n, F, seed=0)).cuda()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     dev = sg.DeviceForest(flat, device=0)
-    defaults = dict(select_impl=0, sort_rows=-1, apply_row_warps=0, apply_ilp=4, warp_elems=-1, rows_per_chunk=131072,
+    defaults = dict(select_impl=0, sort_rows=-1, apply_row_warps=0, apply_ilp=4, warp_elems=-1, rows_per_chunk=262144,
                     cta_capacity=4096)
     if args.grid == "default":
         grid = [dict(sort_rows=s, apply_ilp=i, apply_row_warps=rw)
