@@ -178,11 +178,13 @@ def row_member_counts(flat, leaf_ids):
     if flat.node_ids is None:
         packed = leaf_ids + flat.tree_offsets[:-1][None, :]
     else:
-        inv = np.empty(flat.n_nodes, dtype=np.int64)
+        packed = np.empty_like(leaf_ids)
         for t in range(flat.n_trees):
             n0, n1 = flat.tree_offsets[t], flat.tree_offsets[t + 1]
-            inv[n0 + flat.node_ids[n0:n1]] = np.arange(n0, n1)
-        packed = inv[leaf_ids + flat.tree_offsets[:-1][None, :]]
+            ids = flat.node_ids[n0:n1]
+            inv = np.empty(n1 - n0, dtype=np.int64)        # sklearn id -> packed slot
+            inv[ids[ids >= 0]] = n0 + np.flatnonzero(ids >= 0)
+            packed[:, t] = inv[leaf_ids[:, t]]
     return cnt[packed].sum(axis=1)
 
 

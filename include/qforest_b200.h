@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define QF_ABI_VERSION 1
+#define QF_ABI_VERSION 2
 
 typedef enum qf_status {
     QF_OK = 0,
@@ -55,17 +55,23 @@ const char* qf_last_error(void);
  * Replaces the per-tree fit bookkeeping of quantile/ensemble.py:83-101 (the dense
  * (T,N) y_train_leaves_ / y_weights_ arrays) and the 64-byte AoS node records of
  * sklearn:tree/_tree.pxd:15-25 by
- *   nodes_out[n_nodes]  8-byte packed nodes in depth-first preorder (left child = +1):
+ *   nodes_out[n_nodes + 1]  8-byte packed nodes in level order with sibling pairs: slot 0 =
+ *       root, slot 1 = padding (all zero, never reached), then level after level, left to
+ *       right, the two children of every internal node side by side (right child = left
+ *       child + 1; every pair starts on a 16-byte boundary because a tree occupies an even
+ *       number of slots).  Rows that are close in feature space sit on neighbouring nodes
+ *       of a level, which is what keeps the leaf-lookup warps on few 32-byte sectors.
  *       internal: lo32 = float bits of floor_f32(threshold)   (largest f32 <= the f64
  *                        threshold, so `x <= thr` on float32 x decides exactly like
  *                        sklearn:tree/_tree.pyx:989, which compares in float64)
- *                 hi32 = (right_child_offset << feature_bits) | feature,  bit31 = 0
+ *                 hi32 = (left_child_offset << feature_bits) | feature,  bit31 = 0
  *       leaf:     lo32 = index of the leaf's first member in the global member array
  *                 hi32 = 0x80000000 | number_of_members
- *   node_id_out[n_nodes] scikit-learn node id of every packed position (so that
- *       `apply` can return scikit-learn ids, forest.py:583-604)
- *   members_out[n_inbag] one 8-byte entry per in-bag training sample, grouped by leaf in
- *       packed-node order and sorted by rank inside a leaf:
+ *   node_id_out[n_nodes + 1] scikit-learn node id of every packed slot, -1 for the padding
+ *       (so that `apply` can return scikit-learn ids, forest.py:583-604)
+ *   members_out[n_inbag] one 8-byte entry per in-bag training sample, grouped by leaf, the
+ *       leaves from left to right (depth-first order: lists of neighbouring leaves are
+ *       neighbours in memory), sorted by rank inside a leaf:
  *                 lo32 = rank of the sample in np.argsort(y_train_)  (ensemble.py:133)
  *                 hi32 = float bits of y_weights_[t, sample] = f32(count / leaf_count_sum)
  *                        (ensemble.py:94-99)
@@ -77,8 +83,8 @@ const char* qf_last_error(void);
  *   member_base: global index of this tree's first member entry
  * Outputs (besides the arrays): n_inbag_out, max_leaf_members_out, max_depth_out,
  *   sum_sq_leaf_members_out (sum over leaves of members^2: expected gather size).
- * Fails with QF_ERR_LIMIT when a right-child offset needs more than 31-feature_bits
- * bits or a member index exceeds 2^32-1.
+ * Fails with QF_ERR_LIMIT when a child offset needs more than 31-feature_bits bits or a
+ * member index exceeds 2^32-1.
  */
 int qf_pack_tree(int64_t n_nodes,
                  const int64_t* children_left, const int64_t* children_right,
@@ -96,7 +102,9 @@ int64_t qf_count_inbag(int64_t n_train, const int64_t* counts);
 
 /* qf_pack_tree with train_leaves == NULL packs the STRUCTURE only (nodes_out, node_id_out,
  * max_depth_out; n_train / counts / sorter / members_out are ignored): leaves are left empty
- * (lo32 = 0, hi32 = 0x80000000) for qf_build_csr to fill on the device. */
+ * (hi32 = 0x80000000) with lo32 = member_base + left-to-right ordinal of the leaf, for
+ * qf_build_csr to fill on the device.  Pass member_base = (first packed slot of the tree) / 2:
+ * a tree of k slots has k / 2 leaves, so the ordinals of a forest are dense and unique. */
 
 /* ------------------------------------------------------------------------------------
  * Device side, fit time: the leaf -> member lists built on the GPU (K4).
@@ -104,7 +112,8 @@ int64_t qf_count_inbag(int64_t n_train, const int64_t* counts);
  * Replaces the same reference code as the member part of qf_pack_tree -- the O(T*L*N) loop
  * of quantile/ensemble.py:87-101 and tree_.apply(X_train) per tree (tree.py:98-101) -- and
  * produces bit for bit the same nodes / members arrays: leaf lookup of the training rows
- * with the predict path's own kernel, per-leaf counts, a scan over the packed nodes, a
+ * with the predict path's own kernel, per-leaf counts, a scan over the leaves in left-to-right
+ * order (the ordinals a structure-only qf_pack_tree left in lo32), a
  * scatter of (rank, f32(count / leaf count sum)) entries and a sort of every list by rank.
  * All "_dev" arrays live on `device`.  counts_dev is laid out [n_train][n_trees] (uint16
  * bootstrap multiplicities, ensemble.py:88-94) or NULL (every sample once).  Lists longer
@@ -142,12 +151,12 @@ typedef struct qf_forest_desc {
     int32_t n_features;         /* F                                                    */
     int32_t feature_bits;       /* as given to qf_pack_tree                             */
     int64_t n_train;            /* N                                                    */
-    int64_t n_nodes;            /* sum of nodes over trees                              */
+    int64_t n_nodes;            /* sum of packed slots over trees (nodes + 1 each)      */
     int64_t n_members;          /* sum of in-bag members over trees                     */
     const uint64_t* nodes;      /* host [n_nodes]   packed nodes, trees back to back    */
     const int64_t* tree_offsets;/* host [T+1]       first packed node of each tree      */
-    const int32_t* node_ids;    /* host [n_nodes]   sklearn id per packed node, or NULL
-                                                     when packed position == sklearn id */
+    const int32_t* node_ids;    /* host [n_nodes]   sklearn id per packed slot (qf_pack_tree);
+                                                     NULL: apply returns packed slots    */
     const uint64_t* members;    /* host [n_members] (rank, weight) entries              */
     const float* y_sorted;      /* host [N]  y_train_.astype(f32)[sorter] (utils.py:46,52) */
     const double* leaf_values;  /* host [n_nodes]   tree_.value per packed node, or NULL

@@ -18,7 +18,7 @@ QF_ERR_LIMIT = -3
 QF_ERR_WORKSPACE = -4
 QF_MODE_EXACT = 0
 QF_MODE_FAST = 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class QFError(RuntimeError):

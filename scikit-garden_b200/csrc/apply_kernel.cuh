@@ -5,18 +5,25 @@
 // iff x[feature] <= threshold.
 //
 // What bounds this kernel is not HBM but the L1TEX tag stage: a warp-level node load costs
-// one wavefront per DISTINCT 128-byte line its 32 lanes touch, ~1 wavefront per cycle per
-// SM.  With test rows in arrival order every lane is in a different part of the tree after
-// a few levels (32 wavefronts per load; ncu: l1tex wavefronts 66 % of peak, the limiter).
-// Two measures bring that down ~3x (tools/sim_wavefronts.py counts them on real forests):
+// one pass per DISTINCT 32-byte sector its 32 lanes touch, ~1 per cycle per SM (ncu: l1tex
+// throughput 85 % of peak with sectors + shared wavefronts = 0.9 per SM cycle).  With test
+// rows in arrival order every lane is in a different part of the tree after a few levels
+// (32 sectors per load).  Three measures bring that down (tools/sim_wavefronts.py counts
+// them on real forests):
 //
 //   1. locality order: rows are first bucketed by the leaf they reach in ONE tree (its
-//      depth-first leaf position is a space-filling order adapted to the data), and the
+//      left-to-right leaf order is a space-filling order adapted to the data), and the
 //      kernel walks the rows in that order.  Neighbouring lanes then follow the same path
-//      through the upper ~10 levels of EVERY tree and share lines far below that.
+//      through the upper ~10 levels of EVERY tree and stay close far below that.
 //   2. lock step: all lanes of a warp walk the same tree at the same time (a chain is
 //      re-armed with the warp's next tree only when every lane has reached its leaf), so
 //      that the coherence of (1) is not lost to lanes drifting into different trees.
+//   3. level-order nodes with sibling pairs: lanes that are close in feature space sit on
+//      neighbouring nodes of a level, and a level is contiguous in memory, so k distinct
+//      nodes cost about k / 4 sectors; the two children of a node share a sector, so a
+//      warp that splits at a node does not pay for it on the next level (simulated on the
+//      C2 forest: 5.8 -> 4.3 sectors and 5.4 -> 2.8 lines per warp load against depth-first
+//      preorder).
 //
 // Mapping: a CTA owns ROWS = 32 * row_warps consecutive rows of the locality order, staged
 // ONCE into shared memory as a transposed tile xt[f][row] (lane == row, so every
@@ -27,7 +34,7 @@
 // node loads overlap.
 //
 // Node format: include/qforest_b200.h (8 bytes: floor-f32 threshold | offset<<fb | feature;
-// leaf: member start | 0x80000000|count).  Left child = node + 1 (preorder).
+// leaf: member start | 0x80000000|count).  Children = node + offset (left), + offset + 1 (right).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -140,8 +147,12 @@ apply_kernel(const ApplyParams p, void* __restrict__ out) {
                 if (static_cast<int32_t>(nd[k].y) >= 0) {
                     float x;
                     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(xcol_s + (nd[k].y & fmask) * fstride));
-                    // sklearn:tree/_tree.pyx:989  `X[i, feature] <= threshold` -> left (= node + 1)
-                    node[k] += (x <= __uint_as_float(nd[k].x)) ? 1u : (nd[k].y >> fbits);
+                    // sklearn:tree/_tree.pyx:989  `X[i, feature] <= threshold` -> left, else the
+                    // sibling right behind it.  set.gtu gives 0xffffffff for "not <=": one
+                    // three-input add takes the step (node + offset - (-1))
+                    uint32_t right;
+                    asm("set.gtu.u32.f32 %0, %1, %2;" : "=r"(right) : "f"(x), "f"(__uint_as_float(nd[k].x)));
+                    node[k] = node[k] + (nd[k].y >> fbits) - right;
                 }
             }
         }
@@ -175,7 +186,7 @@ apply_kernel(const ApplyParams p, void* __restrict__ out) {
 
 // ---------------------------------------------------------------------------------------
 // Locality order: counting sort of the rows by the leaf they reach in ONE tree.
-//   locality_key_kernel   : bucket[row] = (leaf position in the tree) >> key_shift, histogram
+//   locality_key_kernel   : bucket[row] = (first member of the leaf) >> key_shift, histogram
 //   exclusive_scan_kernel : single CTA, in-place exclusive prefix sum of the kKeyBins counters
 //   order_scatter_kernel  : order[atomicAdd(&cursor[bucket[row]], 1)] = row
 // The order inside a bucket is whatever the atomics give; results do not depend on it
@@ -188,19 +199,22 @@ constexpr int kScanThreads = kKeyBins / 8;
 // after the first touch), so there is no tile staging and no barrier for a single tree
 __global__ void __launch_bounds__(128)
 locality_key_kernel(const uint2* __restrict__ nodes, uint32_t root, const float* __restrict__ X,
-                    int64_t ldx, int64_t n, int fbits, int key_shift, int* __restrict__ bucket,
+                    int64_t ldx, int64_t n, int fbits, int key_shift, int key_bins, int* __restrict__ bucket,
                     int* __restrict__ hist) {
     const int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (row >= n) return;
     const float* __restrict__ x = X + row * ldx;
     const uint32_t fmask = (1u << fbits) - 1u;
     uint32_t node = root;
+    uint2 nd;
     for (;;) {
-        const uint2 nd = __ldg(nodes + node);
+        nd = __ldg(nodes + node);
         if (static_cast<int32_t>(nd.y) < 0) break;
-        node += (__ldg(x + (nd.y & fmask)) <= __uint_as_float(nd.x)) ? 1u : (nd.y >> fbits);   // _tree.pyx:989
+        node += (nd.y >> fbits) + ((__ldg(x + (nd.y & fmask)) <= __uint_as_float(nd.x)) ? 0u : 1u);   // _tree.pyx:989
     }
-    const int b = static_cast<int>((node - root) >> key_shift);
+    // lo32 of a leaf of the FIRST tree: index of its first member, which grows from left to
+    // right over the leaves (before qf_build_csr: the leaf's left-to-right ordinal)
+    const int b = static_cast<int>(min(nd.x >> key_shift, static_cast<uint32_t>(key_bins - 1)));
     bucket[row] = b;
     atomicAdd(hist + b, 1);
 }

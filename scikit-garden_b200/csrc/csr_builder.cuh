@@ -6,8 +6,10 @@
 // flattener qf_pack_tree produces:
 //   leaf lookup of the training rows     K1 (apply_kernel, EMIT_NODE) on X_train
 //   count_kernel                         per leaf: in-bag members and sum of their multiplicities
-//   exclusive scan over all packed nodes leaf -> first member index (lists grouped by leaf in
-//                                        packed-node order, trees back to back)
+//   leaf_order_kernel                    counts permuted into left-to-right leaf order (the
+//                                        ordinal a structure-only qf_pack_tree left in lo32)
+//   exclusive scan over the ordinals     leaf -> first member index (lists grouped by leaf,
+//                                        leaves from left to right, trees back to back)
 //   leaf_record_kernel                   leaves get (start, 0x80000000 | count)
 //   scatter_kernel                       member = (rank in argsort(y_train_), f32(count / leaf sum)),
 //                                        ensemble.py:94-99: int / int -> float64 -> float32
@@ -89,18 +91,32 @@ csr_scan_sums_kernel(uint64_t* __restrict__ block_sum, int64_t n_blocks, uint64_
     if (threadIdx.x == 0) *total_out = carry_s;
 }
 
-// start[i] = exclusive prefix of leaf_cnt; leaves get their record.  One thread walks 4
-// consecutive nodes; a block covers kCsrScanBlock nodes.
+// thread per packed node: a leaf drops its member count at its left-to-right ordinal (lo32
+// as written by a structure-only qf_pack_tree) and records where it lives
+__global__ void csr_leaf_order_kernel(const uint2* __restrict__ nodes, int64_t n, const uint32_t* __restrict__ leaf_cnt,
+                                      int64_t n_leaves, uint32_t* __restrict__ cnt_ord, int32_t* __restrict__ node_of,
+                                      int* __restrict__ bad_ordinal) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint2 nd = nodes[i];
+    if (!(nd.y & 0x80000000u)) return;
+    if (nd.x >= n_leaves || (nd.y & 0x7fffffffu)) { atomicExch(bad_ordinal, 1); return; }
+    if (atomicCAS(node_of + nd.x, -1, static_cast<int32_t>(i)) != -1) { atomicExch(bad_ordinal, 1); return; }   // two leaves, one ordinal
+    cnt_ord[nd.x] = leaf_cnt[i];
+}
+
+// over the leaf ordinals: start = exclusive prefix of cnt_ord; the leaf at every ordinal gets
+// its record.  One thread walks 4 consecutive ordinals; a block covers kCsrScanBlock of them.
 __global__ void __launch_bounds__(256)
-csr_leaf_record_kernel(uint2* __restrict__ nodes, const uint32_t* __restrict__ leaf_cnt, int64_t n,
-                       const uint64_t* __restrict__ block_sum, uint32_t* __restrict__ start) {
+csr_leaf_record_kernel(uint2* __restrict__ nodes, const uint32_t* __restrict__ cnt_ord, const int32_t* __restrict__ node_of,
+                       int64_t n_leaves, const uint64_t* __restrict__ block_sum, uint32_t* __restrict__ start) {
     __shared__ uint32_t warp_tot[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t i0 = static_cast<int64_t>(blockIdx.x) * kCsrScanBlock + threadIdx.x * 4;
     uint32_t c[4], mine = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        c[k] = (i0 + k < n) ? leaf_cnt[i0 + k] : 0u;
+        c[k] = (i0 + k < n_leaves) ? cnt_ord[i0 + k] : 0u;
         mine += c[k];
     }
     uint32_t incl = mine;
@@ -115,10 +131,12 @@ csr_leaf_record_kernel(uint2* __restrict__ nodes, const uint32_t* __restrict__ l
     for (int w = 0; w < warp; ++w) run += warp_tot[w];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int64_t i = i0 + k;
-        if (i < n) {
-            start[i] = static_cast<uint32_t>(run);
-            if (nodes[i].y & 0x80000000u) nodes[i] = make_uint2(static_cast<uint32_t>(run), 0x80000000u | c[k]);
+        if (i0 + k < n_leaves) {
+            const int32_t node = node_of[i0 + k];
+            if (node >= 0) {                                  // every ordinal of a well-formed forest has its leaf
+                start[node] = static_cast<uint32_t>(run);
+                nodes[node] = make_uint2(static_cast<uint32_t>(run), 0x80000000u | c[k]);
+            }
             run += c[k];
         }
     }

@@ -1,5 +1,5 @@
 // Host-side forest flattener (no CUDA calls): one fitted scikit-learn tree ->
-// 8-byte packed nodes in depth-first preorder + the leaf -> in-bag member lists that
+// 8-byte packed nodes in level order (sibling pairs) + the leaf -> in-bag member lists that
 // replace the dense (T,N) y_train_leaves_ / y_weights_ arrays of the reference
 // (skgarden/quantile/ensemble.py:83-101).  Layout documented in include/qforest_b200.h.
 #include <cmath>
@@ -55,37 +55,61 @@ extern "C" int qf_pack_tree(int64_t n_nodes, const int64_t* left, const int64_t*
         return qf::fail(QF_ERR_LIMIT, "qf_pack_tree: more than 2^31 nodes or training rows");
     const uint32_t max_off = (1u << (31 - feature_bits)) - 1u;
 
-    // pass 1: depth-first preorder numbering (left subtree first).  sklearn's
-    // depth-first builder already numbers this way; the best-first builder
-    // (max_leaf_nodes) does not, so always renumber and keep the map.
+    // pass 1: level-order numbering with sibling pairs.  Slot 0 = root, slot 1 = padding (so
+    // that every pair starts on a 16-byte boundary), then level after level, left to right, the
+    // two children of every internal node side by side.  Rows that are neighbours in feature
+    // space sit on neighbouring nodes of a level, so the 32 lanes of a leaf-lookup warp touch
+    // few 32-byte sectors per visit.
+    const int64_t n_slots = n_nodes + 1;
     std::vector<int32_t> pos_of(n_nodes, -1);
-    std::vector<int64_t> stack;
-    std::vector<int32_t> depth_stack;
-    stack.reserve(128);
-    depth_stack.reserve(128);
-    stack.push_back(0);
-    depth_stack.push_back(0);
-    int32_t next = 0, max_depth = 0;
-    while (!stack.empty()) {
-        const int64_t nd = stack.back();
-        const int32_t d = depth_stack.back();
-        stack.pop_back();
-        depth_stack.pop_back();
-        if (nd < 0 || nd >= n_nodes || pos_of[nd] != -1)
-            return qf::fail(QF_ERR_INVALID, "qf_pack_tree: children arrays do not form a tree");
-        pos_of[nd] = next;
-        node_id_out[next] = static_cast<int32_t>(nd);
-        ++next;
-        if (d > max_depth) max_depth = d;
-        if (left[nd] != -1) {              // sklearn: leaf <=> children_left == -1 (_tree.pyx:978)
-            stack.push_back(right[nd]);
-            depth_stack.push_back(d + 1);
-            stack.push_back(left[nd]);     // popped first -> left child gets position + 1
-            depth_stack.push_back(d + 1);
+    std::vector<int64_t> queue;                            // sklearn ids in level order
+    queue.reserve(n_nodes);
+    queue.push_back(0);
+    pos_of[0] = 0;
+    node_id_out[0] = 0;
+    node_id_out[1] = -1;
+    nodes_out[1] = 0;                                      // never reached by a walk, not a leaf
+    int32_t next = 2, max_depth = 0;
+    size_t level_end = 1;                                  // queue index where the current level ends
+    for (size_t qi = 0; qi < queue.size(); ++qi) {
+        if (qi == level_end) {
+            ++max_depth;
+            level_end = queue.size();
+        }
+        const int64_t nd = queue[qi];
+        if (left[nd] == -1) continue;                      // sklearn: leaf <=> children_left == -1 (_tree.pyx:978)
+        const int64_t kids[2] = {left[nd], right[nd]};
+        for (const int64_t c : kids) {
+            if (c <= 0 || c >= n_nodes || pos_of[c] != -1 || next >= n_slots)
+                return qf::fail(QF_ERR_INVALID, "qf_pack_tree: children arrays do not form a tree");
+            pos_of[c] = next;
+            node_id_out[next] = static_cast<int32_t>(c);
+            ++next;
+            queue.push_back(c);
         }
     }
-    if (next != n_nodes)
+    if (next != n_slots)
         return qf::fail(QF_ERR_INVALID, "qf_pack_tree: unreachable nodes in tree");
+
+    // the leaves from left to right (depth-first, left subtree first): the order of the member
+    // lists, and of the leaf ordinals a structure-only packing leaves in lo32
+    std::vector<int64_t> leaf_seq;
+    leaf_seq.reserve(n_nodes / 2 + 1);
+    {
+        std::vector<int64_t> stack;
+        stack.reserve(128);
+        stack.push_back(0);
+        while (!stack.empty()) {
+            const int64_t nd = stack.back();
+            stack.pop_back();
+            if (left[nd] == -1) {
+                leaf_seq.push_back(nd);
+            } else {
+                stack.push_back(right[nd]);
+                stack.push_back(left[nd]);                 // popped first
+            }
+        }
+    }
 
     // pass 2: per-leaf in-bag statistics (ensemble.py:94-99: weights = count / sum of counts)
     std::vector<int64_t> leaf_count_sum(n_nodes, 0);
@@ -101,35 +125,37 @@ extern "C" int qf_pack_tree(int64_t n_nodes, const int64_t* left, const int64_t*
         leaf_members[lf] += 1;
         ++n_inbag;
     }
-    if (member_base + static_cast<uint64_t>(n_inbag) > 0xFFFFFFFFull)
+    if (member_base + static_cast<uint64_t>(structure_only ? n_nodes : n_inbag) > 0xFFFFFFFFull)
         return qf::fail(QF_ERR_LIMIT, "qf_pack_tree: more than 2^32-1 member entries in the forest");
 
-    // pass 3: packed nodes; leaves get their member range in packed (preorder) order
+    // pass 3: packed nodes.  Leaves get their member range in left-to-right leaf order (lists of
+    // leaves that are close in feature space are close in memory); structure only: lo32 = member_base
+    // + left-to-right ordinal of the leaf, which is what qf_build_csr keys its scan on.
     std::vector<uint32_t> cursor(n_nodes, 0);              // indexed by sklearn id
     uint64_t running = member_base;
     uint32_t max_members = 0;
     double sum_sq = 0.0;
-    for (int64_t p = 0; p < n_nodes; ++p) {
-        const int64_t nd = node_id_out[p];
-        if (left[nd] == -1) {
-            const uint32_t m = leaf_members[nd];
-            cursor[nd] = static_cast<uint32_t>(running);
-            nodes_out[p] = (static_cast<uint64_t>(0x80000000u | m) << 32) | static_cast<uint32_t>(running);
-            running += m;
-            if (m > max_members) max_members = m;
-            sum_sq += static_cast<double>(m) * static_cast<double>(m);
-        } else {
-            if (pos_of[left[nd]] != p + 1)
-                return qf::fail(QF_ERR_INVALID, "qf_pack_tree: internal numbering error");
-            const int64_t off = static_cast<int64_t>(pos_of[right[nd]]) - p;
-            const int64_t f = feature[nd];
-            if (off < 2 || static_cast<uint64_t>(off) > max_off)
-                return qf::fail(QF_ERR_LIMIT, "qf_pack_tree: right-child offset does not fit 31-feature_bits bits");
-            if (f < 0 || f >= (int64_t(1) << feature_bits))
-                return qf::fail(QF_ERR_INVALID, "qf_pack_tree: feature index does not fit feature_bits");
-            const uint32_t hi = (static_cast<uint32_t>(off) << feature_bits) | static_cast<uint32_t>(f);
-            nodes_out[p] = (static_cast<uint64_t>(hi) << 32) | f32_bits(floor_to_f32(threshold[nd]));
-        }
+    for (const int64_t nd : leaf_seq) {
+        const uint32_t m = leaf_members[nd];
+        cursor[nd] = static_cast<uint32_t>(running);
+        nodes_out[pos_of[nd]] = (static_cast<uint64_t>(0x80000000u | m) << 32) | static_cast<uint32_t>(running);
+        running += structure_only ? 1 : m;
+        if (m > max_members) max_members = m;
+        sum_sq += static_cast<double>(m) * static_cast<double>(m);
+    }
+    for (int64_t nd = 0; nd < n_nodes; ++nd) {
+        if (left[nd] == -1) continue;
+        const int64_t p = pos_of[nd];
+        if (pos_of[right[nd]] != pos_of[left[nd]] + 1)
+            return qf::fail(QF_ERR_INVALID, "qf_pack_tree: internal numbering error");
+        const int64_t off = static_cast<int64_t>(pos_of[left[nd]]) - p;
+        const int64_t f = feature[nd];
+        if (off < 1 || static_cast<uint64_t>(off) > max_off)
+            return qf::fail(QF_ERR_LIMIT, "qf_pack_tree: child offset does not fit 31-feature_bits bits");
+        if (f < 0 || f >= (int64_t(1) << feature_bits))
+            return qf::fail(QF_ERR_INVALID, "qf_pack_tree: feature index does not fit feature_bits");
+        const uint32_t hi = (static_cast<uint32_t>(off) << feature_bits) | static_cast<uint32_t>(f);
+        nodes_out[p] = (static_cast<uint64_t>(hi) << 32) | f32_bits(floor_to_f32(threshold[nd]));
     }
 
     // pass 4: members in rank order -> every leaf's list ends up sorted by rank

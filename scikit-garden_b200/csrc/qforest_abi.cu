@@ -80,7 +80,7 @@ struct qf_forest {
     int apply_row_warps = 0;      // warps along rows per CTA (0 auto)
     int apply_ilp = 4;
     int sort_rows = -1;           // walk rows in locality order: -1 auto, 0 never, 1 always
-    int key_shift = 0, key_bins = 1;   // locality buckets = leaf position in tree 0 >> key_shift
+    int key_shift = 0, key_bins = 1;   // locality buckets = first member of the leaf in tree 0 >> key_shift
     uint32_t root0 = 0;
     int64_t rows_per_chunk = 262144;    // rows per kernel chunk (denser chunks = closer neighbours in the locality order: C3-quarter K1 2.66 -> 2.52 ms against 131072)
     int cta_capacity = 0;         // cap on the members per row of the first bucket stage (0 = its capacity)
@@ -286,7 +286,7 @@ int build_locality_order(qf_forest* f, const float* X, int64_t n, int64_t ldx, c
     {
         SpanTimer span(f, SPAN_OTHER, st);
         qf::locality_key_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(
-            f->d_nodes, f->root0, X, ldx, n, f->fbits, f->key_shift, bucket, hist);
+            f->d_nodes, f->root0, X, ldx, n, f->fbits, f->key_shift, f->key_bins, bucket, hist);
     }
     QF_CUDA_TRY(cudaGetLastError());
     {
@@ -590,8 +590,9 @@ int qf_forest_create(const qf_forest_desc* d, qf_forest** out) {
     f->max_row_members = d->max_row_members > 0 ? d->max_row_members : d->n_members;
     f->expected_row_members = d->expected_row_members > 0 ? d->expected_row_members
                                                           : static_cast<double>(f->max_row_members);
-    {   // locality buckets: leaf position inside tree 0, at most kMaxKeyBins of them
-        const int64_t n0 = d->tree_offsets[1] - d->tree_offsets[0];
+    {   // locality buckets: first member of the leaf reached in tree 0 (members of the first tree
+        // start at 0 and there are at most n_train of them), at most kKeyBins buckets
+        const int64_t n0 = d->n_train;
         int shift = 0;
         while (((n0 - 1) >> shift) >= qf::kKeyBins) ++shift;
         f->root0 = static_cast<uint32_t>(d->tree_offsets[0]);
@@ -994,7 +995,8 @@ int qf_build_csr(const qf_csr_build_desc* d, int64_t* n_members_out) {
 
     const int T = d->n_trees;
     const int64_t N = d->n_train, n_nodes = d->n_nodes, total = N * T;
-    const int64_t n_blocks = (n_nodes + qf::kCsrScanBlock - 1) / qf::kCsrScanBlock;
+    const int64_t n_leaves = n_nodes / 2 + 1;            // a tree of k packed slots has k / 2 leaves
+    const int64_t n_blocks = (n_leaves + qf::kCsrScanBlock - 1) / qf::kCsrScanBlock;
     // a minimal forest object for the leaf-lookup launcher (no member lists yet)
     qf_forest f;
     f.device = d->device;
@@ -1007,7 +1009,7 @@ int qf_build_csr(const qf_csr_build_desc* d, int64_t* n_members_out) {
     f.d_nodes = reinterpret_cast<uint2*>(d->nodes_dev);
 
     struct Scratch {
-        void* p[9] = {};
+        void* p[11] = {};
         ~Scratch() { for (void* q : p) cudaFree(q); }
     } sc;
     auto alloc = [&](int k, size_t bytes) -> cudaError_t { return cudaMalloc(&sc.p[k], bytes ? bytes : 16); };
@@ -1020,6 +1022,8 @@ int qf_build_csr(const qf_csr_build_desc* d, int64_t* n_members_out) {
     QF_CUDA_TRY(alloc(6, static_cast<size_t>((n_nodes + T) / 2 + 2) * 4 + 16));   // long lists (<= one per leaf: a tree of k nodes has (k + 1) / 2) + counters
     QF_CUDA_TRY(alloc(7, static_cast<size_t>(T + 1) * 8));                  // tree offsets
     QF_CUDA_TRY(alloc(8, static_cast<size_t>(T) * 24));                     // per-tree stats
+    QF_CUDA_TRY(alloc(9, static_cast<size_t>(n_leaves) * 4));               // member counts in left-to-right leaf order
+    QF_CUDA_TRY(alloc(10, static_cast<size_t>(n_leaves) * 4));              // packed node of every leaf ordinal
     uint32_t* d_roots = static_cast<uint32_t*>(sc.p[0]);
     int32_t* d_idx = static_cast<int32_t*>(sc.p[1]);
     uint32_t* leaf_cnt = static_cast<uint32_t*>(sc.p[2]);
@@ -1032,6 +1036,8 @@ int qf_build_csr(const qf_csr_build_desc* d, int64_t* n_members_out) {
     unsigned long long* d_inbag = static_cast<unsigned long long*>(sc.p[8]);
     uint32_t* d_maxleaf = reinterpret_cast<uint32_t*>(d_inbag + T);
     double* d_sumsq = reinterpret_cast<double*>(d_inbag + 2 * T);
+    uint32_t* cnt_ord = static_cast<uint32_t*>(sc.p[9]);
+    int32_t* node_of = static_cast<int32_t*>(sc.p[10]);
 
     std::vector<uint32_t> roots(T);
     for (int t = 0; t < T; ++t) roots[t] = static_cast<uint32_t>(d->tree_offsets[t]);
@@ -1041,6 +1047,9 @@ int qf_build_csr(const qf_csr_build_desc* d, int64_t* n_members_out) {
     QF_CUDA_TRY(cudaMemset(leaf_cnt, 0, static_cast<size_t>(n_nodes) * 4));
     QF_CUDA_TRY(cudaMemset(leaf_sum, 0, static_cast<size_t>(n_nodes) * 4));
     QF_CUDA_TRY(cudaMemset(counters, 0, 16));
+    QF_CUDA_TRY(cudaMemset(start, 0, static_cast<size_t>(n_nodes) * 4));
+    QF_CUDA_TRY(cudaMemset(cnt_ord, 0, static_cast<size_t>(n_leaves) * 4));
+    QF_CUDA_TRY(cudaMemset(node_of, 0xFF, static_cast<size_t>(n_leaves) * 4));
 
     cudaStream_t st = nullptr;
     int rc = QF_OK;
@@ -1056,18 +1065,25 @@ int qf_build_csr(const qf_csr_build_desc* d, int64_t* n_members_out) {
     if (rc != QF_OK) return rc;
     const unsigned grid = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, int64_t(prop.multiProcessorCount) * 32));
     qf::csr_count_kernel<<<grid, 256, 0, st>>>(d_idx, d->counts_dev, total, leaf_cnt, leaf_sum);
-    qf::csr_block_sum_kernel<<<static_cast<unsigned>(n_blocks), 256, 0, st>>>(leaf_cnt, n_nodes, block_sum);
+    uint2* nodes = reinterpret_cast<uint2*>(d->nodes_dev);
+    qf::csr_leaf_order_kernel<<<static_cast<unsigned>((n_nodes + 255) / 256), 256, 0, st>>>(nodes, n_nodes, leaf_cnt, n_leaves,
+                                                                                          cnt_ord, node_of, counters + 2);
+    qf::csr_block_sum_kernel<<<static_cast<unsigned>(n_blocks), 256, 0, st>>>(cnt_ord, n_leaves, block_sum);
     qf::csr_scan_sums_kernel<<<1, 1024, 0, st>>>(block_sum, n_blocks, block_sum + n_blocks);
     QF_CUDA_TRY(cudaGetLastError());
     uint64_t n_members = 0;
     QF_CUDA_TRY(cudaMemcpy(&n_members, block_sum + n_blocks, 8, cudaMemcpyDeviceToHost));
+    int bad_ordinal = 0;
+    QF_CUDA_TRY(cudaMemcpy(&bad_ordinal, counters + 2, 4, cudaMemcpyDeviceToHost));
+    if (bad_ordinal)
+        return qf::fail(QF_ERR_INVALID, "qf_build_csr: leaves do not carry their left-to-right ordinal "
+                                        "(nodes must come from qf_pack_tree with train_leaves == NULL and member_base = slot / 2)");
     if (n_members > 0xFFFFFFFFull)
         return qf::fail(QF_ERR_LIMIT, "qf_build_csr: more than 2^32-1 member entries in the forest");
     if (static_cast<int64_t>(n_members) > d->members_capacity)
         return qf::fail(QF_ERR_INVALID, "qf_build_csr: members_capacity too small");
-    uint2* nodes = reinterpret_cast<uint2*>(d->nodes_dev);
     uint2* members = reinterpret_cast<uint2*>(d->members_dev);
-    qf::csr_leaf_record_kernel<<<static_cast<unsigned>(n_blocks), 256, 0, st>>>(nodes, leaf_cnt, n_nodes, block_sum, start);
+    qf::csr_leaf_record_kernel<<<static_cast<unsigned>(n_blocks), 256, 0, st>>>(nodes, cnt_ord, node_of, n_leaves, block_sum, start);
     qf::csr_scatter_kernel<<<grid, 256, 0, st>>>(d_idx, d->counts_dev, total, T, d->rank_dev, start, leaf_cnt, leaf_sum, members);
     qf::csr_sort_small_kernel<<<static_cast<unsigned>((n_nodes + 255) / 256), 256, 0, st>>>(nodes, n_nodes, members, big,
                                                                                           counters, counters + 1);

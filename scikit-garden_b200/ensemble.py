@@ -152,8 +152,12 @@ class _BaseForestQuantileRegressor(RegressorMixin, BaseEstimator):
                 m0, m1 = fl.member_offsets[t], fl.member_offsets[t + 1]
                 nd = fl.nodes[n0:n1]
                 hi = (nd >> np.uint64(32)).astype(np.uint32)
-                is_leaf = (hi & np.uint32(0x80000000)) != 0
+                is_leaf = np.flatnonzero((hi & np.uint32(0x80000000)) != 0)
+                # the member lists follow the leaves from left to right = by first member index
+                is_leaf = is_leaf[np.argsort((nd[is_leaf] & np.uint64(0xFFFFFFFF)), kind="stable")]
                 cnt = (hi[is_leaf] & np.uint32(0x7FFFFFFF)).astype(np.int64)
+                is_leaf = is_leaf[cnt > 0]
+                cnt = cnt[cnt > 0]
                 ids = (np.arange(n1 - n0, dtype=np.int32) if fl.node_ids is None
                        else fl.node_ids[n0:n1])[is_leaf]
                 mem = fl.members[m0:m1]

@@ -4,9 +4,11 @@ Replaces the fit bookkeeping of the reference (skgarden/quantile/ensemble.py:83-
 dense (T,N) ``y_train_leaves_`` / ``y_weights_`` arrays, built by an O(T*L*N) loop) and
 scikit-learn's 64-byte AoS node records (sklearn/tree/_tree.pxd:15-25) by
 
-* 8-byte packed nodes in depth-first preorder, trees back to back,
+* 8-byte packed nodes in level order with sibling pairs (one padding slot per tree, see
+  ``include/qforest_b200.h``), trees back to back,
 * per-tree leaf -> in-bag member lists (CSR) whose entries are
-  (rank in ``np.argsort(y_train_)``, float32 weight), sorted by rank inside a leaf,
+  (rank in ``np.argsort(y_train_)``, float32 weight), sorted by rank inside a leaf, the
+  leaves from left to right,
 * ``y_sorted = y_train_.astype(float32)[sorter]`` (skgarden/quantile/utils.py:46,52).
 
 The packing itself is native code (``qf_pack_tree`` in csrc/pack_forest.cpp, called
@@ -45,9 +47,9 @@ class FlatForest:
     n_features: int
     feature_bits: int
     n_train: int
-    nodes: np.ndarray            # uint64 [n_nodes]
+    nodes: np.ndarray            # uint64 [n_nodes] packed slots (sklearn node_count + 1 per tree)
     tree_offsets: np.ndarray     # int64  [T+1]
-    node_ids: Optional[np.ndarray]   # int32 [n_nodes]; None when identical to packed order
+    node_ids: Optional[np.ndarray]   # int32 [n_nodes] sklearn id of every slot (-1 = padding)
     members: np.ndarray          # uint64 [n_members]
     member_offsets: np.ndarray   # int64  [T+1]
     y_sorted: np.ndarray         # float32 [N]
@@ -73,7 +75,7 @@ class FlatForest:
 
     # -- on-disk format: a plain .npz of the arrays above
     def save(self, path: str) -> None:
-        np.savez(path, n_trees=self.n_trees, n_features=self.n_features,
+        np.savez(path, layout=LAYOUT_VERSION, n_trees=self.n_trees, n_features=self.n_features,
                  feature_bits=self.feature_bits, n_train=self.n_train, nodes=self.nodes,
                  tree_offsets=self.tree_offsets,
                  node_ids=np.zeros(0, np.int32) if self.node_ids is None else self.node_ids,
@@ -87,6 +89,10 @@ class FlatForest:
     @classmethod
     def load(cls, path: str) -> "FlatForest":
         z = np.load(path)
+        if "layout" not in z.files or int(z["layout"]) != LAYOUT_VERSION:
+            raise ValueError("%s holds a forest in another packed layout (file %s, library %d); "
+                             "flatten the forest again" % (path, int(z["layout"]) if "layout" in z.files else 1,
+                                                          LAYOUT_VERSION))
         node_ids = z["node_ids"]
         return cls(int(z["n_trees"]), int(z["n_features"]), int(z["feature_bits"]),
                    int(z["n_train"]), z["nodes"], z["tree_offsets"],
@@ -95,6 +101,14 @@ class FlatForest:
                    int(z["max_row_members"]), float(z["expected_row_members"]),
                    int(z["max_depth"]), z["sorter"],
                    z["leaf_impurity"] if "leaf_impurity" in z.files and z["leaf_impurity"].size else None)
+
+
+LAYOUT_VERSION = 2      # 1: depth-first preorder nodes; 2: level order with sibling pairs
+
+
+def _per_slot(values, ids):
+    """values[sklearn id] -> per packed slot (0 in the padding slot, id -1)."""
+    return np.where(ids >= 0, values[np.maximum(ids, 0)], 0.0)
 
 
 def _tree_arrays(tree):
@@ -147,7 +161,7 @@ def flatten_forest(trees: Sequence, train_leaves, counts, y_train, n_features: i
 
     arrays = [_tree_arrays(t) for t in trees]
     node_counts = np.array([a[0].shape[0] for a in arrays], dtype=np.int64)
-    tree_offsets = np.concatenate([[0], np.cumsum(node_counts)]).astype(np.int64)
+    tree_offsets = np.concatenate([[0], np.cumsum(node_counts + 1)]).astype(np.int64)    # + the padding slot
 
     def counts_of(t):
         if counts is None or counts[t] is None:
@@ -178,7 +192,7 @@ def flatten_forest(trees: Sequence, train_leaves, counts, y_train, n_features: i
         n_inbag, max_members, depth = C.c_int64(0), C.c_int32(0), C.c_int32(0)
         sum_sq = C.c_double(0.0)
         nodes_t, ids_t, members_t = nodes[n0:n1], node_ids[n0:n1], members[m0:m1]
-        rc = L.qf_pack_tree(n1 - n0, _ptr(left), _ptr(right), _ptr(feat), _ptr(thr), feature_bits,
+        rc = L.qf_pack_tree(left.shape[0], _ptr(left), _ptr(right), _ptr(feat), _ptr(thr), feature_bits,
                             N, _ptr(lv), _ptr(cnt), _ptr(sorter), m0,
                             _ptr(nodes_t), _ptr(ids_t), _ptr(members_t) if m1 > m0 else None,
                             C.byref(n_inbag), C.byref(max_members), C.byref(depth), C.byref(sum_sq))
@@ -186,9 +200,9 @@ def flatten_forest(trees: Sequence, train_leaves, counts, y_train, n_features: i
             raise _native.QFError(rc, "tree %d: %s" % (t, _native.last_error()))
         if n_inbag.value != m1 - m0:
             raise RuntimeError("tree %d: in-bag count mismatch" % t)
-        leaf_values[n0:n1] = val[ids_t]
+        leaf_values[n0:n1] = _per_slot(val, ids_t)
         if leaf_impurity is not None:
-            leaf_impurity[n0:n1] = impurities[t][ids_t]
+            leaf_impurity[n0:n1] = _per_slot(impurities[t], ids_t)
         stats[t] = (max_members.value, depth.value, sum_sq.value)
 
     workers = n_jobs if n_jobs and n_jobs > 0 else min(T, os.cpu_count() or 1)
@@ -202,11 +216,9 @@ def flatten_forest(trees: Sequence, train_leaves, counts, y_train, n_features: i
     if unit_weights:
         members &= np.uint64(0xFFFFFFFF)
         members |= np.uint64(0x3F800000) << np.uint64(32)          # float32 1.0
-    identity = bool(np.array_equal(
-        node_ids, np.concatenate([np.arange(c, dtype=np.int32) for c in node_counts])))
     return FlatForest(
         n_trees=T, n_features=int(n_features), feature_bits=feature_bits, n_train=N,
-        nodes=nodes, tree_offsets=tree_offsets, node_ids=None if identity else node_ids,
+        nodes=nodes, tree_offsets=tree_offsets, node_ids=node_ids,
         members=members, member_offsets=member_offsets, y_sorted=y_sorted,
         leaf_values=leaf_values, max_row_members=int(stats[:, 0].sum()),
         expected_row_members=float((stats[:, 2] / np.maximum(inbag, 1)).sum()),
@@ -239,7 +251,7 @@ def flatten_forest_device(trees: Sequence, X_train, counts, y_train, n_features:
     feature_bits = max(1, int(n_features - 1).bit_length())
     arrays = [_tree_arrays(t) for t in trees]
     node_counts = np.array([a[0].shape[0] for a in arrays], dtype=np.int64)
-    tree_offsets = np.concatenate([[0], np.cumsum(node_counts)]).astype(np.int64)
+    tree_offsets = np.concatenate([[0], np.cumsum(node_counts + 1)]).astype(np.int64)    # + the padding slot
     n_nodes = int(tree_offsets[-1])
     nodes = np.empty(n_nodes, dtype=np.uint64)
     node_ids = np.empty(n_nodes, dtype=np.int32)
@@ -253,14 +265,15 @@ def flatten_forest_device(trees: Sequence, X_train, counts, y_train, n_features:
         n0, n1 = int(tree_offsets[t]), int(tree_offsets[t + 1])
         depth = C.c_int32(0)
         nodes_t, ids_t = nodes[n0:n1], node_ids[n0:n1]
-        rc = L.qf_pack_tree(n1 - n0, _ptr(left), _ptr(right), _ptr(feat), _ptr(thr), feature_bits,
-                            0, None, None, None, 0, _ptr(nodes_t), _ptr(ids_t), None,
+        # member_base = first leaf ordinal of the tree (a tree of k slots has k / 2 leaves)
+        rc = L.qf_pack_tree(left.shape[0], _ptr(left), _ptr(right), _ptr(feat), _ptr(thr), feature_bits,
+                            0, None, None, None, n0 // 2, _ptr(nodes_t), _ptr(ids_t), None,
                             None, None, C.byref(depth), None)
         if rc != 0:
             raise _native.QFError(rc, "tree %d: %s" % (t, _native.last_error()))
-        leaf_values[n0:n1] = val[ids_t]
+        leaf_values[n0:n1] = _per_slot(val, ids_t)
         if leaf_impurity is not None:
-            leaf_impurity[n0:n1] = impurities[t][ids_t]
+            leaf_impurity[n0:n1] = _per_slot(impurities[t], ids_t)
         depths[t] = depth.value
 
     workers = n_jobs if n_jobs and n_jobs > 0 else min(T, os.cpu_count() or 1)
@@ -326,11 +339,9 @@ def flatten_forest_device(trees: Sequence, X_train, counts, y_train, n_features:
         members &= np.uint64(0xFFFFFFFF)
         members |= np.uint64(0x3F800000) << np.uint64(32)
     member_offsets = np.concatenate([[0], np.cumsum(inbag)]).astype(np.int64)
-    identity = bool(np.array_equal(
-        node_ids, np.concatenate([np.arange(c, dtype=np.int32) for c in node_counts])))
     return FlatForest(
         n_trees=T, n_features=int(n_features), feature_bits=feature_bits, n_train=N,
-        nodes=nodes, tree_offsets=tree_offsets, node_ids=None if identity else node_ids,
+        nodes=nodes, tree_offsets=tree_offsets, node_ids=node_ids,
         members=members, member_offsets=member_offsets, y_sorted=y_sorted,
         leaf_values=leaf_values, max_row_members=int(max_leaf.sum()),
         expected_row_members=float((sum_sq / np.maximum(inbag, 1)).sum()),

@@ -21,7 +21,7 @@ def decode_apply(flat, X):
             thr = lo[nd].view(np.float32)                      # floor-f32 threshold
             f = (hi[nd] & fmask).astype(np.int64)
             off = (hi[nd] >> np.uint32(flat.feature_bits)).astype(np.int64)
-            node[r] = nd + np.where(X[r, f] <= thr, 1, off)    # float32 compare
+            node[r] = nd + off + np.where(X[r, f] <= thr, 0, 1)   # float32 compare; right child = left + 1
             active[r] = (hi[node[r]] & np.uint32(0x80000000)) == 0
         node_idx[:, t] = node
     start = lo[node_idx].astype(np.int64)

@@ -57,17 +57,31 @@ def _chain_tree(depth, left_heavy):
     return n, left, right, feat, thr
 
 
+def _complete_tree(depth):
+    """Complete binary tree in heap numbering (node k has children 2k+1, 2k+2)."""
+    n = 2 ** (depth + 1) - 1
+    left = np.full(n, -1, dtype=np.int64)
+    right = np.full(n, -1, dtype=np.int64)
+    inner = np.arange(2 ** depth - 1)
+    left[inner], right[inner] = 2 * inner + 1, 2 * inner + 2
+    feat = np.where(left >= 0, 0, -2).astype(np.int64)
+    thr = np.where(left >= 0, 0.5, -2.0)
+    return n, left, right, feat, thr
+
+
 def test_offset_limit_is_reported():
-    # feature_bits = 24 leaves 7 bits for the right-child offset (max 127).  A left-heavy
-    # chain of depth 100 puts the root's right child 200 nodes away -> QF_ERR_LIMIT (never
-    # a silently truncated offset); the right-heavy mirror image (offsets of 2) packs fine.
+    # feature_bits = 24 leaves 7 bits for the child offset (max 127).  In level order the children
+    # of a node lie about one level width behind it: chains of any depth pack fine (offsets of 1
+    # or 2), a complete tree of depth 9 has levels of 256 nodes -> QF_ERR_LIMIT (never a silently
+    # truncated offset).
     lib = _native.lib()
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    for left_heavy, expect in ((False, _native.QF_OK), (True, _native.QF_ERR_LIMIT)):
-        n, left, right, feat, thr = _chain_tree(100, left_heavy)
+    cases = [(_chain_tree(100, False), _native.QF_OK), (_chain_tree(100, True), _native.QF_OK),
+             (_complete_tree(6), _native.QF_OK), (_complete_tree(9), _native.QF_ERR_LIMIT)]
+    for (n, left, right, feat, thr), expect in cases:
         leaves = np.full(5, n - 1, dtype=np.int64)
         sorter = np.arange(5, dtype=np.int64)
-        nodes, ids, mem = np.zeros(n, np.uint64), np.zeros(n, np.int32), np.zeros(5, np.uint64)
+        nodes, ids, mem = np.zeros(n + 1, np.uint64), np.zeros(n + 1, np.int32), np.zeros(5, np.uint64)
         rc = lib.qf_pack_tree(n, p(left), p(right), p(feat), p(thr), 24, 5, p(leaves), None, p(sorter),
                               0, p(nodes), p(ids), p(mem), None, None, None, None)
         assert rc == expect, _native.last_error()

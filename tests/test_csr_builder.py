@@ -30,14 +30,20 @@ def test_structure_only_packing_matches_full_packing():
     for t, e in enumerate(est.estimators_):
         left, right, feat, thr, _ = _tree_arrays(e.tree_)
         n = len(left)
-        nodes, ids, depth = np.empty(n, np.uint64), np.empty(n, np.int32), C.c_int32(0)
+        nodes, ids, depth = np.empty(n + 1, np.uint64), np.empty(n + 1, np.int32), C.c_int32(0)
+        base = int(fl.tree_offsets[t]) // 2                # first leaf ordinal of the tree
         rc = L.qf_pack_tree(n, _ptr(left), _ptr(right), _ptr(feat), _ptr(thr), fl.feature_bits, 0, None, None,
-                            None, 0, _ptr(nodes), _ptr(ids), None, None, None, C.byref(depth), None)
+                            None, base, _ptr(nodes), _ptr(ids), None, None, None, C.byref(depth), None)
         assert rc == 0, _native.last_error()
         ref = fl.nodes[fl.tree_offsets[t]:fl.tree_offsets[t + 1]]
         leaf = (ref >> np.uint64(63)) == 1
         assert_array_equal(nodes[~leaf], ref[~leaf])
-        assert np.all(nodes[leaf] == np.uint64(0x80000000) << np.uint64(32))
+        # empty leaves carrying their left-to-right ordinal: same order as the member ranges
+        assert np.all(nodes[leaf] >> np.uint64(32) == np.uint64(0x80000000))
+        ordinal = (nodes[leaf] & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        assert sorted(ordinal) == list(range(base, base + (n + 1) // 2))
+        start = (ref[leaf] & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        assert np.all(np.diff(start[np.argsort(ordinal)]) >= 0)
         assert_array_equal(ids, fl.node_ids[fl.tree_offsets[t]:fl.tree_offsets[t + 1]])
         assert depth.value == e.tree_.max_depth
 
@@ -58,9 +64,7 @@ def test_device_builder_equals_host_flattener(kind, kw):
     assert_array_equal(dev.members, host.members)             # ranks and float32 weight bits
     assert_array_equal(dev.member_offsets, host.member_offsets)
     assert_array_equal(dev.leaf_values, host.leaf_values)
-    assert (dev.node_ids is None) == (host.node_ids is None)
-    if host.node_ids is not None:
-        assert_array_equal(dev.node_ids, host.node_ids)
+    assert_array_equal(dev.node_ids, host.node_ids)
     assert dev.max_row_members == host.max_row_members and dev.max_depth == host.max_depth
     assert dev.expected_row_members == host.expected_row_members
     # and the estimator predicts the same through either builder

@@ -14,7 +14,7 @@ def test_layout_reproduces_reference(name):
     g = _golden.load(name)
     flat = _golden.flat_from_golden(g)
     assert flat.n_trees == len(g.estimators)
-    assert flat.n_nodes == g.node_offsets[-1]
+    assert flat.n_nodes == g.node_offsets[-1] + flat.n_trees          # one padding slot per tree
     node_idx, start, count = _layout.decode_apply(flat, g.X_test)
     assert_array_equal(_layout.sklearn_ids(flat, node_idx), g.apply)        # leaf ids bit-exact
     assert count.min() >= 1                                                 # every leaf has members
@@ -26,12 +26,47 @@ def test_layout_reproduces_reference(name):
     np.testing.assert_allclose(got / flat.n_trees, g.mean, rtol=1e-12)
 
 
-def test_best_first_trees_are_renumbered():
-    g = _golden.load("rf_maxleaf50")
-    flat = _golden.flat_from_golden(g)
-    assert flat.node_ids is not None             # max_leaf_nodes: sklearn order is not preorder
-    g2 = _golden.load("et_msl5")
-    assert _golden.flat_from_golden(g2).node_ids is None
+def test_level_order_layout_with_sibling_pairs():
+    """include/qforest_b200.h: slot 0 root, slot 1 padding, children side by side and later than
+    their parent, every level contiguous; leaves' member ranges grow from left to right."""
+    for name in ("rf_maxleaf50", "et_msl5"):           # best-first and depth-first sklearn numbering
+        g = _golden.load(name)
+        flat = _golden.flat_from_golden(g)
+        assert flat.node_ids is not None
+        lo = (flat.nodes & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        hi = (flat.nodes >> np.uint64(32)).astype(np.uint32)
+        for t, est in enumerate(g.estimators):
+            tr = est.tree_
+            n0, n1 = int(flat.tree_offsets[t]), int(flat.tree_offsets[t + 1])
+            assert n1 - n0 == tr.node_count + 1 and n0 % 2 == 0
+            ids = flat.node_ids[n0:n1]
+            assert ids[0] == 0 and ids[1] == -1 and flat.nodes[n0 + 1] == 0
+            assert sorted(ids[ids >= 0]) == list(range(tr.node_count))
+            pos = np.empty(tr.node_count, dtype=np.int64)
+            pos[ids[ids >= 0]] = np.flatnonzero(ids >= 0)
+            inner = np.flatnonzero(tr.children_left != -1)
+            off = (hi[n0 + pos[inner]] >> np.uint32(flat.feature_bits)).astype(np.int64)
+            assert_array_equal(pos[tr.children_left[inner]], pos[inner] + off)
+            assert_array_equal(pos[tr.children_right[inner]], pos[inner] + off + 1)
+            assert np.all(pos[tr.children_left[inner]] % 2 == 0)
+            # level order: depth never decreases along the slots
+            depth = np.zeros(tr.node_count, dtype=np.int64)
+            for nd in np.argsort(pos):                   # parents come before their children
+                if tr.children_left[nd] != -1:
+                    depth[tr.children_left[nd]] = depth[tr.children_right[nd]] = depth[nd] + 1
+            assert np.all(np.diff(depth[np.argsort(pos)]) >= 0)
+            # member ranges follow the leaves from left to right (depth-first order)
+            order, stack = [], [0]
+            while stack:
+                nd = stack.pop()
+                if tr.children_left[nd] == -1:
+                    order.append(nd)
+                else:
+                    stack += [tr.children_right[nd], tr.children_left[nd]]
+            starts = lo[n0 + pos[order]]
+            cnts = (hi[n0 + pos[order]] & np.uint32(0x7FFFFFFF)).astype(np.int64)
+            assert starts[0] == flat.member_offsets[t]
+            assert_array_equal(starts[1:], starts[:-1] + cnts[:-1])
 
 
 def test_members_sorted_by_rank_within_leaf():
@@ -70,7 +105,8 @@ def test_flat_forest_roundtrip(tmp_path):
     back = sg.FlatForest.load(p)
     assert_array_equal(back.nodes, flat.nodes)
     assert_array_equal(back.members, flat.members)
-    assert back.max_row_members == flat.max_row_members and back.node_ids is None
+    assert back.max_row_members == flat.max_row_members
+    assert_array_equal(back.node_ids, flat.node_ids)
 
 
 def test_pack_tree_rejects_bad_input():

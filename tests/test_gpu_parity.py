@@ -28,7 +28,7 @@ def _cuda(x):
 
 def test_native_library_is_loaded():
     from skgarden_b200 import _native
-    assert _native.lib().qf_abi_version() == 1
+    assert _native.lib().qf_abi_version() == _native.ABI_VERSION == 2
     with open("/proc/self/maps") as fh:
         assert "libqforest_b200.so" in fh.read()
 

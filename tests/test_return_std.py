@@ -52,9 +52,10 @@ def test_impurities_travel_with_the_flattened_forest(tmp_path):
     g = _load("rf_msl10")
     flat = _flat(g)
     assert flat.leaf_impurity is not None and flat.leaf_impurity.shape == flat.leaf_values.shape
-    for t, tree in enumerate(g.trees):                        # identity node order (depth-first builder)
+    for t, tree in enumerate(g.trees):
         n0, n1 = flat.tree_offsets[t], flat.tree_offsets[t + 1]
-        assert_array_equal(flat.leaf_impurity[n0:n1], tree.impurity)
+        ids = flat.node_ids[n0:n1]
+        assert_array_equal(flat.leaf_impurity[n0:n1][ids >= 0], tree.impurity[ids[ids >= 0]])
     path = str(tmp_path / "f.npz")
     flat.save(path)
     assert_array_equal(sg.FlatForest.load(path).leaf_impurity, flat.leaf_impurity)
