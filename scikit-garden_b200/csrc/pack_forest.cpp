@@ -2,7 +2,9 @@
 // 8-byte packed nodes in level order (sibling pairs) + the leaf -> in-bag member lists that
 // replace the dense (T,N) y_train_leaves_ / y_weights_ arrays of the reference
 // (skgarden/quantile/ensemble.py:83-101).  Layout documented in include/qforest_b200.h.
+#include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -62,31 +64,46 @@ extern "C" int qf_pack_tree(int64_t n_nodes, const int64_t* left, const int64_t*
     // few 32-byte sectors per visit.
     const int64_t n_slots = n_nodes + 1;
     std::vector<int32_t> pos_of(n_nodes, -1);
-    std::vector<int64_t> queue;                            // sklearn ids in level order
-    queue.reserve(n_nodes);
-    queue.push_back(0);
+    std::vector<int32_t> depth_of(n_nodes, 0);
     pos_of[0] = 0;
     node_id_out[0] = 0;
     node_id_out[1] = -1;
     nodes_out[1] = 0;                                      // never reached by a walk, not a leaf
     int32_t next = 2, max_depth = 0;
-    size_t level_end = 1;                                  // queue index where the current level ends
-    for (size_t qi = 0; qi < queue.size(); ++qi) {
-        if (qi == level_end) {
-            ++max_depth;
-            level_end = queue.size();
+    // Generalisation used for experiments: QF_NODE_BLOCK_LEVELS=h groups h levels of descendants of
+    // a node into one contiguous block (blocks in level order); unset / 0 = one block = plain level order.
+    int block_levels = INT32_MAX;
+    if (const char* env = std::getenv("QF_NODE_BLOCK_LEVELS")) {
+        const int h = std::atoi(env);
+        if (h > 0) block_levels = h;
+    }
+    std::vector<int64_t> roots(1, 0), next_roots, level, next_level;
+    while (!roots.empty()) {
+        next_roots.clear();
+        for (const int64_t r : roots) {
+            level.assign(1, r);
+            for (int k = 0; k < block_levels && !level.empty(); ++k) {
+                next_level.clear();
+                for (const int64_t nd : level) {
+                    if (left[nd] == -1) continue;          // sklearn: leaf <=> children_left == -1 (_tree.pyx:978)
+                    const int64_t kids[2] = {left[nd], right[nd]};
+                    for (const int64_t c : kids) {
+                        if (c <= 0 || c >= n_nodes || pos_of[c] != -1 || next >= n_slots)
+                            return qf::fail(QF_ERR_INVALID, "qf_pack_tree: children arrays do not form a tree");
+                        pos_of[c] = next;
+                        node_id_out[next] = static_cast<int32_t>(c);
+                        ++next;
+                        depth_of[c] = depth_of[nd] + 1;
+                        if (depth_of[c] > max_depth) max_depth = depth_of[c];
+                        next_level.push_back(c);
+                    }
+                }
+                level.swap(next_level);
+            }
+            for (const int64_t nd : level)
+                if (left[nd] != -1) next_roots.push_back(nd);
         }
-        const int64_t nd = queue[qi];
-        if (left[nd] == -1) continue;                      // sklearn: leaf <=> children_left == -1 (_tree.pyx:978)
-        const int64_t kids[2] = {left[nd], right[nd]};
-        for (const int64_t c : kids) {
-            if (c <= 0 || c >= n_nodes || pos_of[c] != -1 || next >= n_slots)
-                return qf::fail(QF_ERR_INVALID, "qf_pack_tree: children arrays do not form a tree");
-            pos_of[c] = next;
-            node_id_out[next] = static_cast<int32_t>(c);
-            ++next;
-            queue.push_back(c);
-        }
+        roots.swap(next_roots);
     }
     if (next != n_slots)
         return qf::fail(QF_ERR_INVALID, "qf_pack_tree: unreachable nodes in tree");
