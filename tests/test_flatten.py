@@ -118,3 +118,38 @@ def test_pack_tree_rejects_bad_input():
     bad = [np.zeros(len(g.y_train), dtype=np.int64)] * len(trees)     # node 0 is not a leaf
     with pytest.raises(_native.QFError):
         sg.flatten_forest(trees, bad, None, g.y_train, 13)
+
+
+@pytest.mark.parametrize("block_levels", ["0", "1", "2", "5"])
+def test_packer_on_odd_tree_shapes(block_levels, monkeypatch):
+    """Single-leaf trees, stumps, chains, best-first numbering, with plain level order and the
+    blocked variants of the layout (QF_NODE_BLOCK_LEVELS): leaf ids and member lists decode to
+    scikit-learn's apply and to the oracle's percentiles."""
+    from sklearn.ensemble import ExtraTreesRegressor, RandomForestRegressor
+    from oracle import qrf_oracle as O
+    monkeypatch.setenv("QF_NODE_BLOCK_LEVELS", block_levels)
+    rng = np.random.RandomState(int(block_levels))
+    X = rng.randn(400, 4).astype(np.float32)
+    Xt = rng.randn(64, 4).astype(np.float32)
+    chain_y = np.cumsum(np.abs(rng.randn(400))) * (X[:, 0] > -10)       # deep one-sided splits
+    cases = [
+        (RandomForestRegressor(n_estimators=3, random_state=0), np.zeros(400)),               # root is a leaf
+        (RandomForestRegressor(n_estimators=3, max_depth=1, random_state=0), X[:, 0] + 0.0),   # stumps
+        (ExtraTreesRegressor(n_estimators=3, max_leaf_nodes=7, random_state=0), X[:, 1] * X[:, 0]),
+        (RandomForestRegressor(n_estimators=2, min_samples_leaf=1, random_state=1), chain_y),
+        (ExtraTreesRegressor(n_estimators=4, min_samples_leaf=3, bootstrap=True, random_state=2),
+         np.round(X[:, 0] - X[:, 2], 1)),
+    ]
+    for est, y in cases:
+        est.fit(X, y)
+        trees = [e.tree_ for e in est.estimators_]
+        boot = bool(est.bootstrap)
+        counts = [sg.bootstrap_counts(e.random_state, 400) for e in est.estimators_] if boot else None
+        flat = sg.flatten_forest(trees, [t.apply(X) for t in trees], counts, y, 4)
+        assert flat.n_nodes == sum(t.node_count + 1 for t in trees)
+        node_idx, start, count = _layout.decode_apply(flat, Xt)
+        leaves = est.apply(Xt)
+        assert_array_equal(_layout.sklearn_ids(flat, node_idx), leaves)
+        index = O.SparseIndex(y, *O.fit_attributes(est.estimators_, X, boot), flat.sorter)
+        want = O.predict_sparse(index, leaves, [10, 50, 90])
+        assert_array_equal(_layout.decode_predict(flat, start, count, [10, 50, 90]), want)
