@@ -61,9 +61,9 @@ struct ApplyParams {
 enum { APPLY_EMIT_SEGMENT = 0, APPLY_EMIT_NODE = 1 };
 
 constexpr int kApplyThreads = 256;
-constexpr int kApplyLevels = 2;                         // visits per chain between two warp votes
+constexpr int kApplyLevels = 2;                         // visits per chain between two warp votes (default)
 
-template <int ILP, int EMIT>
+template <int ILP, int EMIT, int LEVELS = kApplyLevels>
 __global__ void __launch_bounds__(kApplyThreads)
 apply_kernel(const ApplyParams p, void* __restrict__ out) {
     extern __shared__ float xt[];                       // [F][ROWS]
@@ -110,7 +110,7 @@ apply_kernel(const ApplyParams p, void* __restrict__ out) {
     // chain k of every lane walks the same tree (warp-uniform tree[k]).  Per visit and chain:
     // one predicated 8-byte node load, one predicated shared-memory load, compare, select, add.
     // The sign bit of nd[k].y is the chain's state: a lane that reached its leaf keeps the leaf
-    // node in nd[k] and its loads are predicated off.  Every kApplyLevels visits the sign bits of
+    // node in nd[k] and its loads are predicated off.  Every LEVELS visits the sign bits of
     // all chains are AND-reduced over the warp (one REDUX); a chain whose 32 lanes all sit on a
     // leaf writes its results and is re-armed with the warp's next tree.
     // fbits and the node base take a round trip through shared memory: that makes them opaque
@@ -138,7 +138,7 @@ apply_kernel(const ApplyParams p, void* __restrict__ out) {
 
     while (armed) {
 #pragma unroll
-        for (int lvl = 0; lvl < kApplyLevels; ++lvl) {
+        for (int lvl = 0; lvl < LEVELS; ++lvl) {
 #pragma unroll
             for (int k = 0; k < ILP; ++k)
                 if (static_cast<int32_t>(nd[k].y) >= 0) nd[k] = __ldg(nodes + node[k]);

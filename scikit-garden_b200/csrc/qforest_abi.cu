@@ -79,6 +79,7 @@ struct qf_forest {
     // options (0 = auto where noted)
     int apply_row_warps = 0;      // warps along rows per CTA (0 auto)
     int apply_ilp = 4;
+    int apply_levels = qf::kApplyLevels;   // visits between two warp votes (1, 2, 3, 4; ILP 4 only)
     int sort_rows = -1;           // walk rows in locality order: -1 auto, 0 never, 1 always
     int key_shift = 0, key_bins = 1;   // locality buckets = first member of the leaf in tree 0 >> key_shift
     uint32_t root0 = 0;
@@ -264,6 +265,14 @@ int launch_apply(qf_forest* f, const float* X, int64_t n, int64_t ldx, void* out
         ++f->launches;
         return QF_OK;
     };
+    if (f->apply_ilp == 4 && f->apply_levels != qf::kApplyLevels) {
+        switch (f->apply_levels) {
+            case 1: return run(qf::apply_kernel<4, EMIT, 1>);
+            case 3: return run(qf::apply_kernel<4, EMIT, 3>);
+            case 4: return run(qf::apply_kernel<4, EMIT, 4>);
+            default: break;
+        }
+    }
     switch (f->apply_ilp) {
         case 1: return run(qf::apply_kernel<1, EMIT>);
         case 2: return run(qf::apply_kernel<2, EMIT>);
@@ -736,6 +745,9 @@ int qf_forest_set_option(qf_forest* f, const char* key, int64_t value) {
         if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8)
             return qf::fail(QF_ERR_INVALID, "apply_row_warps must be 0 (auto), 1, 2, 4 or 8");
         f->apply_row_warps = static_cast<int>(value);
+    } else if (k == "apply_levels") {
+        if (value < 1 || value > 4) return qf::fail(QF_ERR_INVALID, "apply_levels must be 1, 2, 3 or 4");
+        f->apply_levels = static_cast<int>(value);
     } else if (k == "apply_ilp") {
         if (value != 1 && value != 2 && value != 4 && value != 8)
             return qf::fail(QF_ERR_INVALID, "apply_ilp must be 1, 2, 4 or 8");

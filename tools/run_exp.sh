@@ -1,13 +1,8 @@
 #!/bin/bash
-# one-off experiments: node block layouts (QF_NODE_BLOCK_LEVELS, csrc/pack_forest.cpp)
+# one-off experiments: visits between two warp votes in the leaf lookup (apply_levels)
 tag=${1:-exp}
 out=gpurun_out
 mkdir -p $out
-for h in 0 3 2; do
-  export QF_NODE_BLOCK_LEVELS=$h
-  python tools/sweep.py --config c2 --reps 7 --grid "[{}]" > $out/sweep_c2_${tag}_h$h.log 2>&1; echo "c2 h=$h: $(grep -m1 apply= $out/sweep_c2_${tag}_h$h.log | cut -c60-200)"
-done
-for h in 0 3; do
-  export QF_NODE_BLOCK_LEVELS=$h
-  python tools/sweep.py --config c3q --mode fast --reps 3 --grid "[{}]" > $out/sweep_c3q_${tag}_h$h.log 2>&1; echo "c3q h=$h: $(grep -m1 apply= $out/sweep_c3q_${tag}_h$h.log | cut -c60-200)"
-done
+G='[{},{"apply_levels":1},{"apply_levels":3},{"apply_levels":4}]'
+python tools/sweep.py --config c2 --reps 9 --grid "$G" > $out/sweep_c2_$tag.log 2>&1; grep "apply=" $out/sweep_c2_$tag.log | cut -c1-150
+python -m pytest tests -m gpu -x -q > $out/pytest_gpu_$tag.log 2>&1; echo "pytest exit $?"; tail -2 $out/pytest_gpu_$tag.log
