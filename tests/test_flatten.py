@@ -153,3 +153,16 @@ def test_packer_on_odd_tree_shapes(block_levels, monkeypatch):
         index = O.SparseIndex(y, *O.fit_attributes(est.estimators_, X, boot), flat.sorter)
         want = O.predict_sparse(index, leaves, [10, 50, 90])
         assert_array_equal(_layout.decode_predict(flat, start, count, [10, 50, 90]), want)
+
+
+def test_load_refuses_another_packed_layout(tmp_path):
+    g = _golden.load("c1_rfqr_boston")
+    flat = _golden.flat_from_golden(g)
+    p = str(tmp_path / "forest.npz")
+    flat.save(p)
+    z = dict(np.load(p))
+    z.pop("layout")                                   # a file written before the layout was versioned
+    old = str(tmp_path / "old.npz")
+    np.savez(old, **z)
+    with pytest.raises(ValueError, match="layout"):
+        sg.FlatForest.load(old)
