@@ -64,7 +64,7 @@ constexpr int kApplyThreads = 256;
 constexpr int kApplyLevels = 2;                         // visits per chain between two warp votes (default)
 
 template <int ILP, int EMIT, int LEVELS = kApplyLevels>
-__global__ void __launch_bounds__(kApplyThreads)
+__global__ void __launch_bounds__(kApplyThreads, ILP <= 4 ? 8 : 1)
 apply_kernel(const ApplyParams p, void* __restrict__ out) {
     extern __shared__ float xt[];                       // [F][ROWS]
     __shared__ uint64_t s_nodes;
