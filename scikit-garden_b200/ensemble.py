@@ -140,14 +140,16 @@ class _BaseForestQuantileRegressor(RegressorMixin, BaseEstimator):
         self._dense_attrs = None
 
     # -- fitted attributes of the reference, materialised on demand --------------------
-    def _dense_fit_attributes(self):
+    def _dense_fit_attributes(self, trees=None):
         """(T,N) ``y_train_leaves_`` int32 / ``y_weights_`` float32 (ensemble.py:84-101),
-        rebuilt from the member lists (out-of-bag: -1 / 0)."""
-        if getattr(self, "_dense_attrs", None) is None:
+        rebuilt from the member lists (out-of-bag: -1 / 0).  ``trees``: only these rows
+        (not cached)."""
+        if trees is not None or getattr(self, "_dense_attrs", None) is None:
             fl = self._check_fitted()
-            leaves = -np.ones((fl.n_trees, fl.n_train), dtype=np.int32)
-            weights = np.zeros((fl.n_trees, fl.n_train), dtype=np.float32)
-            for t in range(fl.n_trees):
+            which = range(fl.n_trees) if trees is None else list(trees)
+            leaves = -np.ones((len(which), fl.n_train), dtype=np.int32)
+            weights = np.zeros((len(which), fl.n_train), dtype=np.float32)
+            for row, t in enumerate(which):
                 n0, n1 = fl.tree_offsets[t], fl.tree_offsets[t + 1]
                 m0, m1 = fl.member_offsets[t], fl.member_offsets[t + 1]
                 nd = fl.nodes[n0:n1]
@@ -162,8 +164,10 @@ class _BaseForestQuantileRegressor(RegressorMixin, BaseEstimator):
                        else fl.node_ids[n0:n1])[is_leaf]
                 mem = fl.members[m0:m1]
                 sample = fl.sorter[(mem & np.uint64(0xFFFFFFFF)).astype(np.int64)]
-                leaves[t, sample] = np.repeat(ids, cnt)
-                weights[t, sample] = (mem >> np.uint64(32)).astype(np.uint32).view(np.float32)
+                leaves[row, sample] = np.repeat(ids, cnt)
+                weights[row, sample] = (mem >> np.uint64(32)).astype(np.uint32).view(np.float32)
+            if trees is not None:
+                return leaves, weights
             self._dense_attrs = (leaves, weights)
         return self._dense_attrs
 

@@ -75,7 +75,13 @@ class FlatForest:
 
     # -- on-disk format: a plain .npz of the arrays above
     def save(self, path: str) -> None:
-        np.savez(path, layout=LAYOUT_VERSION, n_trees=self.n_trees, n_features=self.n_features,
+        # through an open handle: np.savez(str) would append ".npz" to a path without it and
+        # load(path) with the same string would then fail
+        with open(path, "wb") as fh:
+            self._savez(fh)
+
+    def _savez(self, fh) -> None:
+        np.savez(fh, layout=LAYOUT_VERSION, n_trees=self.n_trees, n_features=self.n_features,
                  feature_bits=self.feature_bits, n_train=self.n_train, nodes=self.nodes,
                  tree_offsets=self.tree_offsets,
                  node_ids=np.zeros(0, np.int32) if self.node_ids is None else self.node_ids,

@@ -12,7 +12,7 @@ import numpy as np
 from .flatten import FlatForest
 
 _ARRAYS = ["nodes", "tree_offsets", "node_ids", "members", "member_offsets", "y_sorted",
-           "leaf_values", "sorter"]
+           "leaf_values", "sorter", "leaf_impurity"]
 _SCALARS = ["n_trees", "n_features", "feature_bits", "n_train", "max_row_members",
             "expected_row_members", "max_depth"]
 
@@ -59,4 +59,5 @@ def broadcast_flat(flat, rank: int, device, src: int = 0) -> FlatForest:
         return flat
     return FlatForest(nodes=out["nodes"], tree_offsets=out["tree_offsets"], node_ids=out["node_ids"],
                       members=out["members"], member_offsets=out["member_offsets"], y_sorted=out["y_sorted"],
-                      leaf_values=out["leaf_values"], sorter=out["sorter"], **meta["scalars"])
+                      leaf_values=out["leaf_values"], sorter=out["sorter"],
+                      leaf_impurity=out["leaf_impurity"], **meta["scalars"])
