@@ -229,6 +229,12 @@ int qf_forest_predict_quantiles_host(qf_forest* f, const float* X_host, int64_t 
  * walked in locality order (0/1), 0}. */
 int qf_forest_plan(const qf_forest* f, int64_t n_rows, int32_t* out);
 
+/* Name of the weight+percentile kernel that takes the bulk of the rows of a call over n_rows
+ * rows with n_quantiles percentiles in `mode` (for bench accounting: the roofline line names the
+ * kernel it measured).  May build the compact leaf lists of QF_MODE_FAST as a side effect. */
+int qf_forest_quantile_kernel_name(qf_forest* f, int64_t n_rows, int32_t n_quantiles, int32_t mode,
+                                   char* buf, int32_t len);
+
 /* Per-call counters of the most recent predict/apply call on this handle (for bench
  * accounting): number of kernel launches issued and rows that overflowed the
  * in-shared-memory path into the dense fallback (valid after the stream is synced). */
@@ -241,7 +247,7 @@ int qf_forest_last_launches(const qf_forest* f);
 int qf_forest_last_timings(qf_forest* f, double* apply_ms, double* quantile_ms);
 
 /* Tuning knobs (bench / tests): key in {"sort_rows", "apply_row_warps", "apply_ilp",
- * "apply_levels", "rows_per_chunk", "cta_capacity", "cta2_capacity", "warp_elems", "warp_unit", "select_bits", "select_impl", "dense_ctas",
+ * "apply_levels", "rows_per_chunk", "cta_capacity", "cta2_capacity", "warp_elems", "warp_unit", "select_bits", "select_impl", "select3_capw", "dense_ctas",
  * "profile"}.
  * Returns QF_ERR_INVALID for unknown keys or values. */
 int qf_forest_set_option(qf_forest* f, const char* key, int64_t value);

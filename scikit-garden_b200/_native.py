@@ -75,6 +75,7 @@ SIGNATURES = {
     "qf_forest_predict_mean_std": (C.c_int, [_P, _P, _I64, _I64, C.c_double, _P, _P, _P, _I64, _P]),
     "qf_forest_predict_quantiles_host": (C.c_int, [_P, _P, _I64, _I64, _P, _I32, _P, _I32, _I64]),
     "qf_forest_plan": (C.c_int, [_P, _I64, _P]),
+    "qf_forest_quantile_kernel_name": (C.c_int, [_P, _I64, _I32, _I32, C.c_char_p, _I32]),
     "qf_forest_last_launches": (C.c_int, [_P]),
     "qf_forest_last_timings": (C.c_int, [_P, _P, _P]),
     "qf_forest_set_option": (C.c_int, [_P, C.c_char_p, _I64]),

@@ -53,12 +53,16 @@ struct ApplyParams {
     int F;
     int fbits;
     int row_warps;                         // warps along rows per CTA (block = 256 threads)
+    int64_t ld_out;                        // APPLY_EMIT_COMPACT: row stride (in words) of the tree-major output
 };
 
 // what a finished walk writes
 //   SEGMENT: uint2 out[pos][T]   (member start, member count), pos = position in the locality order
 //   NODE   : int32 out[row][T]   packed node index of the leaf, row = row of X
-enum { APPLY_EMIT_SEGMENT = 0, APPLY_EMIT_NODE = 1 };
+//   COMPACT: uint32 out[T][ld_out]  lo32 of the leaf node (the compact list word when the walk runs on
+//            the compact copy of the nodes, compact_lists.cuh), TREE-major: lane == row, so a warp
+//            writes 128 contiguous bytes per tree instead of 32 scattered sectors
+enum { APPLY_EMIT_SEGMENT = 0, APPLY_EMIT_NODE = 1, APPLY_EMIT_COMPACT = 2 };
 
 constexpr int kApplyThreads = 256;
 constexpr int kApplyLevels = 2;                         // visits per chain between two warp votes (default)
@@ -77,18 +81,34 @@ apply_kernel(const ApplyParams p, void* __restrict__ out) {
     const int tree_warps = (kApplyThreads / 32) / p.row_warps;
     const int64_t pos0 = static_cast<int64_t>(blockIdx.x) * rows_per_cta;
 
-    // stage the row tile transposed (threads sweep a row's features: coalesced per row)
-    const int tile = rows_per_cta * p.F;
+    // stage the row tile transposed (threads sweep a row's features: coalesced per row).  Rows
+    // whose length and stride are multiples of four (two) floats go through 128-bit (64-bit)
+    // loads: 80-, 200- and 256-byte rows of configs 2, 3 and 5
+    const bool al16 = ((p.F | p.ldx) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.X) & 15) == 0;
+    const bool al8 = ((p.F | p.ldx) & 1) == 0 && (reinterpret_cast<uintptr_t>(p.X) & 7) == 0;
+    const int vec = al16 ? 4 : (al8 ? 2 : 1);           // floats per load (block-uniform)
+    const int fv = p.F / vec;
+    const int tile = rows_per_cta * fv;
     for (int i = threadIdx.x; i < tile; i += kApplyThreads) {
-        const int r = i / p.F;
-        const int f = i - r * p.F;
+        const int r = i / fv;
+        const int f = (i - r * fv) * vec;
         const int64_t pos = pos0 + r;
-        float v = 0.0f;
+        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         if (pos < p.n) {
             const int64_t row = p.order ? static_cast<int64_t>(__ldg(p.order + pos)) : pos;
-            v = __ldg(p.X + row * p.ldx + f);
+            const float* __restrict__ src = p.X + row * p.ldx + f;
+            if (vec == 4) {
+                v = __ldg(reinterpret_cast<const float4*>(src));
+            } else if (vec == 2) {
+                const float2 u = __ldg(reinterpret_cast<const float2*>(src));
+                v.x = u.x; v.y = u.y;
+            } else {
+                v.x = __ldg(src);
+            }
         }
-        xt[f * rows_per_cta + r] = v;
+        xt[f * rows_per_cta + r] = v.x;
+        if (vec >= 2) xt[(f + 1) * rows_per_cta + r] = v.y;
+        if (vec == 4) { xt[(f + 2) * rows_per_cta + r] = v.z; xt[(f + 3) * rows_per_cta + r] = v.w; }
     }
     __syncthreads();
 
@@ -100,7 +120,7 @@ apply_kernel(const ApplyParams p, void* __restrict__ out) {
     const int64_t pos = pos0 + r;
     const bool row_ok = pos < p.n;                      // lanes past the end walk a zero row and write nothing
     int64_t out_row = pos;
-    if (EMIT != APPLY_EMIT_SEGMENT && row_ok && p.order) out_row = __ldg(p.order + pos);
+    if (EMIT == APPLY_EMIT_NODE && row_ok && p.order) out_row = __ldg(p.order + pos);
     // shared-memory byte address of this lane's column of the tile; feature f is at
     // xcol_s + f * 4 * rows_per_cta (32-bit address arithmetic, ld.shared)
     const uint32_t xcol_s = static_cast<uint32_t>(__cvta_generic_to_shared(xt + r));
@@ -168,6 +188,8 @@ apply_kernel(const ApplyParams p, void* __restrict__ out) {
                     if (EMIT == APPLY_EMIT_SEGMENT)
                         static_cast<uint2*>(out)[out_row * p.T + tree[k]] =
                             make_uint2(nd[k].x, nd[k].y & 0x7fffffffu);
+                    else if (EMIT == APPLY_EMIT_COMPACT)
+                        static_cast<uint32_t*>(out)[static_cast<int64_t>(tree[k]) * p.ld_out + out_row] = nd[k].x;
                     else
                         static_cast<int32_t*>(out)[out_row * p.T + tree[k]] = static_cast<int32_t>(node[k]);
                 }

@@ -5,6 +5,7 @@
 #include <climits>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -15,6 +16,8 @@
 #include "quantile_kernel.cuh"
 #include "select_kernel.cuh"
 #include "select2_kernel.cuh"
+#include "compact_lists.cuh"
+#include "select3_kernel.cuh"
 #include "csr_builder.cuh"
 
 namespace qf {
@@ -86,56 +89,90 @@ struct qf_forest {
     int64_t rows_per_chunk = 262144;    // rows per kernel chunk (denser chunks = closer neighbours in the locality order: C3-quarter K1 2.66 -> 2.52 ms against 131072)
     int cta_capacity = 0;         // cap on the members per row of the first bucket stage (0 = its capacity)
     int select_bits = qf::kSelectL2Bits;   // log2 refinement slots of the selection kernel (tests lower it)
-    int select_impl = 0;                   // 0: single-refinement kernel when the training set allows; 1: always the multi-level one
+    int select3_capw = 0;                  // octets per warp segment of the select3 stage (0 = auto; tests shrink it)
+    int select_impl = 0;                   // 0: auto (select3 on compact lists, else select2, else multi-level); 1: always the
+                                           // multi-level kernel; 2: select2 (8-byte members) when the training set allows
     int cta2_capacity = 8192;     // same for the 512-thread overflow stage (0 = stage not used)
     int warp_elems = -1;          // warp kernel: keys per lane (2, 4, 8), 0 = never, -1 = auto
     int warp_unit = 1;            // 0: never take the one-member-per-leaf gather of the warp kernel
     int dense_ctas = 0;           // 0 = auto
-    // counters
-    int launches = 0;
+    // compact leaf lists (compact_lists.cuh), built on the first QF_MODE_FAST call that can use them
+    std::mutex compact_mu;
+    int compact_state = 0;                 // 0: not tried, 1: ready, -1: this forest is not compactable
+    uint2* d_nodes_c = nullptr;            // copy of d_nodes whose leaves carry the compact list word
+    uint4* d_lists = nullptr;              // two uint4 per octet
+    int64_t n_octets = 0;
+    std::vector<double> tree_octets;       // octets a row expects to read from every tree
+    // The handle may be used from several host threads at once (one stream / workspace per
+    // thread): everything a call mutates lives in its CallStats and is published under `mu` when
+    // the call returns; calls that share the host pipeline or the event pool serialise on a mutex.
+    struct Span { int kind; cudaEvent_t a, b; };
+    struct CallStats {
+        int launches = 0;
+        std::vector<Span> spans;
+    };
+    std::mutex mu;                         // guards `last` and the event pool
+    CallStats last;                        // counters / event spans of the most recent call
+    std::mutex pipe_mu;                    // qf_forest_predict_quantiles_host: one call at a time per handle
     HostPipe pipe;
-    // per-kernel CUDA-event timing of the most recent call (option "profile")
+    // per-kernel CUDA-event timing of the most recent call (option "profile"; calls then serialise on prof_mu)
     int profile = 0;
+    std::mutex prof_mu;
     std::vector<cudaEvent_t> event_pool;
     size_t events_used = 0;
-    struct Span { int kind; cudaEvent_t a, b; };
-    std::vector<Span> spans;
 };
 
 namespace {
 
 enum { SPAN_APPLY = 0, SPAN_QUANTILE = 1, SPAN_OTHER = 2 };
 
+using CallStats = qf_forest::CallStats;
+
+// One per entry-point call: its counters, and (profiling on) the lock that keeps the event pool
+// to one call at a time.  The destructor publishes the counters as the handle's "last call".
+struct CallScope {
+    qf_forest* f;
+    CallStats cs;
+    std::unique_lock<std::mutex> prof;
+    explicit CallScope(qf_forest* f_) : f(f_) {
+        if (f->profile) {
+            prof = std::unique_lock<std::mutex>(f->prof_mu);
+            std::lock_guard<std::mutex> g(f->mu);
+            f->events_used = 0;
+        }
+    }
+    ~CallScope() {
+        std::lock_guard<std::mutex> g(f->mu);
+        f->last = std::move(cs);
+    }
+};
+
 // RAII: records an event pair around a launch when profiling is on
 struct SpanTimer {
-    qf_forest* f;
     cudaStream_t st;
     cudaEvent_t b = nullptr;
-    SpanTimer(qf_forest* f_, int kind, cudaStream_t st_) : f(f_), st(st_) {
+    SpanTimer(qf_forest* f, CallStats& cs, int kind, cudaStream_t st_) : st(st_) {
         if (!f->profile) return;
         cudaEvent_t ev[2];
-        for (cudaEvent_t& e : ev) {
-            if (f->events_used == f->event_pool.size()) {
-                cudaEvent_t n;
-                if (cudaEventCreate(&n) != cudaSuccess) return;
-                f->event_pool.push_back(n);
+        {
+            std::lock_guard<std::mutex> g(f->mu);
+            for (cudaEvent_t& e : ev) {
+                if (f->events_used == f->event_pool.size()) {
+                    cudaEvent_t n;
+                    if (cudaEventCreate(&n) != cudaSuccess) return;
+                    f->event_pool.push_back(n);
+                }
+                e = f->event_pool[f->events_used++];
             }
-            e = f->event_pool[f->events_used++];
         }
         cudaEventRecord(ev[0], st);
         b = ev[1];
-        f->spans.push_back({kind, ev[0], ev[1]});
+        cs.spans.push_back({kind, ev[0], ev[1]});
     }
     ~SpanTimer() {
         if (b) cudaEventRecord(b, st);
     }
 };
-
-void reset_call_counters(qf_forest* f) {
-    f->launches = 0;
-    f->events_used = 0;
-    f->spans.clear();
-}
 
 // Which kernels a call runs, and how the caller's workspace is carved up for one chunk.
 // The weight+percentile kernels form a chain; a row that does not fit a stage is appended
@@ -155,9 +192,10 @@ struct Plan {
 
 constexpr int kMaxBucketThreads = 512;
 
-Plan make_plan(const qf_forest* f, int64_t n_rows) {
+Plan make_plan(const qf_forest* f, int64_t n_rows, int64_t rows_per_chunk = 0) {
     Plan pl;
-    pl.chunk_rows = std::max<int64_t>(1, std::min<int64_t>(n_rows, f->rows_per_chunk));
+    if (rows_per_chunk <= 0) rows_per_chunk = f->rows_per_chunk;
+    pl.chunk_rows = std::max<int64_t>(1, std::min<int64_t>(n_rows, rows_per_chunk));
     const int64_t max_members = std::max<int64_t>(f->max_row_members, 1);
     const double typical = std::max(1.0, f->expected_row_members) * 1.25;
     // warp kernel: ranks must fit 32 - log2(32*E) bits, and the typical row must fit 32*E
@@ -195,7 +233,9 @@ Plan make_plan(const qf_forest* f, int64_t n_rows) {
         pl.dense_ctas = static_cast<int>(std::min<int64_t>(g, pl.chunk_rows));
     }
     int64_t o = 0;
-    pl.off_seg = o;    o += align_up(pl.chunk_rows * f->T * 8);
+    // K1 output: (start, count) pairs row-major, or one 32-bit list word per (tree, row) tree-major
+    // with rows padded to a multiple of four (select3)
+    pl.off_seg = o;    o += align_up(std::max<int64_t>(pl.chunk_rows * f->T * 8, ((pl.chunk_rows + 3) & ~int64_t(3)) * f->T * 4));
     pl.off_counts = o; o += kAlign;                               // one int counter per overflow list
     for (int k = 0; k < 3; ++k) { pl.off_rows[k] = o; o += align_up(pl.chunk_rows * 4); }
     // locality order is worth its three small launches once there are enough rows for
@@ -231,10 +271,11 @@ int set_smem(Kernel kernel, size_t smem) {
 // One launch of the leaf-lookup kernel over trees [t_begin, t_end).  `order` (device,
 // nullable) is the locality order of the rows.
 template <int EMIT>
-int launch_apply(qf_forest* f, const float* X, int64_t n, int64_t ldx, void* out, const int* order,
-                 int t_begin, int t_end, cudaStream_t st) {
+int launch_apply(qf_forest* f, CallStats& cs, const float* X, int64_t n, int64_t ldx, void* out, const int* order,
+                 int t_begin, int t_end, cudaStream_t st, int64_t ld_out = 0) {
     qf::ApplyParams ap;
-    ap.nodes = f->d_nodes;
+    ap.nodes = EMIT == qf::APPLY_EMIT_COMPACT ? f->d_nodes_c : f->d_nodes;
+    ap.ld_out = ld_out;
     ap.roots = f->d_roots;
     ap.X = X;
     ap.order = order;
@@ -258,11 +299,11 @@ int launch_apply(qf_forest* f, const float* X, int64_t n, int64_t ldx, void* out
         int rc = set_smem(kernel, smem);
         if (rc != QF_OK) return rc;
         {
-            SpanTimer span(f, SPAN_APPLY, st);
+            SpanTimer span(f, cs, SPAN_APPLY, st);
             kernel<<<static_cast<unsigned>(grid), qf::kApplyThreads, smem, st>>>(ap, out);
         }
         QF_CUDA_TRY(cudaGetLastError());
-        ++f->launches;
+        ++cs.launches;
         return QF_OK;
     };
     if (f->apply_ilp == 4 && f->apply_levels != qf::kApplyLevels) {
@@ -284,7 +325,7 @@ int launch_apply(qf_forest* f, const float* X, int64_t n, int64_t ldx, void* out
 // Locality order of one chunk of rows (apply_kernel.cuh): bucket every row by its leaf in
 // tree 0, exclusive scan of the bucket populations, scatter.  Returns the device order
 // array, or nullptr when the plan does not sort.
-int build_locality_order(qf_forest* f, const float* X, int64_t n, int64_t ldx, const Plan& pl,
+int build_locality_order(qf_forest* f, CallStats& cs, const float* X, int64_t n, int64_t ldx, const Plan& pl,
                          unsigned char* base, cudaStream_t st, const int** order_out) {
     *order_out = nullptr;
     if (!pl.sort_rows) return QF_OK;
@@ -293,22 +334,22 @@ int build_locality_order(qf_forest* f, const float* X, int64_t n, int64_t ldx, c
     int* hist = reinterpret_cast<int*>(base + pl.off_hist);
     QF_CUDA_TRY(cudaMemsetAsync(hist, 0, qf::kKeyBins * sizeof(int), st));
     {
-        SpanTimer span(f, SPAN_OTHER, st);
+        SpanTimer span(f, cs, SPAN_OTHER, st);
         qf::locality_key_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(
             f->d_nodes, f->root0, X, ldx, n, f->fbits, f->key_shift, f->key_bins, bucket, hist);
     }
     QF_CUDA_TRY(cudaGetLastError());
     {
-        SpanTimer span(f, SPAN_OTHER, st);
+        SpanTimer span(f, cs, SPAN_OTHER, st);
         qf::exclusive_scan_kernel<<<1, qf::kScanThreads, 0, st>>>(hist);
     }
     QF_CUDA_TRY(cudaGetLastError());
     {
-        SpanTimer span(f, SPAN_OTHER, st);
+        SpanTimer span(f, cs, SPAN_OTHER, st);
         qf::order_scatter_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(bucket, n, hist, order);
     }
     QF_CUDA_TRY(cudaGetLastError());
-    f->launches += 3;
+    cs.launches += 3;
     *order_out = order;
     return QF_OK;
 }
@@ -364,7 +405,7 @@ int launch_select_kernel(const qf_forest* f, unsigned grid, const qf::QuantilePa
     int nbits = 0;                                      // ranks are < 2^nbits
     while ((int64_t(1) << nbits) < f->N) ++nbits;
     // training sets of up to 2M samples: one refinement level is enough (select2_kernel.cuh)
-    if (f->select_impl == 0 && f->select_bits == qf::kSelectL2Bits && nbits <= 12 + qf::kSelect2SlotBits &&
+    if (f->select_impl != 1 && f->select_bits == qf::kSelectL2Bits && nbits <= 12 + qf::kSelect2SlotBits &&
         f->T <= qf::kSelect2MaxIPT * qf::kSelect2Threads && f->n_members < (int64_t(1) << 31) &&
         static_cast<int>(f->tree_max_leaf.size()) == f->T) {
         // pair-table segment of every warp: its leaves are 32 * ipt consecutive trees, a leaf of c
@@ -416,6 +457,137 @@ int launch_select_kernel(const qf_forest* f, unsigned grid, const qf::QuantilePa
     return threads == 128 ? run(qf::quantile_select_kernel<128>) : run(qf::quantile_select_kernel<256>);
 }
 
+// Compact leaf lists (compact_lists.cuh) for the select3 kernel, built once per forest on the
+// first call that can use them.  Synchronous (cudaMalloc + a handful of launches on the legacy
+// stream); returns with f->compact_state = 1 (ready) or -1 (forest not compactable: the 8-byte
+// kernels stay in charge).
+int ensure_compact(qf_forest* f) {
+    std::lock_guard<std::mutex> guard(f->compact_mu);
+    if (f->compact_state != 0) return QF_OK;
+    f->compact_state = -1;
+    if (f->N > (int64_t(1) << 24) || f->n_members <= 0) return QF_OK;     // ranks live in 24 bits
+    struct Tmp {
+        void* p[4] = {};
+        ~Tmp() { for (void* q : p) cudaFree(q); }
+    } tmp;
+    const int64_t n_tiles = (f->n_members + qf::kCompactScanTile - 1) / qf::kCompactScanTile;
+    QF_CUDA_TRY(cudaMalloc(&tmp.p[0], static_cast<size_t>(f->n_members) * 4));          // octets per leaf -> first octet
+    QF_CUDA_TRY(cudaMalloc(&tmp.p[1], static_cast<size_t>(n_tiles + 1) * 8));           // tile sums + total
+    QF_CUDA_TRY(cudaMalloc(&tmp.p[2], 16));                                             // flags
+    QF_CUDA_TRY(cudaMalloc(&tmp.p[3], static_cast<size_t>(f->T) * 16));                 // per-tree stats
+    uint32_t* oct_at = static_cast<uint32_t*>(tmp.p[0]);
+    uint64_t* tile_sum = static_cast<uint64_t*>(tmp.p[1]);
+    int* flags = static_cast<int*>(tmp.p[2]);
+    unsigned long long* stats = static_cast<unsigned long long*>(tmp.p[3]);
+    QF_CUDA_TRY(cudaMemset(oct_at, 0, static_cast<size_t>(f->n_members) * 4));
+    QF_CUDA_TRY(cudaMemset(flags, 0, 16));
+    QF_CUDA_TRY(cudaMemset(stats, 0, static_cast<size_t>(f->T) * 16));
+    const unsigned node_blocks = static_cast<unsigned>((f->n_nodes + 255) / 256);
+    qf::compact_mark_kernel<<<node_blocks, 256>>>(f->d_nodes, f->n_nodes, f->d_members, oct_at, flags);
+    qf::scan_tile_sums_kernel<<<static_cast<unsigned>(n_tiles), 256>>>(oct_at, f->n_members, tile_sum);
+    qf::scan_tile_offsets_kernel<<<1, 1024>>>(tile_sum, n_tiles, tile_sum + n_tiles);
+    QF_CUDA_TRY(cudaGetLastError());
+    int h_flags = 0;
+    uint64_t n_octets = 0;
+    QF_CUDA_TRY(cudaMemcpy(&h_flags, flags, 4, cudaMemcpyDeviceToHost));
+    QF_CUDA_TRY(cudaMemcpy(&n_octets, tile_sum + n_tiles, 8, cudaMemcpyDeviceToHost));
+    if (h_flags != 0 || n_octets == 0 || n_octets > qf::kCompactOffMask) return QF_OK;   // not compactable
+    qf::scan_apply_kernel<<<static_cast<unsigned>(n_tiles), 256>>>(oct_at, f->n_members, tile_sum);
+    uint2* nodes_c = nullptr;
+    uint4* lists = nullptr;
+    cudaError_t e = cudaMalloc(&nodes_c, static_cast<size_t>(f->n_nodes) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&lists, static_cast<size_t>(n_octets) * 32);
+    if (e == cudaSuccess) {
+        qf::compact_fill_kernel<<<node_blocks, 256>>>(f->d_nodes, f->n_nodes, f->d_members, oct_at, nodes_c, lists);
+        qf::compact_tree_stats_kernel<<<f->T, 256>>>(f->d_nodes, f->d_roots, f->n_nodes, f->T, stats);
+        e = cudaGetLastError();
+    }
+    std::vector<unsigned long long> h_stats(static_cast<size_t>(f->T) * 2);
+    if (e == cudaSuccess) e = cudaMemcpy(h_stats.data(), stats, h_stats.size() * 8, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) {
+        cudaFree(nodes_c);
+        cudaFree(lists);
+        return qf::fail(QF_ERR_CUDA, std::string("compact leaf lists: ") + cudaGetErrorString(e));
+    }
+    f->tree_octets.assign(f->T, 1.0);
+    for (int t = 0; t < f->T; ++t)
+        if (h_stats[2 * t + 1]) f->tree_octets[t] = static_cast<double>(h_stats[2 * t]) / static_cast<double>(h_stats[2 * t + 1]);
+    f->d_nodes_c = nodes_c;
+    f->d_lists = lists;
+    f->n_octets = static_cast<int64_t>(n_octets);
+    f->device_bytes += f->n_nodes * 8 + static_cast<int64_t>(n_octets) * 32;
+    f->compact_state = 1;
+    return QF_OK;
+}
+
+// Geometry of the select3 kernel for this forest, or ok = false when it cannot take it (then
+// select2 / the multi-level kernel do).
+struct Select3Geometry {
+    bool ok = false;
+    int log2nb = 11, shift1 = 0, ipt = 1, capw = 0;
+    float fx_scale = 0.0f;
+    size_t smem = 0;
+};
+
+Select3Geometry select3_geometry(const qf_forest* f, int nq) {
+    Select3Geometry g;
+    if (f->select_impl != 0 || f->select_bits != qf::kSelectL2Bits || nq > qf::kSelect2QB) return g;
+    if (f->T > qf::kSelect3MaxIPT * qf::kSelect3Threads) return g;
+    int k = 0;                                          // weights of a row sum to <= bound < 2^k
+    const int64_t bound = std::max<int64_t>(f->T, f->row_weight_bound);
+    while ((int64_t(1) << k) < bound + 1) ++k;
+    if (k > 20) return g;
+    int nbits = 0;                                      // ranks are < 2^nbits
+    while ((int64_t(1) << nbits) < f->N) ++nbits;
+    if (nbits > 12 + qf::kSelect2SlotBits) return g;
+    g.fx_scale = static_cast<float>(int64_t(1) << (31 - k));
+    g.log2nb = nbits <= 11 + qf::kSelect2SlotBits ? 11 : 12;
+    g.shift1 = std::max(0, nbits - g.log2nb);
+    g.ipt = (f->T + qf::kSelect3Threads - 1) / qf::kSelect3Threads;
+    if (g.ipt == 3) g.ipt = 4;
+    return g;
+}
+
+// stage capacity per warp: 1.25 x the octets the busiest warp expects + 8, a multiple of 4
+bool select3_finish_geometry(const qf_forest* f, Select3Geometry& g) {
+    if (f->compact_state != 1 || static_cast<int>(f->tree_octets.size()) != f->T) return false;
+    double busiest = 0.0;
+    for (int w = 0; w < qf::kSelect3Warps; ++w) {
+        double e = 0.0;
+        for (int i = 0; i < g.ipt; ++i)
+            for (int l = 0; l < 32; ++l) {
+                const int t = w * 32 + l + i * qf::kSelect3Threads;
+                if (t < f->T) e += f->tree_octets[t];
+            }
+        busiest = std::max(busiest, e);
+    }
+    int capw = static_cast<int>(busiest * 1.25) + 8;
+    if (f->select3_capw > 0) capw = f->select3_capw;
+    capw = (capw + 3) & ~3;
+    g.capw = capw;
+    g.smem = qf::select3_kernel_smem(g.log2nb, g.shift1, capw);
+    // three CTAs per SM is what the kernel is tuned for; one oversized stage (big leaves) is not worth it
+    g.ok = g.smem <= 72 * 1024;
+    return g.ok;
+}
+
+int launch_select3_kernel(const qf_forest* f, const Select3Geometry& g, const qf::Select3Params& sp,
+                          const qf::QuantileList& ql, cudaStream_t st) {
+    const int64_t n_groups = (sp.n + qf::kSelect3RowGroup - 1) / qf::kSelect3RowGroup;
+    const unsigned grid = static_cast<unsigned>(std::min<int64_t>(n_groups, int64_t(f->sm_count) * qf::kSelect3CtasPerSm));
+    auto run = [&](auto kernel) -> int {
+        int rc = set_smem(kernel, g.smem);
+        if (rc != QF_OK) return rc;
+        kernel<<<grid, qf::kSelect3Threads, g.smem, st>>>(sp, ql);
+        return QF_OK;
+    };
+    if (g.log2nb == 11)
+        return g.ipt == 1 ? run(qf::quantile_select3_kernel<11, 1>)
+             : g.ipt == 2 ? run(qf::quantile_select3_kernel<11, 2>) : run(qf::quantile_select3_kernel<11, 4>);
+    return g.ipt == 1 ? run(qf::quantile_select3_kernel<12, 1>)
+         : g.ipt == 2 ? run(qf::quantile_select3_kernel<12, 2>) : run(qf::quantile_select3_kernel<12, 4>);
+}
+
 // QF_MODE_FAST adds weights as 32-bit fixed point with 2^(31-k) units per unit of weight
 // (2^k > total weight of a row).  A member of a leaf of L samples weighs about 1/L, i.e.
 // 2^(31-k) / L units: below ~2^14 units the rounding of each weight (the same direction for a
@@ -432,7 +604,7 @@ bool fast_mode_is_precise(const qf_forest* f) {
 
 // `pl` is the caller's carve-up of `ws` (made once for the largest chunk, so that the
 // zeroed dense scratch stays where the kernels expect it for every chunk).
-int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, const double* q_host,
+int quantiles_on_stream(qf_forest* f, CallStats& cs, const float* X, int64_t n, int64_t ldx, const double* q_host,
                         int nq, double* out, int mode, const Plan& pl, void* ws, int64_t ws_bytes,
                         cudaStream_t st) {
     // QF_MODE_FAST swaps the shared-memory sorting stages for histogram selection; the warp
@@ -446,12 +618,55 @@ int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, co
     int* lists[3];
     for (int k = 0; k < 3; ++k) lists[k] = reinterpret_cast<int*>(base + pl.off_rows[k]);
 
+    // QF_MODE_FAST on forests whose typical row is too large for the warp kernel: every row goes
+    // through the select3 kernel on compact leaf lists (one 32-bit list word per (tree, row) out of
+    // K1, tree-major)
+    Select3Geometry g3;
+    if (select && pl.warp_elems == 0) {
+        g3 = select3_geometry(f, nq);
+        if (g3.fx_scale > 0.0f) {
+            int rc = ensure_compact(f);
+            if (rc != QF_OK) return rc;
+            select3_finish_geometry(f, g3);
+        }
+    }
+    const int64_t ld3 = (pl.chunk_rows + 3) & ~int64_t(3);
+
     for (int64_t r0 = 0; r0 < n; r0 += pl.chunk_rows) {
         const int64_t rows = std::min(pl.chunk_rows, n - r0);
         const int* order = nullptr;
-        int rc = build_locality_order(f, X + r0 * ldx, rows, ldx, pl, base, st, &order);
+        int rc = build_locality_order(f, cs, X + r0 * ldx, rows, ldx, pl, base, st, &order);
         if (rc != QF_OK) return rc;
-        rc = launch_apply<qf::APPLY_EMIT_SEGMENT>(f, X + r0 * ldx, rows, ldx, seg, order, 0, f->T, st);
+        if (g3.ok) {
+            rc = launch_apply<qf::APPLY_EMIT_COMPACT>(f, cs, X + r0 * ldx, rows, ldx, seg, order, 0, f->T, st, ld3);
+            if (rc != QF_OK) return rc;
+            qf::QuantileList ql;
+            std::memset(&ql, 0, sizeof(ql));
+            for (int i = 0; i < nq; ++i) ql.q[i] = q_host[i];
+            qf::Select3Params sp;
+            sp.seg = reinterpret_cast<const uint32_t*>(seg);
+            sp.ld = ld3;
+            sp.order = order;
+            sp.lists = f->d_lists;
+            sp.y_sorted = f->d_y_sorted;
+            sp.out = out + r0 * nq;
+            sp.n = rows;
+            sp.ldo = nq;
+            sp.T = f->T;
+            sp.Q = nq;
+            sp.fx_scale = g3.fx_scale;
+            sp.shift1 = g3.shift1;
+            sp.capw = g3.capw;
+            {
+                SpanTimer span(f, cs, SPAN_QUANTILE, st);
+                rc = launch_select3_kernel(f, g3, sp, ql, st);
+            }
+            if (rc != QF_OK) return rc;
+            QF_CUDA_TRY(cudaGetLastError());
+            ++cs.launches;
+            continue;
+        }
+        rc = launch_apply<qf::APPLY_EMIT_SEGMENT>(f, cs, X + r0 * ldx, rows, ldx, seg, order, 0, f->T, st);
         if (rc != QF_OK) return rc;
         for (int q0 = 0; q0 < nq; q0 += qf::kMaxQuantilesPerLaunch) {
             const int qn = std::min(qf::kMaxQuantilesPerLaunch, nq - q0);
@@ -487,7 +702,7 @@ int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, co
                 const unsigned grid =
                     static_cast<unsigned>((rows + qf::kWarpKernelWarps - 1) / qf::kWarpKernelWarps);
                 {
-                    SpanTimer span(f, SPAN_QUANTILE, st);
+                    SpanTimer span(f, cs, SPAN_QUANTILE, st);
                     // unit_leaves (deep bootstrap trees, min_samples_leaf=1): member t of the row is
                     // the single member of its leaf in tree t -- no offsets to scan
                     const bool unit = f->unit_leaves && f->warp_unit != 0;
@@ -503,7 +718,7 @@ int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, co
                     }
                 }
                 QF_CUDA_TRY(cudaGetLastError());
-                ++f->launches;
+                ++cs.launches;
                 advance();
             }
             if (select && (pl.s1_threads || pl.dense_needed)) {   // every remaining row, any member count
@@ -511,12 +726,12 @@ int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, co
                 const unsigned grid = qp.row_list ? static_cast<unsigned>(std::min<int64_t>(rows, int64_t(f->sm_count) * 8))
                                                   : static_cast<unsigned>(rows);
                 {
-                    SpanTimer span(f, SPAN_QUANTILE, st);
+                    SpanTimer span(f, cs, SPAN_QUANTILE, st);
                     rc = launch_select_kernel(f, grid, qp, ql, st);
                 }
                 if (rc != QF_OK) return rc;
                 QF_CUDA_TRY(cudaGetLastError());
-                ++f->launches;
+                ++cs.launches;
                 continue;
             }
             const int bucket_threads[2] = {pl.s1_threads, pl.s2_limit ? kMaxBucketThreads : 0};
@@ -529,22 +744,22 @@ int quantiles_on_stream(qf_forest* f, const float* X, int64_t n, int64_t ldx, co
                 const unsigned grid = qp.row_list ? static_cast<unsigned>(std::min<int64_t>(rows, int64_t(f->sm_count) * 4))
                                                   : static_cast<unsigned>(rows);
                 {
-                    SpanTimer span(f, SPAN_QUANTILE, st);
+                    SpanTimer span(f, cs, SPAN_QUANTILE, st);
                     rc = launch_bucket_kernel(bucket_threads[b], grid, qp, ql, f->T, st);
                 }
                 if (rc != QF_OK) return rc;
                 QF_CUDA_TRY(cudaGetLastError());
-                ++f->launches;
+                ++cs.launches;
                 advance();
             }
             if (pl.dense_needed) {
                 chain();                                 // the dense kernel never overflows
                 {
-                    SpanTimer span(f, SPAN_QUANTILE, st);
+                    SpanTimer span(f, cs, SPAN_QUANTILE, st);
                     qf::quantile_dense_kernel<256><<<pl.dense_ctas, 256, 0, st>>>(qp, ql, base + pl.off_dense, f->N);
                 }
                 QF_CUDA_TRY(cudaGetLastError());
-                ++f->launches;
+                ++cs.launches;
             }
         }
     }
@@ -678,6 +893,8 @@ void qf_forest_destroy(qf_forest* f) {
     cudaFree(f->d_y_sorted);
     cudaFree(f->d_values);
     cudaFree(f->d_impurity);
+    cudaFree(f->d_nodes_c);
+    cudaFree(f->d_lists);
     for (cudaEvent_t e : f->event_pool) cudaEventDestroy(e);
     {
         HostPipe& hp = f->pipe;
@@ -718,13 +935,52 @@ int qf_forest_plan(const qf_forest* f, int64_t n_rows, int32_t* out) {
     return QF_OK;
 }
 
-int qf_forest_last_launches(const qf_forest* f) { return f ? f->launches : 0; }
+int qf_forest_quantile_kernel_name(qf_forest* f, int64_t n_rows, int32_t nq, int32_t mode, char* buf, int32_t len) {
+    if (!f || !buf || len <= 0 || n_rows < 0) return qf::fail(QF_ERR_INVALID, "qf_forest_quantile_kernel_name: bad argument");
+    const Plan pl = make_plan(f, n_rows);
+    char name[96];
+    const bool select = mode == QF_MODE_FAST && nq <= qf::kSelectMaxQ && fast_mode_is_precise(f);
+    if (pl.warp_elems) {
+        std::snprintf(name, sizeof(name), "quantile_warp_kernel<%d>", pl.warp_elems);
+    } else if (select) {
+        Select3Geometry g3 = select3_geometry(f, nq);
+        if (g3.fx_scale > 0.0f) {
+            DeviceGuard guard(f->device);
+            if (ensure_compact(f) == QF_OK) select3_finish_geometry(f, g3);
+        }
+        int nbits = 0;
+        while ((int64_t(1) << nbits) < f->N) ++nbits;
+        if (g3.ok)
+            std::snprintf(name, sizeof(name), "quantile_select3_kernel<%d, %d>", g3.log2nb, g3.ipt);
+        else if (f->select_impl != 1 && f->select_bits == qf::kSelectL2Bits && nbits <= 12 + qf::kSelect2SlotBits &&
+                 f->T <= qf::kSelect2MaxIPT * qf::kSelect2Threads)
+            std::snprintf(name, sizeof(name), "quantile_select2_kernel<%d>", nbits <= 11 + qf::kSelect2SlotBits ? 11 : 12);
+        else
+            std::snprintf(name, sizeof(name), "quantile_select_kernel<%d>", f->T <= 128 ? 128 : 256);
+    } else {
+        std::snprintf(name, sizeof(name), "quantile_bucket_kernel<%d>", pl.s1_threads);
+    }
+    std::snprintf(buf, static_cast<size_t>(len), "%s", name);
+    return QF_OK;
+}
+
+int qf_forest_last_launches(const qf_forest* f) {
+    if (!f) return 0;
+    qf_forest* m = const_cast<qf_forest*>(f);
+    std::lock_guard<std::mutex> g(m->mu);
+    return m->last.launches;
+}
 
 int qf_forest_last_timings(qf_forest* f, double* apply_ms, double* quantile_ms) {
     if (!f) return qf::fail(QF_ERR_INVALID, "qf_forest_last_timings: null forest");
     DeviceGuard guard(f->device);
     double acc[3] = {0.0, 0.0, 0.0};
-    for (const qf_forest::Span& s : f->spans) {
+    std::vector<qf_forest::Span> spans;
+    {
+        std::lock_guard<std::mutex> g(f->mu);
+        spans = f->last.spans;
+    }
+    for (const qf_forest::Span& s : spans) {
         QF_CUDA_TRY(cudaEventSynchronize(s.b));
         float ms = 0.0f;
         QF_CUDA_TRY(cudaEventElapsedTime(&ms, s.a, s.b));
@@ -765,12 +1021,15 @@ int qf_forest_set_option(qf_forest* f, const char* key, int64_t value) {
         if (value != 0 && value != 1) return qf::fail(QF_ERR_INVALID, "warp_unit must be 0 or 1");
         f->warp_unit = static_cast<int>(value);
     } else if (k == "select_impl") {
-        if (value != 0 && value != 1) return qf::fail(QF_ERR_INVALID, "select_impl must be 0 or 1");
+        if (value < 0 || value > 2) return qf::fail(QF_ERR_INVALID, "select_impl must be 0 (auto), 1 (multi-level) or 2 (select2)");
         f->select_impl = static_cast<int>(value);
     } else if (k == "select_bits") {
         if (value < 1 || value > qf::kSelectL2Bits)
             return qf::fail(QF_ERR_INVALID, "select_bits must be in [1, 10]");
         f->select_bits = static_cast<int>(value);
+    } else if (k == "select3_capw") {
+        if (value < 0 || value > 4096) return qf::fail(QF_ERR_INVALID, "select3_capw must be in [0, 4096]");
+        f->select3_capw = static_cast<int>(value);
     } else if (k == "warp_elems") {
         if (value != -1 && value != 0 && value != 2 && value != 4 && value != 8)
             return qf::fail(QF_ERR_INVALID, "warp_elems must be -1 (auto), 0 (off), 2, 4 or 8");
@@ -790,7 +1049,8 @@ int qf_forest_apply(qf_forest* f, const float* X, int64_t n, int64_t ldx, int64_
                     void* ws, int64_t ws_bytes, void* stream) {
     int rc = check_forest_call(f, X, n, ldx, leaves, "qf_forest_apply");
     if (rc != QF_OK) return rc;
-    reset_call_counters(f);
+    CallScope scope(f);
+    CallStats& cs = scope.cs;
     if (n == 0) return QF_OK;
     DeviceGuard guard(f->device);
     const Plan pl = make_plan(f, n);
@@ -800,16 +1060,16 @@ int qf_forest_apply(qf_forest* f, const float* X, int64_t n, int64_t ldx, int64_
     for (int64_t r0 = 0; r0 < n; r0 += pl.chunk_rows) {
         const int64_t rows = std::min(pl.chunk_rows, n - r0);
         const int* order = nullptr;
-        rc = build_locality_order(f, X + r0 * ldx, rows, ldx, pl, static_cast<unsigned char*>(ws), st, &order);
+        rc = build_locality_order(f, cs, X + r0 * ldx, rows, ldx, pl, static_cast<unsigned char*>(ws), st, &order);
         if (rc != QF_OK) return rc;
-        rc = launch_apply<qf::APPLY_EMIT_NODE>(f, X + r0 * ldx, rows, ldx, idx, order, 0, f->T, st);
+        rc = launch_apply<qf::APPLY_EMIT_NODE>(f, cs, X + r0 * ldx, rows, ldx, idx, order, 0, f->T, st);
         if (rc != QF_OK) return rc;
         const int64_t total = rows * f->T;
         const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, f->sm_count * 16));
         qf::node_to_sklearn_id_kernel<<<blocks, 256, 0, st>>>(idx, total, f->T, f->d_roots, f->d_node_ids,
                                                              leaves + r0 * f->T);
         QF_CUDA_TRY(cudaGetLastError());
-        ++f->launches;
+        ++cs.launches;
     }
     return QF_OK;
 }
@@ -820,7 +1080,8 @@ int qf_forest_predict_mean(qf_forest* f, const float* X, int64_t n, int64_t ldx,
     if (rc != QF_OK) return rc;
     if (!f->d_values)
         return qf::fail(QF_ERR_INVALID, "qf_forest_predict_mean: forest was created without leaf_values");
-    reset_call_counters(f);
+    CallScope scope(f);
+    CallStats& cs = scope.cs;
     if (n == 0) return QF_OK;
     DeviceGuard guard(f->device);
     const Plan pl = make_plan(f, n);
@@ -831,14 +1092,14 @@ int qf_forest_predict_mean(qf_forest* f, const float* X, int64_t n, int64_t ldx,
     for (int64_t r0 = 0; r0 < n; r0 += pl.chunk_rows) {
         const int64_t rows = std::min(pl.chunk_rows, n - r0);
         const int* order = nullptr;
-        rc = build_locality_order(f, X + r0 * ldx, rows, ldx, pl, static_cast<unsigned char*>(ws), st, &order);
+        rc = build_locality_order(f, cs, X + r0 * ldx, rows, ldx, pl, static_cast<unsigned char*>(ws), st, &order);
         if (rc != QF_OK) return rc;
-        rc = launch_apply<qf::APPLY_EMIT_NODE>(f, X + r0 * ldx, rows, ldx, idx, order, 0, f->T, st);
+        rc = launch_apply<qf::APPLY_EMIT_NODE>(f, cs, X + r0 * ldx, rows, ldx, idx, order, 0, f->T, st);
         if (rc != QF_OK) return rc;
         qf::mean_kernel<<<static_cast<unsigned>((rows + 127) / 128), 128, 0, st>>>(idx, rows, f->T, f->d_values,
                                                                                    out + r0);
         QF_CUDA_TRY(cudaGetLastError());
-        ++f->launches;
+        ++cs.launches;
     }
     return QF_OK;
 }
@@ -861,7 +1122,8 @@ int qf_forest_predict_mean_std(qf_forest* f, const float* X, int64_t n, int64_t 
     if (!std_out) return qf::fail(QF_ERR_INVALID, "qf_forest_predict_mean_std: null output");
     if (!f->d_values || !f->d_impurity)
         return qf::fail(QF_ERR_INVALID, "qf_forest_predict_mean_std: forest has no leaf_values / leaf impurities");
-    reset_call_counters(f);
+    CallScope scope(f);
+    CallStats& cs = scope.cs;
     if (n == 0) return QF_OK;
     DeviceGuard guard(f->device);
     const Plan pl = make_plan(f, n);
@@ -872,14 +1134,14 @@ int qf_forest_predict_mean_std(qf_forest* f, const float* X, int64_t n, int64_t 
     for (int64_t r0 = 0; r0 < n; r0 += pl.chunk_rows) {
         const int64_t rows = std::min(pl.chunk_rows, n - r0);
         const int* order = nullptr;
-        rc = build_locality_order(f, X + r0 * ldx, rows, ldx, pl, static_cast<unsigned char*>(ws), st, &order);
+        rc = build_locality_order(f, cs, X + r0 * ldx, rows, ldx, pl, static_cast<unsigned char*>(ws), st, &order);
         if (rc != QF_OK) return rc;
-        rc = launch_apply<qf::APPLY_EMIT_NODE>(f, X + r0 * ldx, rows, ldx, idx, order, 0, f->T, st);
+        rc = launch_apply<qf::APPLY_EMIT_NODE>(f, cs, X + r0 * ldx, rows, ldx, idx, order, 0, f->T, st);
         if (rc != QF_OK) return rc;
         qf::mean_std_kernel<<<static_cast<unsigned>((rows + 127) / 128), 128, 0, st>>>(
             idx, rows, f->T, f->d_values, f->d_impurity, min_variance, mean_out + r0, std_out + r0);
         QF_CUDA_TRY(cudaGetLastError());
-        ++f->launches;
+        ++cs.launches;
     }
     return QF_OK;
 }
@@ -891,7 +1153,8 @@ int qf_forest_predict_quantiles(qf_forest* f, const float* X, int64_t n, int64_t
     if (rc != QF_OK) return rc;
     rc = check_quantiles(q_host, nq, mode, "qf_forest_predict_quantiles");
     if (rc != QF_OK) return rc;
-    reset_call_counters(f);
+    CallScope scope(f);
+    CallStats& cs = scope.cs;
     if (n == 0) return QF_OK;
     DeviceGuard guard(f->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -900,7 +1163,7 @@ int qf_forest_predict_quantiles(qf_forest* f, const float* X, int64_t n, int64_t
         return qf::fail(QF_ERR_WORKSPACE, "qf_forest_predict_quantiles: workspace too small");
     rc = zero_dense_scratch(f, pl, ws, st);
     if (rc != QF_OK) return rc;
-    return quantiles_on_stream(f, X, n, ldx, q_host, nq, out, mode, pl, ws, ws_bytes, st);
+    return quantiles_on_stream(f, cs, X, n, ldx, q_host, nq, out, mode, pl, ws, ws_bytes, st);
 }
 
 int qf_forest_predict_quantiles_host(qf_forest* f, const float* X_host, int64_t n, int64_t ldx,
@@ -910,7 +1173,8 @@ int qf_forest_predict_quantiles_host(qf_forest* f, const float* X_host, int64_t 
     if (rc != QF_OK) return rc;
     rc = check_quantiles(q_host, nq, mode, "qf_forest_predict_quantiles_host");
     if (rc != QF_OK) return rc;
-    reset_call_counters(f);
+    CallScope scope(f);
+    CallStats& cs = scope.cs;
     if (n == 0) return QF_OK;
     DeviceGuard guard(f->device);
     // measured at 100k x 20 rows: splitting below rows_per_chunk only adds per-chunk launches
@@ -918,10 +1182,8 @@ int qf_forest_predict_quantiles_host(qf_forest* f, const float* X_host, int64_t 
     // neighbouring chunks once there are several full-size chunks
     if (chunk_rows <= 0) chunk_rows = f->rows_per_chunk;
     chunk_rows = std::min(chunk_rows, n);
-    const int64_t saved_chunk = f->rows_per_chunk;
-    f->rows_per_chunk = chunk_rows;                       // one kernel chunk per pipeline slot
-    const Plan pl = make_plan(f, chunk_rows);
-    f->rows_per_chunk = saved_chunk;
+    const Plan pl = make_plan(f, chunk_rows, chunk_rows);  // one kernel chunk per pipeline slot
+    std::lock_guard<std::mutex> pipe_guard(f->pipe_mu);    // the pipeline buffers are per handle
     const int64_t x_bytes = chunk_rows * f->F * 4, out_bytes = chunk_rows * nq * 8;
     HostPipe& hp = f->pipe;
     if (!hp.h2d) {
@@ -952,7 +1214,6 @@ int qf_forest_predict_quantiles_host(qf_forest* f, const float* X_host, int64_t 
     }
     rc = zero_dense_scratch(f, pl, hp.ws, hp.compute);
     if (rc != QF_OK) return rc;
-    int total_launches = 0;
     int64_t chunk = 0;
     for (int64_t r0 = 0; r0 < n; r0 += chunk_rows, ++chunk) {
         const int64_t rows = std::min(chunk_rows, n - r0);
@@ -970,10 +1231,8 @@ int qf_forest_predict_quantiles_host(qf_forest* f, const float* X_host, int64_t 
         // kernels: one stream, chunk after chunk
         QF_CUDA_TRY(cudaStreamWaitEvent(hp.compute, hp.x_ready[s], 0));
         if (chunk >= kPipeSlots) QF_CUDA_TRY(cudaStreamWaitEvent(hp.compute, hp.out_free[s], 0));
-        f->launches = 0;
-        rc = quantiles_on_stream(f, hp.x[s], rows, f->F, q_host, nq, hp.out[s], mode, pl, hp.ws, hp.ws_bytes, hp.compute);
+        rc = quantiles_on_stream(f, cs, hp.x[s], rows, f->F, q_host, nq, hp.out[s], mode, pl, hp.ws, hp.ws_bytes, hp.compute);
         if (rc != QF_OK) return rc;
-        total_launches += f->launches;
         QF_CUDA_TRY(cudaEventRecord(hp.computed[s], hp.compute));
         // D2H
         QF_CUDA_TRY(cudaStreamWaitEvent(hp.d2h, hp.computed[s], 0));
@@ -982,7 +1241,6 @@ int qf_forest_predict_quantiles_host(qf_forest* f, const float* X_host, int64_t 
     }
     QF_CUDA_TRY(cudaStreamSynchronize(hp.d2h));
     QF_CUDA_TRY(cudaStreamSynchronize(hp.compute));
-    f->launches = total_launches;
     return QF_OK;
 }
 
@@ -1065,11 +1323,12 @@ int qf_build_csr(const qf_csr_build_desc* d, int64_t* n_members_out) {
 
     cudaStream_t st = nullptr;
     int rc = QF_OK;
+    CallStats build_stats;
     // tree.py:101 for every tree: leaf of every training row (rows in their own order)
     const int64_t chunk = 131072;
     for (int64_t r0 = 0; r0 < N && rc == QF_OK; r0 += chunk) {
         const int64_t rows = std::min(chunk, N - r0);
-        rc = launch_apply<qf::APPLY_EMIT_NODE>(&f, d->X_train_dev + r0 * d->n_features, rows, d->n_features,
+        rc = launch_apply<qf::APPLY_EMIT_NODE>(&f, build_stats, d->X_train_dev + r0 * d->n_features, rows, d->n_features,
                                                 d_idx + r0 * T, nullptr, 0, T, st);
     }
     f.d_nodes = nullptr;                                 // not owned

@@ -101,21 +101,10 @@ class DeviceForest:
         return dict(zip(keys, [int(v) for v in vals]))
 
     def quantile_kernel_name(self, n_rows: int, n_q: int, mode: int) -> str:
-        """Name of the weight+percentile kernel that takes the bulk of the rows of a call
-        (mirrors the stage selection of quantiles_on_stream in csrc/qforest_abi.cu)."""
-        plan = self.plan(n_rows)
-        if plan["warp_elems"]:
-            return "quantile_warp_kernel<%d>" % plan["warp_elems"]
-        if mode == _native.QF_MODE_FAST and n_q <= 16:
-            name = (C.c_char * 64)()
-            if hasattr(self._lib, "qf_forest_select_kernel_name"):
-                self._lib.qf_forest_select_kernel_name(self._h, int(n_q), name, 64)
-                return name.value.decode()
-            nbits = max(1, int(self.flat_meta["n_train"] - 1).bit_length())
-            if nbits <= 21 and self.n_trees <= 1024:
-                return "quantile_select2_kernel<%d>" % (11 if nbits <= 20 else 12)
-            return "quantile_select_kernel<%d>" % plan["s1_threads"]
-        return "quantile_bucket_kernel<%d>" % plan["s1_threads"]
+        """Name of the weight+percentile kernel that takes the bulk of the rows of a call."""
+        buf = C.create_string_buffer(96)
+        _native.check(self._lib.qf_forest_quantile_kernel_name(self._h, int(n_rows), int(n_q), int(mode), buf, 96))
+        return buf.value.decode()
 
     def last_timings(self):
         """(apply_ms, quantile_ms) of the most recent call; needs set_option("profile", 1)."""

@@ -1,0 +1,229 @@
+"""GPU tests of the QF_MODE_FAST kernel on compact leaf lists (csrc/select3_kernel.cuh,
+csrc/compact_lists.cuh) and of the kernels at the sizes bench.py times them (``pytest -m gpu``).
+Oracles: committed outputs of the unmodified reference (tests/golden), oracle/qrf_oracle.py and
+scikit-learn's own ``tree_.apply``.  Bars: QF_MODE_FAST within 1e-4 of the scale of y (BASELINE.json,
+float32), order statistics (q = 0, 100) and QF_MODE_EXACT bit-exact."""
+import threading
+
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_array_equal
+
+import _atsize
+import _golden
+from oracle import qrf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _dev(flat, **opts):
+    import skgarden_b200 as sg
+    d = sg.DeviceForest(flat, device=0)
+    for k, v in opts.items():
+        d.set_option(k, v)
+    return d
+
+
+def _cuda(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+FAST = 1
+
+
+@pytest.mark.parametrize("name", _golden.CASES)
+@pytest.mark.parametrize("capw", [0, 4])
+def test_select3_against_reference_outputs(name, capw):
+    # every golden forest through the CTA-level fast path with <= 3 percentiles per call (the
+    # select3 kernel wherever the forest is compactable); capw = 4 pushes rows out of the
+    # shared-memory stage into the direct-from-global path
+    g = _golden.load(name)
+    flat = _golden.flat_from_golden(g)
+    dev = _dev(flat, warp_elems=0, select3_capw=capw)
+    X = _cuda(g.X_test)
+    scale = np.abs(g.y_train).max()
+    names = set()
+    for lo in range(0, len(g.q), 3):
+        qs = g.q[lo:lo + 3]
+        names.add(dev.quantile_kernel_name(len(g.X_test), len(qs), FAST))
+        got = dev.predict_quantiles(X, qs, mode=FAST).cpu().numpy().T
+        want = g.pred[lo:lo + 3]
+        assert_allclose(got, want, rtol=1e-4, atol=1e-4 * scale)
+        for k, q in enumerate(qs):
+            if q in (0.0, 100.0):
+                assert_array_equal(got[k], want[k])
+    if name in ("c1_rfqr_boston", "c1_etqr_boston", "et_msl5", "rf_noboot_msl3_ties", "rf_maxleaf50", "rf_pure_leaves"):
+        assert all(n.startswith("quantile_select3_kernel") for n in names), names
+    dev.close()
+
+
+@pytest.mark.parametrize("rows", [1, 2, 3, 4, 5, 7, 8, 9, 33])
+def test_select3_ragged_row_counts_and_chunks(rows):
+    # row groups of four: every tail length, and chunks that are not multiples of four
+    g = _golden.load("et_msl5")
+    flat = _golden.flat_from_golden(g)
+    dev = _dev(flat, warp_elems=0)
+    qs = [5.0, 50.0, 95.0]
+    ref = _dev(flat, warp_elems=0, select_impl=2)
+    want = ref.predict_quantiles(_cuda(g.X_test), qs, mode=FAST).cpu().numpy()
+    assert dev.quantile_kernel_name(rows, 3, FAST).startswith("quantile_select3_kernel")
+    got = dev.predict_quantiles(_cuda(g.X_test[:rows]), qs, mode=FAST).cpu().numpy()
+    assert_allclose(got, want[:rows], rtol=2e-6, atol=2e-6)
+    dev.set_option("rows_per_chunk", 5)
+    got = dev.predict_quantiles(_cuda(g.X_test), qs, mode=FAST).cpu().numpy()
+    assert_allclose(got, want, rtol=2e-6, atol=2e-6)
+    host = dev.predict_quantiles_host(g.X_test, qs, mode=FAST, chunk_rows=37)
+    assert_array_equal(host, got)
+    dev.close()
+    ref.close()
+
+
+@pytest.mark.parametrize("T,msl,bootstrap,N", [(1, 8, False, 6000), (3, 30, True, 6000), (255, 5, True, 6000),
+                                              (600, 12, True, 6000), (1000, 6, False, 3000)])
+def test_select3_tree_counts(T, msl, bootstrap, N):
+    # 1, 2 and 4 trees per thread; against the exact kernels (tolerance) and select2 (same fixed-point
+    # idea, other rounding of the per-member weight)
+    import skgarden_b200 as sg
+    Xtr, ytr, Xt = _atsize.make_data(N, 500, 5, seed=T)
+    est = sg.ExtraTreesQuantileRegressor(n_estimators=T, random_state=0, min_samples_leaf=msl,
+                                         bootstrap=bootstrap, max_depth=9, n_jobs=-1).fit(Xtr, ytr)
+    dev = est._on_device()
+    dev.set_option("warp_elems", 0)
+    for qs in ([0, 50, 100], [2.5], [33.3, 99.9]):
+        exact = est.predict(Xt, quantile=qs)
+        est.mode = "fast"
+        name = dev.quantile_kernel_name(len(Xt), len(qs), FAST)
+        fast = est.predict(Xt, quantile=qs)
+        est.mode = "exact"
+        if max(int((est._flat.nodes >> np.uint64(32)).astype(np.uint32).max() & 0x7FFFFFFF), 0) <= 112:
+            assert name.startswith("quantile_select3_kernel"), name
+        tol = (1e-3 if T >= 1000 else 1e-4) * np.abs(ytr).max()
+        assert_allclose(fast, exact, rtol=1e-4, atol=tol)
+        if qs[0] == 0:
+            assert_array_equal(fast[:, [0, -1]], exact[:, [0, -1]])
+
+
+def test_select3_more_than_a_million_training_rows():
+    # N in (2^20, 2^21]: the 4096-bucket instantiation
+    import skgarden_b200 as sg
+    Xtr, ytr, Xt = _atsize.make_data(1_200_000, 1500, 4, seed=12)
+    est = sg.ExtraTreesQuantileRegressor(n_estimators=6, random_state=0, min_samples_leaf=5, n_jobs=-1).fit(Xtr, ytr)
+    dev = est._on_device()
+    dev.set_option("warp_elems", 0)
+    qs = [0, 50, 100]
+    exact = est.predict(Xt, quantile=qs)
+    est.mode = "fast"
+    assert dev.quantile_kernel_name(len(Xt), 3, FAST) == "quantile_select3_kernel<12, 1>"
+    fast = est.predict(Xt, quantile=qs)
+    assert_allclose(fast, exact, rtol=1e-4, atol=1e-4 * np.abs(ytr).max())
+    assert_array_equal(fast[:, [0, -1]], exact[:, [0, -1]])
+
+
+def test_tree_level_estimator_fast_mode_unit_weights():
+    # unit member weights (quantile/tree.py:45-47): s = 1, count = 1 in the compact lists
+    import skgarden_b200 as sg
+    Xtr, ytr, Xt = _atsize.make_data(4000, 300, 4, seed=3, ties=True)
+    est = sg.DecisionTreeQuantileRegressor(min_samples_leaf=30, random_state=0).fit(Xtr, ytr)
+    exact = est.predict(Xt, quantile=50)
+    dev = est._on_device()
+    dev.set_option("warp_elems", 0)
+    got = dev.predict_quantiles(_cuda(Xt), [5.0, 50.0, 95.0], mode=FAST).cpu().numpy()
+    assert_allclose(got[:, 1], exact, rtol=1e-4, atol=1e-4 * np.abs(ytr).max())
+
+
+# ---- the kernels at the sizes bench.py times them -------------------------
+def test_c2_shaped_forest_against_oracle():
+    # RFQR T=100 msl=1 bootstrap, 100k x 20 train, 100k test rows: warp kernel with the
+    # one-member-per-leaf gather and the 8192-bucket locality order, 2000 sampled rows bit-exact
+    import skgarden_b200 as sg
+    Xtr, ytr, Xt = _atsize.make_data(100_000, 100_000, 20, seed=0)
+    est = sg.RandomForestQuantileRegressor(n_estimators=100, min_samples_leaf=1, random_state=0, n_jobs=-1).fit(Xtr, ytr)
+    qs = [5, 33.3, 50, 95, 99.9]
+    got = est.predict(Xt, quantile=qs)
+    rows = np.random.RandomState(1).choice(len(Xt), 2000, replace=False)
+    leaves = np.array([e.tree_.apply(Xt[rows]) for e in est.estimators_]).T      # scikit-learn's own apply
+    assert_array_equal(est.apply(Xt[rows]), leaves)
+    want = O.predict_sparse(_atsize.thin_index(est, leaves), leaves, qs)
+    assert_array_equal(got[rows], want)
+    est.mode = "fast"
+    fast = est.predict(Xt, quantile=[5, 50, 95])
+    assert_allclose(fast[rows], want[:, [0, 2, 3]], rtol=1e-4, atol=1e-4 * np.abs(ytr).max())
+
+
+def test_c3_shaped_forest_against_oracle():
+    # ETQR T=500 msl=5 bootstrap, 250k x 50 train, 250k test rows (C3 with a quarter of the rows:
+    # same trees per thread, same leaf sizes, 262144-row chunks): select3 (fast) within 1e-4 and the
+    # bucket kernel (exact) bit-exact on 500 sampled rows
+    import skgarden_b200 as sg
+    Xtr, ytr, Xt = _atsize.make_data(250_000, 250_000, 50, seed=0)
+    est = sg.ExtraTreesQuantileRegressor(n_estimators=500, min_samples_leaf=5, random_state=0, n_jobs=-1).fit(Xtr, ytr)
+    qs = [5, 50, 95]
+    rows = np.random.RandomState(2).choice(len(Xt), 500, replace=False)
+    leaves = np.array([e.tree_.apply(Xt[rows]) for e in est.estimators_]).T
+    assert_array_equal(est.apply(Xt[rows]), leaves)
+    want = O.predict_sparse(_atsize.thin_index(est, leaves), leaves, qs)
+    exact = est.predict(Xt, quantile=qs)
+    assert_array_equal(exact[rows], want)
+    est.mode = "fast"
+    dev = est._on_device()
+    assert dev.quantile_kernel_name(len(Xt), 3, FAST) == "quantile_select3_kernel<11, 2>"
+    fast = est.predict(Xt, quantile=qs)
+    scale = np.abs(ytr).max()
+    assert_allclose(fast[rows], want, rtol=1e-4, atol=1e-4 * scale)
+    assert_allclose(fast, exact, rtol=1e-4, atol=2e-4 * scale)        # all rows against the exact kernels
+    dev.set_option("select_impl", 2)                                   # select2 on the 8-byte members
+    fast2 = est.predict(Xt, quantile=qs)
+    assert_allclose(fast, fast2, rtol=1e-5, atol=1e-5 * scale)
+
+
+def test_two_host_threads_on_one_handle():
+    # the handle's per-call state lives in the call (csrc/qforest_abi.cu CallScope): two threads,
+    # each with its own stream, workspace and output, give the single-threaded results
+    import skgarden_b200 as sg
+    g = _golden.load("et_msl5")
+    flat = _golden.flat_from_golden(g)
+    dev = _dev(flat)
+    X = _cuda(np.tile(g.X_test, (20, 1)))
+    want = dev.predict_quantiles(X, g.q).cpu().numpy()
+    want_host = dev.predict_quantiles_host(np.tile(g.X_test, (20, 1)), g.q)
+    assert_array_equal(want_host, want)
+    results, errors = {}, []
+
+    def device_worker(k):
+        try:
+            from skgarden_b200 import _native
+            import ctypes as C
+            st = torch.cuda.Stream()
+            n, q = X.shape[0], np.ascontiguousarray(g.q, dtype=np.float64)
+            need = int(dev._lib.qf_forest_workspace_bytes(dev._h, n, len(q)))
+            with torch.cuda.stream(st):
+                ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+                for _ in range(5):
+                    out = torch.empty((n, len(q)), dtype=torch.float64, device="cuda")
+                    _native.check(dev._lib.qf_forest_predict_quantiles(
+                        dev._h, C.c_void_p(X.data_ptr()), n, X.stride(0), q.ctypes.data_as(C.c_void_p), len(q),
+                        C.c_void_p(out.data_ptr()), 0, C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(st.cuda_stream)))
+                st.synchronize()
+            results[k] = out.cpu().numpy()
+        except Exception as exc:                                   # pragma: no cover
+            errors.append(exc)
+
+    def host_worker(k):
+        try:
+            for _ in range(3):
+                results[k] = dev.predict_quantiles_host(np.tile(g.X_test, (20, 1)), g.q, chunk_rows=64)
+        except Exception as exc:                                   # pragma: no cover
+            errors.append(exc)
+
+    threads = [threading.Thread(target=device_worker, args=(0,)), threading.Thread(target=device_worker, args=(1,)),
+               threading.Thread(target=host_worker, args=(2,)), threading.Thread(target=host_worker, args=(3,))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for k in range(4):
+        assert_array_equal(results[k], want)
+    dev.close()
