@@ -206,6 +206,35 @@ apply_kernel(const ApplyParams p, void* __restrict__ out) {
     }
 }
 
+// Leaf lookup for rows too wide for the shared-memory tile (more than ~1600 features): one
+// thread per row, features read from global memory (L1/L2-resident after the first touch of a
+// line), trees one after the other.  Same outputs as apply_kernel; a correctness path, not a
+// tuned one.
+template <int EMIT>
+__global__ void __launch_bounds__(128)
+apply_wide_rows_kernel(const ApplyParams p, void* __restrict__ out) {
+    const int64_t pos = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (pos >= p.n) return;
+    const int64_t row = p.order ? static_cast<int64_t>(__ldg(p.order + pos)) : pos;
+    const float* __restrict__ x = p.X + row * p.ldx;
+    const uint32_t fmask = (1u << p.fbits) - 1u;
+    for (int t = p.t_begin; t < p.t_end; ++t) {
+        uint32_t node = __ldg(p.roots + t);
+        uint2 nd;
+        for (;;) {
+            nd = __ldg(p.nodes + node);
+            if (static_cast<int32_t>(nd.y) < 0) break;
+            node += (nd.y >> p.fbits) + ((__ldg(x + (nd.y & fmask)) <= __uint_as_float(nd.x)) ? 0u : 1u);   // _tree.pyx:989
+        }
+        if (EMIT == APPLY_EMIT_SEGMENT)
+            static_cast<uint2*>(out)[pos * p.T + t] = make_uint2(nd.x, nd.y & 0x7fffffffu);
+        else if (EMIT == APPLY_EMIT_COMPACT)
+            static_cast<uint32_t*>(out)[static_cast<int64_t>(t) * p.ld_out + pos] = nd.x;
+        else
+            static_cast<int32_t*>(out)[row * p.T + t] = static_cast<int32_t>(node);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // Locality order: counting sort of the rows by the leaf they reach in ONE tree.
 //   locality_key_kernel   : bucket[row] = (first member of the leaf) >> key_shift, histogram

@@ -6,14 +6,16 @@
 // weight of a member is f32(count / leaf count sum) (ensemble.py:94-99), i.e. all weights of a leaf
 // share ONE denominator.  The compact form stores that denominator once per 32 bytes:
 //
-//   octet (32 bytes, 32-byte aligned) = [ s | m0 | m1 | m2 | m3 | m4 | m5 | m6 ]
-//       s  = leaf count sum (uint32)
+//   octet (32 bytes, 32-byte aligned) = [ U | m0 | m1 | m2 | m3 | m4 | m5 | m6 ]
+//       U  = rn(fx_scale / s), s = leaf count sum: the 32-bit fixed-point weight of ONE bootstrap count
+//            of this leaf (fx_scale = 2^(31-k) units per unit of weight, 2^k > the largest total weight
+//            a row can gather), so that a member weighs count * U -- one integer multiply
 //       m  = rank (bits 0..23) | bootstrap count (bits 24..31); 0 = padding
 //   a leaf of c members owns ceil(c / 7) consecutive octets, every one with the header, so that an
 //   octet can be processed without its neighbours (any lane can take any octet).
-//   float32 weight of a member = __fdiv_rn(count, s): bit-identical to the stored weight -- the
-//   builder below verifies that for every member, the forest is "not compactable" otherwise and
-//   the 8-byte kernels stay in charge.
+//   The builder recovers (s, counts) from the stored float32 weights and verifies
+//   __fdiv_rn(count, s) == weight bit for bit for every member; a forest for which that fails (or
+//   with leaves of more than 112 members) is "not compactable" and the 8-byte kernels stay in charge.
 //
 // The walk kernel runs on a COPY of the node array whose leaves carry, in lo32, the compact list
 // word `first octet | (octets - 1) << 28` (0xffffffff: a leaf without in-bag members); K1 emits
@@ -157,7 +159,8 @@ scan_apply_kernel(uint32_t* __restrict__ data, int64_t n, const uint64_t* __rest
 // pass 1's octet counts: first octet of the leaf whose first member is nd.x)
 __global__ void __launch_bounds__(256)
 compact_fill_kernel(const uint2* __restrict__ nodes, int64_t n_nodes, const uint2* __restrict__ members,
-                    const uint32_t* __restrict__ oct_at, uint2* __restrict__ nodes_c, uint4* __restrict__ lists) {
+                    const uint32_t* __restrict__ oct_at, float fx_scale, uint2* __restrict__ nodes_c,
+                    uint4* __restrict__ lists) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
     uint2 nd = nodes[i];
@@ -173,7 +176,7 @@ compact_fill_kernel(const uint2* __restrict__ nodes, int64_t n_nodes, const uint
             const uint32_t noct = (cnt + kOctetMembers - 1) / kOctetMembers;
             for (uint32_t j = 0; j < noct; ++j) {
                 uint32_t w[8];
-                w[0] = s;
+                w[0] = __float2uint_rn(__fdiv_rn(fx_scale, sf));    // fixed-point weight of one bootstrap count
 #pragma unroll
                 for (int e = 0; e < kOctetMembers; ++e) {
                     const uint32_t k = j * kOctetMembers + e;

@@ -292,8 +292,15 @@ int launch_apply(qf_forest* f, CallStats& cs, const float* X, int64_t n, int64_t
         ap.row_warps >>= 1;
     const int rows_per_cta = 32 * ap.row_warps;
     const size_t smem = static_cast<size_t>(f->F) * rows_per_cta * sizeof(float);
-    if (smem > 200 * 1024)
-        return qf::fail(QF_ERR_LIMIT, "apply: n_features too large for the shared-memory row tile");
+    if (smem > 200 * 1024) {                            // rows wider than the shared-memory tile: one thread per row
+        {
+            SpanTimer span(f, cs, SPAN_APPLY, st);
+            qf::apply_wide_rows_kernel<EMIT><<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(ap, out);
+        }
+        QF_CUDA_TRY(cudaGetLastError());
+        ++cs.launches;
+        return QF_OK;
+    }
     const int64_t grid = (n + rows_per_cta - 1) / rows_per_cta;
     auto run = [&](auto kernel) -> int {
         int rc = set_smem(kernel, smem);
@@ -466,6 +473,13 @@ int ensure_compact(qf_forest* f) {
     if (f->compact_state != 0) return QF_OK;
     f->compact_state = -1;
     if (f->N > (int64_t(1) << 24) || f->n_members <= 0) return QF_OK;     // ranks live in 24 bits
+    // fixed-point units per unit of weight (as in launch_select_kernel): the octet headers carry
+    // rn(scale / leaf count sum), the weight of one bootstrap count
+    int kbits = 0;
+    const int64_t bound = std::max<int64_t>(f->T, f->row_weight_bound);
+    while ((int64_t(1) << kbits) < bound + 1) ++kbits;
+    if (kbits > 20) return QF_OK;
+    const float fx_scale = static_cast<float>(int64_t(1) << (31 - kbits));
     struct Tmp {
         void* p[4] = {};
         ~Tmp() { for (void* q : p) cudaFree(q); }
@@ -498,7 +512,7 @@ int ensure_compact(qf_forest* f) {
     cudaError_t e = cudaMalloc(&nodes_c, static_cast<size_t>(f->n_nodes) * 8);
     if (e == cudaSuccess) e = cudaMalloc(&lists, static_cast<size_t>(n_octets) * 32);
     if (e == cudaSuccess) {
-        qf::compact_fill_kernel<<<node_blocks, 256>>>(f->d_nodes, f->n_nodes, f->d_members, oct_at, nodes_c, lists);
+        qf::compact_fill_kernel<<<node_blocks, 256>>>(f->d_nodes, f->n_nodes, f->d_members, oct_at, fx_scale, nodes_c, lists);
         qf::compact_tree_stats_kernel<<<f->T, 256>>>(f->d_nodes, f->d_roots, f->n_nodes, f->T, stats);
         e = cudaGetLastError();
     }
@@ -532,7 +546,7 @@ struct Select3Geometry {
 Select3Geometry select3_geometry(const qf_forest* f, int nq) {
     Select3Geometry g;
     if (f->select_impl != 0 || f->select_bits != qf::kSelectL2Bits || nq > qf::kSelect2QB) return g;
-    if (f->T > qf::kSelect3MaxIPT * qf::kSelect3Threads) return g;
+    if (f->T > qf::kSelect3MaxIPT * qf::kSelect3Workers) return g;
     int k = 0;                                          // weights of a row sum to <= bound < 2^k
     const int64_t bound = std::max<int64_t>(f->T, f->row_weight_bound);
     while ((int64_t(1) << k) < bound + 1) ++k;
@@ -543,7 +557,7 @@ Select3Geometry select3_geometry(const qf_forest* f, int nq) {
     g.fx_scale = static_cast<float>(int64_t(1) << (31 - k));
     g.log2nb = nbits <= 11 + qf::kSelect2SlotBits ? 11 : 12;
     g.shift1 = std::max(0, nbits - g.log2nb);
-    g.ipt = (f->T + qf::kSelect3Threads - 1) / qf::kSelect3Threads;
+    g.ipt = (f->T + qf::kSelect3Workers - 1) / qf::kSelect3Workers;
     if (g.ipt == 3) g.ipt = 4;
     return g;
 }
@@ -556,7 +570,7 @@ bool select3_finish_geometry(const qf_forest* f, Select3Geometry& g) {
         double e = 0.0;
         for (int i = 0; i < g.ipt; ++i)
             for (int l = 0; l < 32; ++l) {
-                const int t = w * 32 + l + i * qf::kSelect3Threads;
+                const int t = w * 32 + l + i * qf::kSelect3Workers;
                 if (t < f->T) e += f->tree_octets[t];
             }
         busiest = std::max(busiest, e);

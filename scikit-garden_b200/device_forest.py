@@ -214,32 +214,156 @@ class DeviceForest:
             int(mode), int(chunk_rows)))
         return out_host
 
+    # -- host-array conveniences (what the estimators call) -------------------------------
+    def _to_device(self, X_host):
+        torch = _torch()
+        return torch.from_numpy(np.ascontiguousarray(X_host, dtype=np.float32)).to("cuda:%d" % self.device)
+
+    def apply_host(self, X_host: np.ndarray) -> np.ndarray:
+        torch = _torch()
+        with torch.cuda.device(self.device):
+            return self.apply(self._to_device(X_host)).cpu().numpy()
+
+    def predict_mean_host(self, X_host: np.ndarray) -> np.ndarray:
+        torch = _torch()
+        with torch.cuda.device(self.device):
+            return self.predict_mean(self._to_device(X_host)).cpu().numpy()
+
+    def predict_mean_std_host(self, X_host: np.ndarray, min_variance: float = 0.0):
+        torch = _torch()
+        with torch.cuda.device(self.device):
+            mean, std = self.predict_mean_std(self._to_device(X_host), min_variance)
+            return mean.cpu().numpy(), std.cpu().numpy()
+
     def predict_stream(self, chunks, quantiles: Sequence[float], mode: int = _native.QF_MODE_EXACT,
                        pinned: bool = True):
         """Streaming front end (BASELINE.json config 5: test rows that do not fit one host
         array): ``chunks`` is any iterable of (m_i, F) float32 arrays; yields one (m_i, Q)
-        float64 array per chunk, in order.  Every chunk goes through the pipelined
-        host-buffer call; with ``pinned`` the rows are staged in a reused page-locked buffer
-        so that the H2D copy runs at full PCIe bandwidth."""
-        torch = _torch()
-        q = [float(v) for v in quantiles]
-        stage_x = stage_o = None
+        float64 array per chunk, in order.  See :func:`stream_predict`."""
+        return stream_predict([self], chunks, quantiles, mode=mode, pinned=pinned)
+
+
+def stream_predict(replicas, chunks, quantiles, mode=_native.QF_MODE_EXACT, pinned=True):
+    """Chunks of test rows through one or several forest replicas, results in order.
+
+    Two worker threads per replica: while one chunk is inside the pipelined host-buffer call
+    (H2D / kernels / D2H on three streams, csrc/qforest_abi.cu), the next one is being staged
+    into the second page-locked buffer, so the GPU never waits for the host copy; chunk k goes
+    to replica k mod G.  ``pinned=False`` hands the caller's arrays to the C call as they are."""
+    import collections
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+    torch = _torch()
+    q = [float(v) for v in quantiles]
+    F = replicas[0].n_features
+    tls = threading.local()
+
+    def work(dev, X):
+        m = X.shape[0]
+        if not pinned:
+            return dev.predict_quantiles_host(X, q, mode=mode)
+        st = getattr(tls, "stage", None)
+        if st is None or st[0].shape[0] < m:
+            st = (torch.empty((m, F), dtype=torch.float32).pin_memory(),
+                  torch.empty((m, len(q)), dtype=torch.float64).pin_memory())
+            tls.stage = st
+        xs, os_ = st[0][:m].numpy(), st[1][:m].numpy()
+        xs[...] = X
+        dev.predict_quantiles_host(xs, q, out_host=os_, mode=mode)
+        return os_.copy()
+
+    pending = collections.deque()
+    depth = 2 * len(replicas)
+    with ThreadPoolExecutor(depth) as pool:
+        k = 0
         for X in chunks:
             X = np.ascontiguousarray(X, dtype=np.float32)
-            if X.ndim != 2 or X.shape[1] != self.n_features:
-                raise ValueError("chunk has shape %r, forest expects (m, %d)" % (X.shape, self.n_features))
-            m = X.shape[0]
-            if m == 0:
-                yield np.empty((0, len(q)), dtype=np.float64)
-                continue
-            if not pinned:
-                yield self.predict_quantiles_host(X, q, mode=mode)
-                continue
-            if stage_x is None or stage_x.shape[0] < m:
-                stage_x = torch.empty((m, self.n_features), dtype=torch.float32).pin_memory()
-                stage_o = torch.empty((m, len(q)), dtype=torch.float64).pin_memory()
-            xs, os_ = stage_x[:m].numpy(), stage_o[:m].numpy()
-            xs[...] = X
-            self.predict_quantiles_host(xs, q, out_host=os_, mode=mode)
-            yield os_.copy()
+            if X.ndim != 2 or X.shape[1] != F:
+                raise ValueError("chunk has shape %r, forest expects (m, %d)" % (X.shape, F))
+            if X.shape[0] == 0:
+                pending.append(None)
+            else:
+                pending.append(pool.submit(work, replicas[k % len(replicas)], X))
+                k += 1
+            while len(pending) > depth or (pending and pending[0] is None):
+                head = pending.popleft()
+                yield np.empty((0, len(q)), dtype=np.float64) if head is None else head.result()
+        while pending:
+            head = pending.popleft()
+            yield np.empty((0, len(q)), dtype=np.float64) if head is None else head.result()
 
+
+class ForestReplicas:
+    """The forest replicated on several GPUs of one box; every call splits its rows into
+    contiguous shards (skgarden/quantile/ensemble.py:137: rows are independent), one host
+    thread per GPU, results written straight into one output array.  No collective: the only
+    traffic is each GPU's own H2D / D2H."""
+
+    def __init__(self, flat: FlatForest, devices: Sequence[int], with_impurity: bool = False):
+        from concurrent.futures import ThreadPoolExecutor
+        devices = [int(d) for d in devices]
+        if not devices or len(set(devices)) != len(devices):
+            raise ValueError("devices must be a non-empty list of distinct CUDA ordinals")
+        self.devices = devices
+        self.replicas = [DeviceForest(flat, device=d, with_impurity=with_impurity) for d in devices]
+        self.n_trees, self.n_features = flat.n_trees, flat.n_features
+        self.device = devices[0]
+        self._pool = ThreadPoolExecutor(len(devices))
+
+    def close(self):
+        for r in self.replicas:
+            r.close()
+        self._pool.shutdown(wait=True)
+
+    def set_option(self, key: str, value: int) -> None:
+        for r in self.replicas:
+            r.set_option(key, value)
+
+    @property
+    def device_bytes(self) -> int:
+        return sum(r.device_bytes for r in self.replicas)
+
+    def _sharded(self, n, fn):
+        from .sharding import shard_rows
+        G = len(self.replicas)
+        jobs = [(self.replicas[g],) + shard_rows(n, G, g) for g in range(G)]
+        futures = [self._pool.submit(fn, dev, lo, hi) for dev, lo, hi in jobs if hi > lo]
+        for f in futures:
+            f.result()
+
+    def predict_quantiles_host(self, X_host, quantiles, out_host=None, mode=_native.QF_MODE_EXACT, chunk_rows=0):
+        q = np.ascontiguousarray(quantiles, dtype=np.float64).ravel()
+        n = X_host.shape[0]
+        if out_host is None:
+            out_host = np.empty((n, q.shape[0]), dtype=np.float64)
+        self._sharded(n, lambda dev, lo, hi: dev.predict_quantiles_host(
+            X_host[lo:hi], q, out_host=out_host[lo:hi], mode=mode, chunk_rows=chunk_rows))
+        return out_host
+
+    def apply_host(self, X_host):
+        out = np.empty((X_host.shape[0], self.n_trees), dtype=np.int64)
+
+        def fn(dev, lo, hi):
+            out[lo:hi] = dev.apply_host(X_host[lo:hi])
+        self._sharded(X_host.shape[0], fn)
+        return out
+
+    def predict_mean_host(self, X_host):
+        out = np.empty(X_host.shape[0], dtype=np.float64)
+
+        def fn(dev, lo, hi):
+            out[lo:hi] = dev.predict_mean_host(X_host[lo:hi])
+        self._sharded(X_host.shape[0], fn)
+        return out
+
+    def predict_mean_std_host(self, X_host, min_variance=0.0):
+        mean = np.empty(X_host.shape[0], dtype=np.float64)
+        std = np.empty(X_host.shape[0], dtype=np.float64)
+
+        def fn(dev, lo, hi):
+            mean[lo:hi], std[lo:hi] = dev.predict_mean_std_host(X_host[lo:hi], min_variance)
+        self._sharded(X_host.shape[0], fn)
+        return mean, std
+
+    def predict_stream(self, chunks, quantiles, mode=_native.QF_MODE_EXACT, pinned=True):
+        return stream_predict(self.replicas, chunks, quantiles, mode=mode, pinned=pinned)

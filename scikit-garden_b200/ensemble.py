@@ -9,6 +9,14 @@
   (ensemble.py:104-143): ``None`` -> mean (float64), scalar q -> (n,) float64 holding the
   reference's float32 results.  Extension: a sequence of q -> (n, Q) in one pass.
 * There is no CPU fallback: predict/apply need the CUDA library and an sm_100 GPU.
+* Keyword-only extras: ``device`` (CUDA ordinal), ``devices`` (list of ordinals: the forest is
+  replicated and the rows of every ``predict`` / ``apply`` / ``predict_stream`` call are split
+  over the GPUs, one host thread each -- results do not depend on the split), ``mode``
+  (``"exact"``: bit-identical to the reference; ``"fast"``: within 1e-4), ``builder``.
+* Limits of the GPU path (the reference has none of them): dense X only (sparse X raises
+  ``NotImplementedError``); the packed node layout holds ``31 - ceil(log2(n_features))`` bits of
+  child offset (level-order distance), i.e. trees wider than 2^(31 - feature_bits) nodes on one
+  level are refused at ``fit`` with ``QFError`` (QF_ERR_LIMIT); at most 2^31 training rows.
 """
 from __future__ import annotations
 
@@ -50,8 +58,8 @@ class _BaseForestQuantileRegressor(RegressorMixin, BaseEstimator):
     def __init__(self, n_estimators=10, criterion="mse", max_depth=None, min_samples_split=2,
                  min_samples_leaf=1, min_weight_fraction_leaf=0.0, max_features="auto",
                  max_leaf_nodes=None, bootstrap=True, oob_score=False, n_jobs=1,
-                 random_state=None, verbose=0, warm_start=False, *, device=0, mode="exact",
-                 builder="host"):
+                 random_state=None, verbose=0, warm_start=False, *, device=0, devices=None,
+                 mode="exact", builder="host"):
         self.n_estimators = n_estimators
         self.criterion = criterion
         self.max_depth = max_depth
@@ -67,6 +75,7 @@ class _BaseForestQuantileRegressor(RegressorMixin, BaseEstimator):
         self.verbose = verbose
         self.warm_start = warm_start
         self.device = device
+        self.devices = devices        # list of CUDA ordinals: forest replicated, rows of every call sharded over them
         self.mode = mode
         self.builder = builder        # "host": qf_pack_tree; "device": qf_build_csr (member lists on the GPU)
 
@@ -89,8 +98,8 @@ class _BaseForestQuantileRegressor(RegressorMixin, BaseEstimator):
         forest = getattr(self, "_forest", None)
         if not (self.warm_start and forest is not None):
             forest = self._make_forest()
-        else:
-            forest.set_params(n_estimators=self.n_estimators)
+        else:                                     # warm start: every constructor parameter follows set_params
+            forest.set_params(**self._make_forest().get_params(deep=False))
         forest.fit(X, y)                                                                    # :81
         self._forest = forest
         self.estimators_ = forest.estimators_
@@ -171,6 +180,25 @@ class _BaseForestQuantileRegressor(RegressorMixin, BaseEstimator):
             self._dense_attrs = (leaves, weights)
         return self._dense_attrs
 
+    # fitted attributes the reference classes inherit from scikit-learn's forest
+    @property
+    def oob_score_(self):
+        return self._fitted_forest().oob_score_
+
+    @property
+    def oob_prediction_(self):
+        return self._fitted_forest().oob_prediction_
+
+    @property
+    def feature_importances_(self):
+        return self._fitted_forest().feature_importances_
+
+    def _fitted_forest(self):
+        forest = getattr(self, "_forest", None)
+        if forest is None:
+            raise NotFittedError("This %s instance is not fitted yet." % type(self).__name__)
+        return forest
+
     @property
     def y_train_leaves_(self):
         return self._dense_fit_attributes()[0]
@@ -189,8 +217,12 @@ class _BaseForestQuantileRegressor(RegressorMixin, BaseEstimator):
     def _on_device(self):
         flat = self._check_fitted()
         if getattr(self, "_device_forest", None) is None:
-            from .device_forest import DeviceForest
-            self._device_forest = DeviceForest(flat, device=self.device, with_impurity=self._needs_impurity)
+            from .device_forest import DeviceForest, ForestReplicas
+            devices = getattr(self, "devices", None)
+            if devices is not None:
+                self._device_forest = ForestReplicas(flat, devices, with_impurity=self._needs_impurity)
+            else:
+                self._device_forest = DeviceForest(flat, device=self.device, with_impurity=self._needs_impurity)
         return self._device_forest
 
     _needs_impurity = False            # the return_std forests (forest.py) upload tree_.impurity too
@@ -213,13 +245,10 @@ class _BaseForestQuantileRegressor(RegressorMixin, BaseEstimator):
     # -- the hot path --------------------------------------------------------------------------
     def predict(self, X, quantile=None):
         """ensemble.py:104-143.  ``quantile`` in [0, 100] (int or float); None = mean."""
-        import torch
         X = self._validate_X(X)
         dev = self._on_device()
         if quantile is None:                                             # ensemble.py:130-131
-            with torch.cuda.device(dev.device):
-                xd = torch.from_numpy(X).to("cuda:%d" % dev.device, non_blocking=False)
-                return dev.predict_mean(xd).cpu().numpy()
+            return dev.predict_mean_host(X)
         qs, scalar = _check_quantiles(quantile)
         out = dev.predict_quantiles_host(X, qs, mode=self._mode())
         return out[:, 0] if scalar else out
@@ -243,12 +272,8 @@ class _BaseForestQuantileRegressor(RegressorMixin, BaseEstimator):
 
     def apply(self, X):
         """forest.py:583-604: (n, T) int64 scikit-learn leaf ids."""
-        import torch
         X = self._validate_X(X)
-        dev = self._on_device()
-        with torch.cuda.device(dev.device):
-            xd = torch.from_numpy(X).to("cuda:%d" % dev.device)
-            return dev.apply(xd).cpu().numpy()
+        return self._on_device().apply_host(X)
 
     # -- persistence: the device handle never travels ----------------------------------------------
     def __getstate__(self):

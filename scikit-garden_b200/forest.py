@@ -13,7 +13,7 @@ import numpy as np
 from sklearn.ensemble import ExtraTreesRegressor as _SkExtraTrees
 from sklearn.ensemble import RandomForestRegressor as _SkRandomForest
 
-from .ensemble import _BaseForestQuantileRegressor
+from .ensemble import _CRITERION, _BaseForestQuantileRegressor
 
 __all__ = ["RandomForestRegressor", "ExtraTreesRegressor"]
 
@@ -25,28 +25,24 @@ class _BaseStdForestRegressor(_BaseForestQuantileRegressor):
                  min_samples_leaf=1, min_weight_fraction_leaf=0.0, max_features="auto",
                  max_leaf_nodes=None, bootstrap=True, oob_score=False, n_jobs=1,
                  random_state=None, verbose=0, warm_start=False, min_variance=0.0, *, device=0,
-                 builder="host"):
+                 devices=None, builder="host"):
         super().__init__(n_estimators=n_estimators, criterion=criterion, max_depth=max_depth,
                          min_samples_split=min_samples_split, min_samples_leaf=min_samples_leaf,
                          min_weight_fraction_leaf=min_weight_fraction_leaf, max_features=max_features,
                          max_leaf_nodes=max_leaf_nodes, bootstrap=bootstrap, oob_score=oob_score,
                          n_jobs=n_jobs, random_state=random_state, verbose=verbose,
-                         warm_start=warm_start, device=device, builder=builder)
+                         warm_start=warm_start, device=device, devices=devices, builder=builder)
         self.min_variance = min_variance
 
     def predict(self, X, return_std=False):
         """forest.py:332-362.  Returns the forest mean, or ``(mean, std)`` with ``return_std``."""
-        import torch
         X = self._validate_X(X)
         dev = self._on_device()
-        with torch.cuda.device(dev.device):
-            xd = torch.from_numpy(X).to("cuda:%d" % dev.device)
-            if not return_std:
-                return dev.predict_mean(xd).cpu().numpy()
-            if self.criterion != "mse":                                  # forest.py:355-358
-                raise ValueError("Expected impurity to be 'mse', got %s instead" % self.criterion)
-            mean, std = dev.predict_mean_std(xd, self.min_variance)
-            return mean.cpu().numpy(), std.cpu().numpy()
+        if not return_std:
+            return dev.predict_mean_host(X)
+        if _CRITERION.get(self.criterion, self.criterion) != "squared_error":    # forest.py:355-358
+            raise ValueError("Expected impurity to be 'mse', got %s instead" % self.criterion)
+        return dev.predict_mean_std_host(X, self.min_variance)
 
 
 class RandomForestRegressor(_BaseStdForestRegressor):
@@ -63,10 +59,11 @@ class ExtraTreesRegressor(_BaseStdForestRegressor):
                  min_samples_leaf=1, min_weight_fraction_leaf=0.0, max_features="auto",
                  max_leaf_nodes=None, bootstrap=False, oob_score=False, n_jobs=1,
                  random_state=None, verbose=0, warm_start=False, min_variance=0.0, *, device=0,
-                 builder="host"):
+                 devices=None, builder="host"):
         super().__init__(n_estimators=n_estimators, criterion=criterion, max_depth=max_depth,
                          min_samples_split=min_samples_split, min_samples_leaf=min_samples_leaf,
                          min_weight_fraction_leaf=min_weight_fraction_leaf, max_features=max_features,
                          max_leaf_nodes=max_leaf_nodes, bootstrap=bootstrap, oob_score=oob_score,
                          n_jobs=n_jobs, random_state=random_state, verbose=verbose,
-                         warm_start=warm_start, min_variance=min_variance, device=device, builder=builder)
+                         warm_start=warm_start, min_variance=min_variance, device=device, devices=devices,
+                         builder=builder)

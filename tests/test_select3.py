@@ -70,10 +70,10 @@ def test_select3_ragged_row_counts_and_chunks(rows):
     want = ref.predict_quantiles(_cuda(g.X_test), qs, mode=FAST).cpu().numpy()
     assert dev.quantile_kernel_name(rows, 3, FAST).startswith("quantile_select3_kernel")
     got = dev.predict_quantiles(_cuda(g.X_test[:rows]), qs, mode=FAST).cpu().numpy()
-    assert_allclose(got, want[:rows], rtol=2e-6, atol=2e-6)
+    assert_allclose(got, want[:rows], rtol=2e-5, atol=2e-5)
     dev.set_option("rows_per_chunk", 5)
     got = dev.predict_quantiles(_cuda(g.X_test), qs, mode=FAST).cpu().numpy()
-    assert_allclose(got, want, rtol=2e-6, atol=2e-6)
+    assert_allclose(got, want, rtol=2e-5, atol=2e-5)
     host = dev.predict_quantiles_host(g.X_test, qs, mode=FAST, chunk_rows=37)
     assert_array_equal(host, got)
     dev.close()
@@ -227,3 +227,20 @@ def test_two_host_threads_on_one_handle():
     for k in range(4):
         assert_array_equal(results[k], want)
     dev.close()
+
+
+def test_more_features_than_the_shared_memory_tile():
+    # 1700 features x 32 rows x 4 bytes > 200 KB: the leaf lookup falls back to one thread per row
+    # reading features from global memory (used to fail with QF_ERR_LIMIT)
+    import skgarden_b200 as sg
+    rng = np.random.RandomState(4)
+    X = rng.randn(700, 1700).astype(np.float32)
+    y = X[:, 0] + X[:, 1500] + 0.1 * rng.randn(700)
+    est = sg.RandomForestQuantileRegressor(n_estimators=5, random_state=0, min_samples_leaf=3,
+                                           max_features=0.5).fit(X[:500], y[:500])
+    Xt = X[500:]
+    leaves = est.apply(Xt)
+    assert_array_equal(leaves, O.forest_apply(est.estimators_, Xt))
+    index = O.SparseIndex(est.y_train_, est.y_train_leaves_, est.y_weights_, est._flat.sorter)
+    assert_array_equal(est.predict(Xt, quantile=[10, 50, 90]), O.predict_sparse(index, leaves, [10, 50, 90]))
+    assert_array_equal(est.predict(Xt), O.predict_mean(est.estimators_, Xt, leaves))
