@@ -505,7 +505,13 @@ int ensure_compact(qf_forest* f) {
     uint64_t n_octets = 0;
     QF_CUDA_TRY(cudaMemcpy(&h_flags, flags, 4, cudaMemcpyDeviceToHost));
     QF_CUDA_TRY(cudaMemcpy(&n_octets, tile_sum + n_tiles, 8, cudaMemcpyDeviceToHost));
-    if (h_flags != 0 || n_octets == 0 || n_octets > qf::kCompactOffMask) return QF_OK;   // not compactable
+    if (h_flags != 0 || n_octets == 0 || n_octets > qf::kCompactOffMask) {               // not compactable
+        char why[160];
+        std::snprintf(why, sizeof(why), "compact leaf lists not built: flags %d (1 leaf > 112 members, 2 weights are not "
+                      "count / sum, 4 rank >= 2^24), %llu octets", h_flags, static_cast<unsigned long long>(n_octets));
+        qf::last_error_slot() = why;                    // informational: the 8-byte kernels take over
+        return QF_OK;
+    }
     qf::scan_apply_kernel<<<static_cast<unsigned>(n_tiles), 256>>>(oct_at, f->n_members, tile_sum);
     uint2* nodes_c = nullptr;
     uint4* lists = nullptr;
@@ -580,8 +586,8 @@ bool select3_finish_geometry(const qf_forest* f, Select3Geometry& g) {
     capw = (capw + 3) & ~3;
     g.capw = capw;
     g.smem = qf::select3_kernel_smem(g.log2nb, g.shift1, capw);
-    // three CTAs per SM is what the kernel is tuned for; one oversized stage (big leaves) is not worth it
-    g.ok = g.smem <= 72 * 1024;
+    // two CTAs per SM is what the kernel is tuned for; one oversized stage (big leaves) is not worth it
+    g.ok = g.smem <= 112 * 1024;
     return g.ok;
 }
 

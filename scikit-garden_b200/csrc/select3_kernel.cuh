@@ -14,31 +14,34 @@
 //   input    K1 leaves ONE 32-bit word per (tree, row): first octet | (octets - 1) << 28, tree-major,
 //            so that a CTA reads the words of FOUR consecutive rows of a tree with one 128-bit load
 //            (prefetched one group of rows ahead into registers).
-//   roles    a CTA is 8 WORKER warps + 1 SCANNER warp.  Workers only ever touch members; everything
-//            that is serial per row (histogram scan, bucket search, selection, interpolation, output)
-//            is the scanner's and runs while the workers' copies of the next row are in flight.  They
-//            meet at three named barriers per row, each an arrive on one side and a sync on the
-//            other (bar.arrive / bar.sync): H "histogram full", M "buckets marked", S "slots full".
-//            No thread waits at a barrier for work that is not its own input.
+//   roles    a CTA is 8 WORKER warps + one SELECT warp per percentile (3).  Workers own everything
+//            that touches members (copies, both passes) and the short parallel scan in between; a
+//            select warp owns the serial tail of its percentile (crossing entry, neighbours,
+//            interpolation, the y loads, the output) and runs it while the workers are already in
+//            the next row.  Workers meet each other at three named barriers per row (bar.sync on 256
+//            threads); workers and select warps only ever ARRIVE for each other (bar.arrive on one
+//            side, bar.sync on the other): nobody waits for work that is not its own input.
 //   copies   every worker thread owns IPT trees.  A warp scan of the octet counts places the lists of
 //            the warp's 32 * IPT leaves back to back in the warp's segment of a shared-memory stage
-//            and every lane moves its own lists there with 16-byte cp.async (LDGSTS): nothing waits
-//            on a global load.  The copies of row r + 1 are issued as soon as the warp is done with
-//            row r's second pass.  A row whose lists exceed the segment is read from global memory
-//            directly (same code, synchronous loads).
-//   pass 1   the warp waits for ITS OWN copies (cp.async.wait_group + __syncwarp: no block barrier)
-//            and walks its segment octet by octet, all lanes busy whatever the leaf sizes: seven
-//            members -> one predicated shared-memory RED each into the NB-bucket histogram.
-//   scan     (scanner) every lane sums its NB / 32 consecutive buckets, one warp scan, then the group
-//            of buckets that holds a percentile's crossing is scanned again across the lanes: the
-//            crossing bucket bq and its nearest non-empty neighbours bp / bn come out of two ballots.
-//            A 16-bit table says which slot arrays a bucket feeds.
+//            and every lane moves its own lists there with 16-byte cp.async (LDGSTS).  Two stages:
+//            the copies of row r + 1 are issued BEFORE row r is touched and complete under it
+//            (cp.async.wait_group 1), so nothing ever waits on a global load.  A row whose lists
+//            exceed the segment is read from global memory directly (same code, synchronous loads).
+//   pass 1   the warp waits for ITS OWN copies (wait_group + __syncwarp: no block barrier) and walks
+//            its segment octet by octet, all lanes busy whatever the leaf sizes: seven members -> one
+//            predicated shared-memory RED each into the NB-bucket histogram.
+//   scan     4 warps x 16 buckets per thread in registers, one warp scan + 4 partials; the thread
+//            that finds a percentile's crossing bucket bq among its own looks for the nearest
+//            non-empty neighbours bp / bn in its registers or, through a 128-bit map of non-empty
+//            16-bucket groups, in one other group of the (not yet cleared) histogram.  A 16-bit table
+//            says which slot arrays a bucket feeds.
 //   pass 2   second walk over the staged octets: the seven table lookups of an octet are issued
 //            together and tested with one branch; the ~50 members of marked buckets are added at
 //            single-rank resolution to the slot arrays [bp | bq | bn] of their percentile(s).
-//   select   (scanner) per percentile: crossing entry e in bq's slots, its neighbours inside bq or,
-//            failing that, the largest rank of bp / the smallest rank of bn; the three percentiles
-//            are then interpolated by three lanes side by side (their y loads overlap).
+//   select   one warp per percentile: crossing entry e in bq's slots, its neighbours inside bq or,
+//            failing that, the largest rank of bp / the smallest rank of bn; lane 0 interpolates.
+//   Histogram and table are double-buffered by row parity, so that clearing them never races with
+//   the next row's writes.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -50,11 +53,12 @@
 namespace qf {
 
 constexpr int kSelect3Workers = 256;                    // worker threads (8 warps)
-constexpr int kSelect3Threads = kSelect3Workers + 32;   // + the scanner warp
 constexpr int kSelect3Warps = kSelect3Workers / 32;
-constexpr int kSelect3CtasPerSm = 3;
+constexpr int kSelect3Threads = kSelect3Workers + 32 * kSelect2QB;    // + one select warp per percentile
+constexpr int kSelect3CtasPerSm = 2;
 constexpr int kSelect3MaxIPT = 4;                       // trees per worker thread: T <= 1024
 constexpr int kSelect3RowGroup = 4;                     // rows per 128-bit load of list words
+constexpr int kSelect3ScanThreads = 128;                // threads that scan the histogram
 
 struct Select3Params {
     const uint32_t* __restrict__ seg;      // [T][ld] compact list words from K1 (APPLY_EMIT_COMPACT)
@@ -69,20 +73,22 @@ struct Select3Params {
     int Q;                                 // <= kSelect2QB
     float fx_scale;                        // fixed-point units per unit of weight (the octet headers were built with it)
     int shift1;                            // bucket = rank >> shift1
-    int capw;                              // octets per warp segment of the stage
+    int capw;                              // octets per warp segment of one stage
 };
 
+// shared memory: 2 histograms | 2 tables | slots | 2 stages
 __host__ __device__ inline size_t select3_kernel_smem(int log2nb, int shift1, int capw) {
     const size_t nb = static_cast<size_t>(1) << log2nb;
-    return nb * 4 + (nb * 2 + 16) + static_cast<size_t>(kSelect2QB) * 3 * select2_slots(shift1) * 4 +
-           static_cast<size_t>(kSelect3Warps) * capw * 32;
+    return 2 * nb * 4 + 2 * (nb * 2) + static_cast<size_t>(kSelect2QB) * 3 * select2_slots(shift1) * 4 +
+           2 * static_cast<size_t>(kSelect3Warps) * capw * 32;
 }
 
 __device__ __forceinline__ void cp_async_16(uint32_t dst_shared, const void* src_global) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_shared), "l"(src_global) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
@@ -94,40 +100,52 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
 __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<uint16_t>(v)) : "memory");
 }
-// named barriers: the producer side arrives and goes on, the consumer side waits
-template <int ID>
+// named barriers (PTX bar): the producer side arrives and goes on, the consumer side waits
+template <int ID, int COUNT>
 __device__ __forceinline__ void bar_arrive() {
     __threadfence_block();                              // the shared-memory writes / REDs before it are performed
-    asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(kSelect3Threads) : "memory");
+    asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
 }
-template <int ID>
-__device__ __forceinline__ void bar_wait() {
-    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(kSelect3Threads) : "memory");
+template <int ID, int COUNT>
+__device__ __forceinline__ void bar_sync() {
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
 }
-enum { kBarHist = 1, kBarMarks = 2, kBarSlots = 3 };
+enum { kBarWorkers = 1, kBarMarks = 2, kBarSlots = 3 };
+
+// what the scan hands to the select warp of a percentile (double-buffered by row parity)
+struct Select3Handoff {
+    uint32_t tau, bp, bq, bn, base, total, pad0, pad1;
+};
 
 // rows of a CTA: groups of four consecutive positions, groups blockIdx.x, + gridDim.x, ...
 struct Select3Rows {
     int64_t g, n_groups, n;
     int l;
     __device__ __forceinline__ int64_t pos() const { return g * kSelect3RowGroup + l; }
-    // next row: true = same group; `more` false = this was the CTA's last row
     __device__ __forceinline__ bool next_in_group() const { return l + 1 < kSelect3RowGroup && pos() + 1 < n; }
+    __device__ __forceinline__ bool has_next(unsigned stride) const { return next_in_group() || g + stride < n_groups; }
+    __device__ __forceinline__ void advance(unsigned stride) {
+        if (next_in_group()) { ++l; } else { g += stride; l = 0; }
+    }
 };
 
 template <int LOG2NB, int IPT>
 __global__ void __launch_bounds__(kSelect3Threads, kSelect3CtasPerSm)
 quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileList ql) {
     constexpr int NB = 1 << LOG2NB;
-    constexpr int GB = NB / 32;                         // buckets per scanner lane ("group")
+    constexpr int BPT = NB / kSelect3ScanThreads;       // buckets per scan thread: 16 or 32
     constexpr int QB = kSelect2QB;
+    constexpr int SW = kSelect3ScanThreads / 32;        // scan warps
     constexpr uint32_t NONE = 0xffffffffu;
-    static_assert(GB == 64 || GB == 128, "a group of buckets is scanned as 2 or 4 buckets per lane");
+    static_assert(BPT == 16 || BPT == 32, "a scan thread keeps its buckets' non-empty flags in one 32-bit mask");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* h1 = reinterpret_cast<uint32_t*>(smem_raw);          // [NB] bucket weights (zero between rows)
-    uint32_t* tbl32 = h1 + NB;                                     // [NB] x 16 bits: slot arrays a bucket feeds
-    uint32_t* l2 = tbl32 + NB / 2 + 4;                             // [QB][3][SL] slots: bp | bq | bn (zero between rows)
+    uint32_t* h1 = reinterpret_cast<uint32_t*>(smem_raw);          // [2][NB] bucket weights (zero between uses)
+    uint32_t* tbl32 = h1 + 2 * NB;                                 // [2][NB] x 16 bits: slot arrays a bucket feeds
+    uint32_t* l2 = tbl32 + NB;                                     // [QB][3][SL] slots: bp | bq | bn (zero between rows)
+    __shared__ uint32_t s_red[SW];                      // weight of every scan warp's buckets
+    __shared__ uint32_t s_ne[SW];                       // bit l: scan thread l of the warp has a non-empty bucket
+    __shared__ Select3Handoff s_hand[2][QB];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -139,7 +157,7 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
     const uint32_t l2_s = static_cast<uint32_t>(__cvta_generic_to_shared(l2));
 
     // shared state starts at zero and every row leaves it at zero
-    for (int i = tid; i < NB + NB / 2 + 4 + QB * 3 * SL; i += kSelect3Threads) h1[i] = 0u;
+    for (int i = tid; i < 2 * NB + NB + QB * 3 * SL; i += kSelect3Threads) h1[i] = 0u;
     __syncthreads();
 
     Select3Rows rows;
@@ -154,7 +172,8 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
         const uint32_t capw = static_cast<uint32_t>(p.capw);
         const uint32_t slot_mask = (1u << p.shift1) - 1u;
         const uint32_t bmask = (1u << (24 - p.shift1)) - 1u;       // (m >> shift) & bmask = bucket of a member word
-        const uint32_t stage_s = static_cast<uint32_t>(__cvta_generic_to_shared(l2 + QB * 3 * SL)) + warp * capw * 32u;
+        const uint32_t stage_bytes = kSelect3Warps * capw * 32u;   // one stage
+        const uint32_t stage0_s = static_cast<uint32_t>(__cvta_generic_to_shared(l2 + QB * 3 * SL)) + warp * capw * 32u;
 
         auto load_group = [&](int64_t g, uint4 (&buf)[IPT]) {      // list words of this thread's trees, 4 rows
 #pragma unroll
@@ -167,9 +186,9 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
         };
         auto pick = [](const uint4& v, int l) -> uint32_t { return l == 0 ? v.x : (l == 1 ? v.y : (l == 2 ? v.z : v.w)); };
 
-        // lists of one row -> this warp's stage segment.  Returns the octets of the warp's leaves
+        // lists of one row -> this warp's segment of stage `st`.  Returns the octets of the warp's leaves
         // (warp-uniform); more than capw: nothing was copied and the row is read from global memory.
-        auto issue_copies = [&](const uint32_t (&w)[IPT]) -> uint32_t {
+        auto issue_copies = [&](const uint32_t (&w)[IPT], uint32_t st) -> uint32_t {
             uint32_t no[IPT], tot = 0;
 #pragma unroll
             for (int i = 0; i < IPT; ++i) {
@@ -184,7 +203,7 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
             }
             const uint32_t wtot = __shfl_sync(0xffffffffu, incl, 31);
             if (wtot <= capw) {
-                uint32_t dst = stage_s + (incl - tot) * 32u;
+                uint32_t dst = stage0_s + st * stage_bytes + (incl - tot) * 32u;
 #pragma unroll
                 for (int i = 0; i < IPT; ++i) {
                     const uint4* __restrict__ src = p.lists + 2 * static_cast<size_t>(w[i] & kCompactOffMask);
@@ -194,17 +213,17 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
                     }
                 }
             }
-            cp_async_commit();
             return wtot;
         };
 
         // f(a, b) on every octet of the warp's leaves: from the stage (all lanes busy) or, for an
         // oversized row, every lane on its own lists straight from global memory
-        auto for_each_octet = [&](uint32_t wtot, const uint32_t (&w)[IPT], auto&& f) {
+        auto for_each_octet = [&](uint32_t wtot, const uint32_t (&w)[IPT], uint32_t st, auto&& f) {
             if (wtot <= capw) {
+                const uint32_t base = stage0_s + st * stage_bytes;
                 for (uint32_t j = lane; j < wtot; j += 32u) {
-                    const uint4 a = ld_shared_v4(stage_s + j * 32u);
-                    const uint4 b = ld_shared_v4(stage_s + j * 32u + 16u);
+                    const uint4 a = ld_shared_v4(base + j * 32u);
+                    const uint4 b = ld_shared_v4(base + j * 32u + 16u);
                     f(a, b);
                 }
             } else {
@@ -224,62 +243,175 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
         uint32_t w[IPT];
 #pragma unroll
         for (int i = 0; i < IPT; ++i) w[i] = cur[i].x;
-        uint32_t wtot = issue_copies(w);
+        uint32_t par = 0u;                              // row parity: stage / histogram / table / hand-off in use
+        uint32_t wtot = issue_copies(w, par);
+        cp_async_commit();
 
         for (;;) {
+            // the copies of the NEXT row go out first (its stage was released by this warp's pass 2 of the
+            // row before this one); one commit group per row, empty when there is no next row
+            uint32_t w2[IPT];
+            const bool more = rows.has_next(gridDim.x);
+            const bool same = rows.next_in_group();
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) w2[i] = same ? pick(cur[i], rows.l + 1) : nxt[i].x;
+            uint32_t wtot2 = 0u;
+            if (more) wtot2 = issue_copies(w2, par ^ 1u);          // block-uniform
+            cp_async_commit();
+
             // pass 1: bucket weights (octet header a.x = fixed-point weight of one bootstrap count).
             // w == 0 (utils.py:55-57) cannot occur (counts are >= 1); padding slots are predicated off.
-            cp_async_wait_all();
+            cp_async_wait<1>();                         // everything but the group just committed: this row is in
             __syncwarp();
-            for_each_octet(wtot, w, [&](const uint4& a, const uint4& b) {
+            const uint32_t h_s = h1_s + par * (NB * 4);
+            for_each_octet(wtot, w, par, [&](const uint4& a, const uint4& b) {
                 const uint32_t m[7] = {a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
                 for (int e = 0; e < 7; ++e)
-                    red_add_shared_unless(h1_s + (((m[e] >> shift) & bmask) << 2), (m[e] >> 24) * a.x, m[e] == 0u ? 1u : 0u);
+                    red_add_shared_unless(h_s + (((m[e] >> shift) & bmask) << 2), (m[e] >> 24) * a.x, m[e] == 0u ? 1u : 0u);
             });
-            bar_arrive<kBarHist>();                     // H: this warp's share of the histogram is in
-            bar_wait<kBarMarks>();                      // M: the scanner has marked the buckets of the percentiles
+            bar_sync<kBarWorkers, kSelect3Workers>();   // B1: histogram complete
+
+            // scan: BPT consecutive buckets per thread of the first SW warps, inclusive prefix in registers
+            uint32_t c[BPT], nz = 0u, mine = 0u, incl = 0u;
+            if (warp < SW) {
+#pragma unroll
+                for (int k = 0; k < BPT / 4; ++k) {
+                    const uint4 x = ld_shared_v4(h_s + (tid * BPT + 4 * k) * 4);
+                    c[4 * k] = x.x; c[4 * k + 1] = x.y; c[4 * k + 2] = x.z; c[4 * k + 3] = x.w;
+                }
+#pragma unroll
+                for (int k = 0; k < BPT; ++k) {
+                    mine += c[k];
+                    nz |= (c[k] != 0u ? 1u : 0u) << k;
+                }
+                incl = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += u;
+                }
+                const uint32_t ne = __ballot_sync(0xffffffffu, mine != 0u);
+                if (lane == 31) s_red[warp] = incl;
+                if (lane == 0) s_ne[warp] = ne;
+            }
+            bar_sync<kBarWorkers, kSelect3Workers>();   // B2: partials visible
+            if (warp < SW) {
+                uint32_t run0 = incl - mine, total = 0u;            // running weight before this thread's buckets
+#pragma unroll
+                for (int v = 0; v < SW; ++v) {
+                    const uint32_t x = s_red[v];
+                    run0 += (v < warp) ? x : 0u;
+                    total += x;
+                }
+                if (total != 0u) {
+                    // target running weight of every percentile (lane q of every scan warp, then broadcast)
+                    uint32_t tau_l = 0u;
+                    if (lane < p.Q) {
+                        const double t = ceil(ql.q[lane] * static_cast<double>(total) / 100.0);
+                        tau_l = static_cast<uint32_t>(fmin(fmax(t, 1.0), static_cast<double>(total)));
+                    }
+                    {
+                        uint32_t run = run0;
+#pragma unroll
+                        for (int k = 0; k < BPT; ++k) { run += c[k]; c[k] = run; }
+                    }
+                    for (int q = 0; q < p.Q; ++q) {
+                        const uint32_t tau = __shfl_sync(0xffffffffu, tau_l, q);
+                        if (run0 < tau && tau <= c[BPT - 1]) {      // exactly one thread: bq is one of its own buckets
+                            int k = 0;
+                            uint32_t before = run0;
+#pragma unroll
+                            for (int j = 0; j < BPT - 1; ++j)
+                                if (c[j] < tau) { k = j + 1; before = c[j]; }
+                            const uint32_t bq = static_cast<uint32_t>(tid * BPT + k);
+                            // nearest non-empty buckets: among this thread's own, else in the nearest non-empty
+                            // group of BPT buckets (map s_ne), read from the histogram itself
+                            const uint32_t below = nz & ((1u << k) - 1u);
+                            const uint32_t above = k == 31 ? 0u : (nz >> (k + 1));
+                            uint32_t bp = NONE, bn = NONE;
+                            if (below) {
+                                bp = static_cast<uint32_t>(tid * BPT + 31 - __clz(below));
+                            } else {
+                                int gsel = -1;           // last non-empty group before this thread's
+                                for (int v = SW - 1; v >= 0; --v) {
+                                    uint32_t msk = s_ne[v];
+                                    if (v > warp) msk = 0u;
+                                    else if (v == warp) msk &= (1u << lane) - 1u;
+                                    if (gsel < 0 && msk) gsel = v * 32 + 31 - __clz(msk);
+                                }
+                                if (gsel >= 0) {
+                                    int best = 0;
+                                    for (int j = 0; j < BPT; ++j)
+                                        if (ld_shared_u32(h_s + (gsel * BPT + j) * 4)) best = j;
+                                    bp = static_cast<uint32_t>(gsel * BPT + best);
+                                }
+                            }
+                            if (above) {
+                                bn = static_cast<uint32_t>(tid * BPT + k + __ffs(above));
+                            } else {
+                                int gsel = -1;           // first non-empty group after this thread's
+                                for (int v = 0; v < SW; ++v) {
+                                    uint32_t msk = s_ne[v];
+                                    if (v < warp) msk = 0u;
+                                    else if (v == warp) msk = lane == 31 ? 0u : (msk & ~((2u << lane) - 1u));
+                                    if (gsel < 0 && msk) gsel = v * 32 + __ffs(msk) - 1;
+                                }
+                                if (gsel >= 0) {
+                                    int best = BPT - 1;
+                                    for (int j = BPT - 1; j >= 0; --j)
+                                        if (ld_shared_u32(h_s + (gsel * BPT + j) * 4)) best = j;
+                                    bn = static_cast<uint32_t>(gsel * BPT + best);
+                                }
+                            }
+                            Select3Handoff hd;
+                            hd.tau = tau; hd.bp = bp; hd.bq = bq; hd.bn = bn; hd.base = before; hd.total = total;
+                            hd.pad0 = hd.pad1 = 0u;
+                            s_hand[par][q] = hd;
+                            // which slot arrays the buckets feed: 3 * q + {0, 1, 2}
+                            uint32_t* tb = tbl32 + par * (NB / 2);
+                            atomicOr(&tb[bq >> 1], (2u << (3 * q)) << (16 * (bq & 1)));
+                            if (bp != NONE) atomicOr(&tb[bp >> 1], (1u << (3 * q)) << (16 * (bp & 1)));
+                            if (bn != NONE) atomicOr(&tb[bn >> 1], (4u << (3 * q)) << (16 * (bn & 1)));
+                        }
+                    }
+                } else if (tid < p.Q) {                 // no member with a non-zero weight: cannot happen for a fitted forest
+                    s_hand[par][tid].total = 0u;
+                }
+            }
+            // B3: marks and hand-off visible; the select warps have released the slots of the previous row
+            bar_sync<kBarMarks, kSelect3Threads>();
+            if (warp < SW) {                            // this histogram is used again two rows from now
+#pragma unroll
+                for (int k = 0; k < BPT / 4; ++k) st_shared_v4(h_s + (tid * BPT + 4 * k) * 4, make_uint4(0u, 0u, 0u, 0u));
+            }
 
             // pass 2: members of marked buckets -> slot arrays at single-rank resolution
-            for_each_octet(wtot, w, [&](const uint4& a, const uint4& b) {
+            const uint32_t t_s = tbl_s + par * (NB * 2);
+            for_each_octet(wtot, w, par, [&](const uint4& a, const uint4& b) {
                 const uint32_t m[7] = {a.y, a.z, a.w, b.x, b.y, b.z, b.w};
                 uint32_t code[7], any = 0u;
 #pragma unroll
                 for (int e = 0; e < 7; ++e) {
-                    code[e] = ld_shared_u16(tbl_s + (((m[e] >> shift) & bmask) << 1));
+                    code[e] = ld_shared_u16(t_s + (((m[e] >> shift) & bmask) << 1));
                     any |= code[e];
                 }
                 if (any) {                              // rare: ~50 members of a row's 3300 (padding: weight 0)
 #pragma unroll
                     for (int e = 0; e < 7; ++e) {
-                        uint32_t c = code[e];
+                        uint32_t cd = code[e];
                         const uint32_t wv = (m[e] >> 24) * a.x;
                         const uint32_t dst = l2_s + (m[e] & slot_mask) * 4u;
-                        while (c) {
-                            const int s = __ffs(c) - 1;
-                            c &= c - 1u;
+                        while (cd) {
+                            const int s = __ffs(cd) - 1;
+                            cd &= cd - 1u;
                             red_add_shared(dst + s * SL * 4, wv);
                         }
                     }
                 }
             });
-            __syncwarp();                               // every lane of the warp is done with the stage
-
-            // next row: of this group, or the first one of the CTA's next group
-            uint32_t w2[IPT];
-            bool more = true;
-            const bool same = rows.next_in_group();
-            if (same) {
-#pragma unroll
-                for (int i = 0; i < IPT; ++i) w2[i] = pick(cur[i], rows.l + 1);
-            } else {
-                more = rows.g + gridDim.x < rows.n_groups;
-#pragma unroll
-                for (int i = 0; i < IPT; ++i) w2[i] = nxt[i].x;
-            }
-            uint32_t wtot2 = 0u;
-            if (more) wtot2 = issue_copies(w2);         // block-uniform
-            bar_arrive<kBarSlots>();                    // S: this warp's share of the slots is in
+            __syncwarp();                               // every lane of the warp is done with this stage
+            bar_arrive<kBarSlots, kSelect3Threads>();   // S: this warp's share of the slots is in
             if (!more) break;
             if (same) {
                 ++rows.l;
@@ -291,17 +423,21 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
                 load_group(rows.g + gridDim.x, nxt);
             }
             wtot = wtot2;
+            par ^= 1u;
 #pragma unroll
             for (int i = 0; i < IPT; ++i) w[i] = w2[i];
         }
+        cp_async_wait<0>();
         return;
     }
 
-    // ============================================= scanner =============================================
+    // ========================================= select warps =========================================
+    const int q = warp - kSelect3Warps;                 // this warp's percentile
+    const bool active = q < p.Q;
     const int nch = SL >> 2;                            // 128-bit chunks per slot array
     const int CH = (nch + 31) >> 5;                     // chunks per lane: 1, 2 or 4 (consecutive)
     const float inv = __fdiv_rn(1.0f, p.fx_scale);
-    const uint32_t lt_lane = (1u << lane) - 1u;
+    const uint32_t L_s = l2_s + q * 3 * SL * 4;         // [bp | bq | bn]
 
     // lane L's share of a slot array: chunks [L * CH, L * CH + CH) -> v[], bit i of the result = slot i of the share non-empty
     auto load_share = [&](uint32_t arr_s, uint4 (&v)[4]) -> uint32_t {
@@ -316,140 +452,23 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
         return nm;
     };
     auto slot_of = [&](int ln, int bit) -> uint32_t { return static_cast<uint32_t>(ln * CH * 4 + bit); };
-    // GB buckets of group G spread over the lanes: lane holds buckets G*GB + lane + 32*j, j < GB/32
-    auto load_buckets = [&](uint32_t G, uint32_t (&x)[GB / 32]) {
-#pragma unroll
-        for (int j = 0; j < GB / 32; ++j) x[j] = ld_shared_u32(h1_s + (G * GB + lane + 32 * j) * 4);
-    };
 
+    uint32_t par = 0u;
+    bar_arrive<kBarMarks, kSelect3Threads>();           // the slots are free for the first row
     for (;;) {
         const int64_t pos = rows.pos();
-        const int64_t out_row = p.order ? static_cast<int64_t>(__ldg(p.order + pos)) : pos;
-        double* __restrict__ out = p.out + out_row * p.ldo;
-
-        bar_wait<kBarHist>();                           // H: all eight worker warps have added their members
-
-        // ---- scan: lane sums of GB consecutive buckets, one warp scan
-        uint32_t mine = 0u;
-#pragma unroll
-        for (int k = 0; k < GB / 4; ++k) {
-            const uint4 x = ld_shared_v4(h1_s + (lane * GB + 4 * k) * 4);
-            mine += x.x + x.y + x.z + x.w;
-        }
-        uint32_t incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += u;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        const uint32_t groups = __ballot_sync(0xffffffffu, mine != 0u);       // groups with weight
-
-        // per percentile (kept in lane q after the loop): buckets, running weight before bq, target weight
-        uint32_t k_bp = NONE, k_bq = 0u, k_bn = NONE, k_base = 0u, k_tau = 0u;
-        uint32_t tau_l = 0u;
-        if (total != 0u && lane < p.Q) {
-            const double t = ceil(ql.q[lane] * static_cast<double>(total) / 100.0);
-            tau_l = static_cast<uint32_t>(fmin(fmax(t, 1.0), static_cast<double>(total)));
-        }
-        if (total != 0u) {
-            for (int q = 0; q < p.Q; ++q) {
-                const uint32_t tau = __shfl_sync(0xffffffffu, tau_l, q);
-                const uint32_t own = __ballot_sync(0xffffffffu, incl - mine < tau && tau <= incl);
-                const int G = __ffs(own) - 1;           // exactly one group holds the crossing
-                uint32_t run = __shfl_sync(0xffffffffu, incl - mine, G);      // weight before the group
-                uint32_t x[GB / 32];
-                load_buckets(G, x);
-                // bucket order inside the group: j major, lane minor
-                uint32_t bq = 0u, before = 0u;
-                uint64_t ne = 0ull;                     // non-empty buckets of the group
-#pragma unroll
-                for (int j = 0; j < GB / 32; ++j) {
-                    uint32_t in = x[j];
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t u = __shfl_up_sync(0xffffffffu, in, d);
-                        if (lane >= d) in += u;
-                    }
-                    const uint32_t hit = __ballot_sync(0xffffffffu, run + in - x[j] < tau && tau <= run + in);
-                    if (hit) {                          // warp-uniform
-                        const int ln = __ffs(hit) - 1;
-                        bq = static_cast<uint32_t>(G * GB + 32 * j + ln);
-                        before = __shfl_sync(0xffffffffu, run + in - x[j], ln);
-                    }
-                    const uint32_t nzj = __ballot_sync(0xffffffffu, x[j] != 0u);
-                    if (j < 2) ne |= static_cast<uint64_t>(nzj) << (32 * j);
-                    run += __shfl_sync(0xffffffffu, in, 31);
-                }
-                // nearest non-empty buckets around bq: inside the group (GB == 64: one 64-bit mask; GB == 128:
-                // the second half is looked at below through the general path), else in the nearest non-empty group
-                uint32_t bp = NONE, bn = NONE;
-                const int kq = static_cast<int>(bq) - G * GB;
-                if (GB == 64) {
-                    const uint64_t below = ne & ((1ull << kq) - 1ull);
-                    const uint64_t above = kq == 63 ? 0ull : (ne >> (kq + 1));
-                    if (below) bp = static_cast<uint32_t>(G * GB + 63 - __clzll(static_cast<long long>(below)));
-                    if (above) bn = static_cast<uint32_t>(G * GB + kq + __ffsll(static_cast<long long>(above)));
-                }
-                // general search: last non-empty bucket in [lo_b, bq) / first in (bq, hi_b) of one group
-                auto extreme_in_group = [&](int Gx, bool want_last, int lo_k, int hi_k) -> uint32_t {   // k range [lo_k, hi_k)
-                    uint32_t y[GB / 32];
-                    load_buckets(Gx, y);
-                    uint32_t best = NONE;
-#pragma unroll
-                    for (int j = 0; j < GB / 32; ++j) {
-                        const int k = 32 * j + lane;
-                        const uint32_t m = __ballot_sync(0xffffffffu, y[j] != 0u && k >= lo_k && k < hi_k);
-                        if (m) {
-                            const int ln = want_last ? (31 - __clz(m)) : (__ffs(m) - 1);
-                            const uint32_t cand = static_cast<uint32_t>(Gx * GB + 32 * j + ln);
-                            if (want_last) best = cand;                     // later j = larger bucket
-                            else if (best == NONE) best = cand;
-                        }
-                    }
-                    return best;
-                };
-                if (GB != 64) {
-                    bp = extreme_in_group(G, true, 0, kq);
-                    bn = extreme_in_group(G, false, kq + 1, GB);
-                }
-                if (bp == NONE) {
-                    const uint32_t lower = groups & ((1u << G) - 1u);
-                    if (lower) bp = extreme_in_group(31 - __clz(lower), true, 0, GB);
-                }
-                if (bn == NONE) {
-                    const uint32_t upper = G == 31 ? 0u : (groups >> (G + 1));
-                    if (upper) bn = extreme_in_group(G + __ffs(upper), false, 0, GB);
-                }
-                if (lane == q) { k_bp = bp; k_bq = bq; k_bn = bn; k_base = before; k_tau = tau; }
-                if (lane == 0) {                        // which slot arrays the buckets feed: 3 * q + {0, 1, 2}
-                    const uint32_t a1 = tbl_s + bq * 2u;
-                    st_shared_u16(a1, ld_shared_u16(a1) | (2u << (3 * q)));
-                    if (bp != NONE) {
-                        const uint32_t a0 = tbl_s + bp * 2u;
-                        st_shared_u16(a0, ld_shared_u16(a0) | (1u << (3 * q)));
-                    }
-                    if (bn != NONE) {
-                        const uint32_t a2 = tbl_s + bn * 2u;
-                        st_shared_u16(a2, ld_shared_u16(a2) | (4u << (3 * q)));
-                    }
-                }
-            }
-        }
-        // the histogram goes back to zero
-#pragma unroll
-        for (int k = 0; k < GB / 4; ++k) st_shared_v4(h1_s + (lane * GB + 4 * k) * 4, make_uint4(0u, 0u, 0u, 0u));
-        bar_arrive<kBarMarks>();                        // M
-        bar_wait<kBarSlots>();                          // S: the slot arrays of this row are complete
-
-        // ---- select: crossing entry and its neighbours, one percentile after the other
-        uint32_t k_re = 0u, k_rs = NONE, k_rp = NONE, k_Ce = 0u, k_We = 0u, k_Ws = 0u, k_Wp = 0u;
-        if (total != 0u) {
-            for (int q = 0; q < p.Q; ++q) {
-                const uint32_t bp = __shfl_sync(0xffffffffu, k_bp, q), bq = __shfl_sync(0xffffffffu, k_bq, q);
-                const uint32_t bn = __shfl_sync(0xffffffffu, k_bn, q), tau = __shfl_sync(0xffffffffu, k_tau, q);
-                const uint32_t base = __shfl_sync(0xffffffffu, k_base, q);
-                const uint32_t L_s = l2_s + q * 3 * SL * 4;                    // [bp | bq | bn]
+        const bool more = rows.has_next(gridDim.x);
+        int64_t out_row = pos;
+        if (active && p.order) out_row = static_cast<int64_t>(__ldg(p.order + pos));
+        bar_sync<kBarSlots, kSelect3Threads>();         // S: the slot arrays of this row are complete
+        float result = 0.0f;
+        bool have = false;
+        uint32_t re = 0u, rs = NONE, rp = NONE, Ce = 0u, We = 0u, Ws = 0u, Wp = 0u, total = 0u;
+        if (active) {
+            const Select3Handoff hd = s_hand[par][q];
+            total = hd.total;
+            if (total != 0u) {
+                const uint32_t tau = hd.tau, bp = hd.bp, bq = hd.bq, bn = hd.bn;
                 uint4 v[4];
                 const uint32_t nm = load_share(L_s + SL * 4, v);
                 uint32_t s16 = 0u;
@@ -461,10 +480,10 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
                     const uint32_t u = __shfl_up_sync(0xffffffffu, in, d);
                     if (lane >= d) in += u;
                 }
-                const uint32_t b0 = base + in - s16;
+                const uint32_t b0 = hd.base + in - s16;
                 const uint32_t who = __ballot_sync(0xffffffffu, b0 < tau && tau <= b0 + s16);
                 const int lc = __ffs(who) - 1;          // exactly one lane (base < tau <= weight up to bq)
-                uint32_t e_bit = 0u, We = 0u, Ce = 0u;
+                uint32_t e_bit = 0u;
                 if (lane == lc) {
                     const uint32_t vv[16] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w,
                                              v[2].x, v[2].y, v[2].z, v[2].w, v[3].x, v[3].y, v[3].z, v[3].w};
@@ -492,7 +511,7 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
                         const int lp = 31 - __clz(lower);
                         pin = slot_of(lp, 31 - __clz(__shfl_sync(0xffffffffu, nm, lp)));
                     }
-                    const uint32_t above = e_bit == 31 ? 0u : (nm_c >> (e_bit + 1));
+                    const uint32_t above = nm_c >> (e_bit + 1);
                     const uint32_t upper = lc == 31 ? 0u : (lanes_ne >> (lc + 1));
                     if (above) sin = slot_of(lc, e_bit + __ffs(above));
                     else if (upper) {
@@ -515,7 +534,6 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
                         wgt = ld_shared_u32(L_s + (which * SL + slot) * 4);
                     }
                 };
-                uint32_t rp = NONE, rs = NONE, Wp = 0u, Ws = 0u;            // ranks and merged weights of pred / succ
                 if (pin != NONE) {
                     rp = (bq << shift) + pin;
                     Wp = ld_shared_u32(L_s + (SL + pin) * 4);
@@ -532,61 +550,57 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
                     extreme_slot(2, false, sl, Ws);
                     if (sl != NONE) rs = (bn << shift) + sl;
                 }
-                if (lane == q) {
-                    k_re = (bq << shift) + e; k_rs = rs; k_rp = rp;
-                    k_Ce = Ce; k_We = We; k_Ws = Ws; k_Wp = Wp;
+                re = (bq << shift) + e;
+                have = true;
+                __syncwarp();
+                // slots and table entries of this percentile back to zero
+                for (int ch = lane; ch < 3 * nch; ch += 32) st_shared_v4(L_s + ch * 16, make_uint4(0u, 0u, 0u, 0u));
+                if (lane == 0) {
+                    const uint32_t t_s = tbl_s + par * (NB * 2);
+                    st_shared_u16(t_s + bq * 2u, 0u);
+                    if (bp != NONE) st_shared_u16(t_s + bp * 2u, 0u);
+                    if (bn != NONE) st_shared_u16(t_s + bn * 2u, 0u);
                 }
             }
-            __syncwarp();
-            // slots and table back to zero
-            for (int ch = lane; ch < p.Q * 3 * nch; ch += 32) st_shared_v4(l2_s + ch * 16, make_uint4(0u, 0u, 0u, 0u));
-            if (lane < p.Q) {
-                st_shared_u16(tbl_s + k_bq * 2u, 0u);
-                if (k_bp != NONE) st_shared_u16(tbl_s + k_bp * 2u, 0u);
-                if (k_bn != NONE) st_shared_u16(tbl_s + k_bn * 2u, 0u);
-            }
         }
+        // the slots are free again: the workers may start pass 2 of the next row
+        if (more) bar_arrive<kBarMarks, kSelect3Threads>();
 
-        // ---- utils.py:69-81 on (pred, e, succ), float32; lane q takes percentile q
-        if (lane < p.Q) {
-            if (total == 0u) {                          // no member with a non-zero weight: cannot happen for a fitted forest
-                out[lane] = __longlong_as_double(0x7ff8000000000000LL);
+        // ---- utils.py:69-81 on (pred, e, succ), float32
+        if (active && lane == 0) {
+            double* __restrict__ out = p.out + out_row * p.ldo;
+            if (!have) {
+                out[q] = __longlong_as_double(0x7ff8000000000000LL);
             } else {
-                const double qv = ql.q[lane];
+                const double qv = ql.q[q];
                 const float s = __fdiv_rn(100.0f, __fmul_rn(static_cast<float>(total), inv));         // utils.py:69,72
                 // the three candidate values are requested together (one HBM latency, not two)
-                const float a_e = __ldg(p.y_sorted + k_re);
-                const float a_s = __ldg(p.y_sorted + (k_rs != NONE ? k_rs : k_re));
-                const float a_p = __ldg(p.y_sorted + (k_rp != NONE ? k_rp : k_re));
-                const float p_e = plotting_position(s, __fmul_rn(static_cast<float>(k_Ce), inv),
-                                                    __fmul_rn(static_cast<float>(k_We), inv));
-                float result = a_e;
+                const float a_e = __ldg(p.y_sorted + re);
+                const float a_s = __ldg(p.y_sorted + (rs != NONE ? rs : re));
+                const float a_p = __ldg(p.y_sorted + (rp != NONE ? rp : re));
+                const float p_e = plotting_position(s, __fmul_rn(static_cast<float>(Ce), inv),
+                                                    __fmul_rn(static_cast<float>(We), inv));
+                result = a_e;
                 if (static_cast<double>(p_e) < qv) {                        // interval (e, succ)
-                    if (k_rs != NONE) {                 // else q lies beyond the last entry: a_last (utils.py:74-75)
-                        const float p_s = plotting_position(s, __fmul_rn(static_cast<float>(k_Ce + k_Ws), inv),
-                                                            __fmul_rn(static_cast<float>(k_Ws), inv));
+                    if (rs != NONE) {                   // else q lies beyond the last entry: a_last (utils.py:74-75)
+                        const float p_s = plotting_position(s, __fmul_rn(static_cast<float>(Ce + Ws), inv),
+                                                            __fmul_rn(static_cast<float>(Ws), inv));
                         const float frac = __fdiv_rn(__fsub_rn(static_cast<float>(qv), p_e), __fsub_rn(p_s, p_e));
                         result = __fadd_rn(a_e, __fmul_rn(frac, __fsub_rn(a_s, a_e)));
                     }
-                } else if (k_rp != NONE) {              // interval (pred, e); else before the first entry: a_0 (utils.py:76-77)
-                    const float p_p = plotting_position(s, __fmul_rn(static_cast<float>(k_Ce - k_We), inv),
-                                                        __fmul_rn(static_cast<float>(k_Wp), inv));
+                } else if (rp != NONE) {                // interval (pred, e); else before the first entry: a_0 (utils.py:76-77)
+                    const float p_p = plotting_position(s, __fmul_rn(static_cast<float>(Ce - We), inv),
+                                                        __fmul_rn(static_cast<float>(Wp), inv));
                     const float frac = __fdiv_rn(__fsub_rn(static_cast<float>(qv), p_p), __fsub_rn(p_e, p_p));
                     result = __fadd_rn(a_p, __fmul_rn(frac, __fsub_rn(a_e, a_p)));
                 }
-                out[lane] = static_cast<double>(result);
+                out[q] = static_cast<double>(result);
             }
         }
         __syncwarp();
-
-        // same row sequence as the workers
-        if (rows.next_in_group()) {
-            ++rows.l;
-        } else {
-            rows.g += gridDim.x;
-            rows.l = 0;
-            if (rows.g >= rows.n_groups) break;
-        }
+        if (!more) break;
+        rows.advance(gridDim.x);
+        par ^= 1u;
     }
 }
 

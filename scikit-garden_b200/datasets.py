@@ -18,6 +18,16 @@ CONFIGS = {
     "c4": dict(kind="rf", n_estimators=200, min_samples_leaf=1, n_train=1_000_000, n_test=1_000_000,
                n_features=20, quantiles=[float(q) for q in range(1, 100)],
                label="RFQR T=200 msl=1 bootstrap, 1M x 20 train, 1M test rows, q=1..99"),
+    # configs[3] stress variant (hard part 6): depth-10 trees, leaves of ~1000 members,
+    # ~125k members per row -- genuinely large candidate sets (exact kernels: dense fallback)
+    "c4_depth10": dict(kind="rf", n_estimators=200, min_samples_leaf=1, max_depth=10, n_train=1_000_000,
+                       n_test=20_000, n_features=20, quantiles=[5.0, 50.0, 95.0],
+                       label="RFQR T=200 max_depth=10 bootstrap, 1M x 20 train, 20k test rows, q={5,50,95} (large candidate sets)"),
+    # configs[4]: streamed test rows (bench.py keeps the 10M x 64 rows in one pinned host array and streams
+    # them through the host-buffer call; tools/bench_stream.py streams chunks through predict_stream)
+    "c5": dict(kind="et", n_estimators=1000, min_samples_leaf=5, n_train=1_000_000, n_test=10_000_000,
+               n_features=64, quantiles=[5.0, 50.0, 95.0],
+               label="ETQR T=1000 msl=5 bootstrap, 1M x 64 train, 10M streamed test rows, q={5,50,95}"),
     # reduced-size stand-ins used by tests and quick runs (NOT bench lines)
     "c2_small": dict(kind="rf", n_estimators=20, min_samples_leaf=1, n_train=20_000, n_test=20_000,
                      n_features=20, quantiles=[5.0, 50.0, 95.0], label="C2 at 1/5 scale"),

@@ -115,7 +115,9 @@ def test_select3_more_than_a_million_training_rows():
     qs = [0, 50, 100]
     exact = est.predict(Xt, quantile=qs)
     est.mode = "fast"
-    assert dev.quantile_kernel_name(len(Xt), 3, FAST) == "quantile_select3_kernel<12, 1>"
+    from skgarden_b200 import _native
+    name = dev.quantile_kernel_name(len(Xt), 3, FAST)
+    assert name == "quantile_select3_kernel<12, 1>", (name, _native.last_error())
     fast = est.predict(Xt, quantile=qs)
     assert_allclose(fast, exact, rtol=1e-4, atol=1e-4 * np.abs(ytr).max())
     assert_array_equal(fast[:, [0, -1]], exact[:, [0, -1]])
@@ -244,3 +246,29 @@ def test_more_features_than_the_shared_memory_tile():
     index = O.SparseIndex(est.y_train_, est.y_train_leaves_, est.y_weights_, est._flat.sorter)
     assert_array_equal(est.predict(Xt, quantile=[10, 50, 90]), O.predict_sparse(index, leaves, [10, 50, 90]))
     assert_array_equal(est.predict(Xt), O.predict_mean(est.estimators_, Xt, leaves))
+
+
+def test_devices_list_shards_rows_over_replicas():
+    # devices=[...]: forest replicated, rows of every call sharded, one host thread per GPU; the
+    # result does not depend on the split (ensemble.py:137: rows are independent).  Uses two GPUs
+    # when the box has them, else the one GPU as a single replica.
+    import skgarden_b200 as sg
+    n_dev = torch.cuda.device_count()
+    devs = [0, 1] if n_dev >= 2 else [0]
+    Xtr, ytr, Xt = _atsize.make_data(5000, 3001, 6, seed=5)
+    kw = dict(n_estimators=20, min_samples_leaf=4, random_state=0, n_jobs=-1)
+    one = sg.ExtraTreesQuantileRegressor(**kw).fit(Xtr, ytr)
+    many = sg.ExtraTreesQuantileRegressor(devices=devs, **kw).fit(Xtr, ytr)
+    qs = [5, 50, 95]
+    assert_array_equal(many.predict(Xt, quantile=qs), one.predict(Xt, quantile=qs))
+    assert_array_equal(many.predict(Xt), one.predict(Xt))
+    assert_array_equal(many.apply(Xt), one.apply(Xt))
+    chunks = [Xt[:1], Xt[1:700], Xt[700:700], Xt[700:2000], Xt[2000:]]
+    got = np.concatenate(list(many.predict_stream(chunks, qs)))
+    assert_array_equal(got, one.predict(Xt, quantile=qs))
+    std_one = sg.RandomForestRegressor(n_estimators=8, random_state=0, min_samples_leaf=3).fit(Xtr, ytr)
+    std_many = sg.RandomForestRegressor(n_estimators=8, random_state=0, min_samples_leaf=3, devices=devs).fit(Xtr, ytr)
+    m1, s1 = std_one.predict(Xt, return_std=True)
+    m2, s2 = std_many.predict(Xt, return_std=True)
+    assert_array_equal(m1, m2)
+    assert_array_equal(s1, s2)

@@ -1,6 +1,6 @@
 #!/bin/bash
-# Round 2, pass C: warp-specialised select3: tests, C3 bench (fast only), ncu of one step.
-tag=${1:-r2_c}
+# Round 2, pass D: warp-specialised select3: tests, C3 bench (fast only), ncu of one step.
+tag=${1:-r2_d}
 out=gpurun_out
 mkdir -p $out
 set -x
