@@ -10,16 +10,19 @@
 //       U  = rn(fx_scale / s), s = leaf count sum: the 32-bit fixed-point weight of ONE bootstrap count
 //            of this leaf (fx_scale = 2^(31-k) units per unit of weight, 2^k > the largest total weight
 //            a row can gather), so that a member weighs count * U -- one integer multiply
-//       m  = rank (bits 0..23) | bootstrap count (bits 24..31); 0 = padding
+//       m  = rank (bits 0..23) | bootstrap count (bits 24..31); padding = count 0 with an arbitrary rank
 //   a leaf of c members owns ceil(c / 7) consecutive octets, every one with the header, so that an
 //   octet can be processed without its neighbours (any lane can take any octet).
 //   The builder recovers (s, counts) from the stored float32 weights and verifies
-//   __fdiv_rn(count, s) == weight bit for bit for every member; a forest for which that fails (or
-//   with leaves of more than 112 members) is "not compactable" and the 8-byte kernels stay in charge.
+//   __fdiv_rn(count, s) == weight bit for bit for every member; a forest for which that fails is
+//   "not compactable" and the 8-byte kernels stay in charge.
 //
 // The walk kernel runs on a COPY of the node array whose leaves carry, in lo32, the compact list
 // word `first octet | (octets - 1) << 28` (0xffffffff: a leaf without in-bag members); K1 emits
-// that word (APPLY_EMIT_COMPACT) and K2 needs nothing else to find a leaf's members.
+// that word (APPLY_EMIT_COMPACT) and K2 needs nothing else to find a leaf's members.  A leaf of more
+// than 15 octets (105 members) is a LONG list: the 4-bit field holds 15 and `first octet` is an info
+// octet whose first word is the number of member octets that follow it (K2 reads such a list straight
+// from global memory; rare, and forests made of such leaves take the exact kernels anyway).
 // A row of config 3 then reads ~650 octets = 21 KB in whole sectors instead of 26 KB + straddle.
 #pragma once
 #include <cstdint>
@@ -29,7 +32,8 @@ namespace qf {
 
 constexpr uint32_t kCompactEmpty = 0xffffffffu;
 constexpr int kOctetMembers = 7;
-constexpr int kCompactMaxOctets = 16;                   // (octets - 1) lives in 4 bits
+constexpr int kCompactMaxOctets = 15;                   // (octets - 1) lives in 4 bits; 15 there = long list (below)
+constexpr uint32_t kCompactLong = 15u;
 constexpr uint32_t kCompactOffMask = 0x0fffffffu;       // first octet: 28 bits (8 GB of lists)
 constexpr int kCompactScanTile = 4096;                  // items per scan block (256 threads x 16)
 
@@ -56,7 +60,7 @@ __device__ inline uint32_t leaf_count_sum(const uint2* __restrict__ m, uint32_t 
 }
 
 // pass 1: octets of every leaf, keyed by the leaf's first member (unique per non-empty leaf);
-// flags: 1 = a leaf is longer than 7 * 16 members, 2 = weights are not count / sum, 4 = rank >= 2^24
+// flags: 2 = weights are not count / sum, 4 = rank >= 2^24
 __global__ void __launch_bounds__(256)
 compact_mark_kernel(const uint2* __restrict__ nodes, int64_t n_nodes, const uint2* __restrict__ members,
                     uint32_t* __restrict__ noct_at, int* __restrict__ flags) {
@@ -66,10 +70,10 @@ compact_mark_kernel(const uint2* __restrict__ nodes, int64_t n_nodes, const uint
     if (!(nd.y & 0x80000000u)) return;
     const uint32_t cnt = nd.y & 0x7fffffffu;
     if (cnt == 0u) return;
-    if (cnt > static_cast<uint32_t>(kOctetMembers * kCompactMaxOctets)) { atomicOr(flags, 1); return; }
     if (leaf_count_sum(members + nd.x, cnt) == 0u) { atomicOr(flags, 2); return; }
     if (members[nd.x + cnt - 1].x >= (1u << 24)) { atomicOr(flags, 4); return; }   // lists are sorted by rank
-    noct_at[nd.x] = (cnt + kOctetMembers - 1) / kOctetMembers;
+    const uint32_t noct = (cnt + kOctetMembers - 1) / kOctetMembers;
+    noct_at[nd.x] = noct > static_cast<uint32_t>(kCompactMaxOctets) ? noct + 1u : noct;    // long list: + the info octet
 }
 
 // in-place exclusive scan of a uint32 array in three launches: tile sums, scan of the tile
@@ -159,8 +163,8 @@ scan_apply_kernel(uint32_t* __restrict__ data, int64_t n, const uint64_t* __rest
 // pass 1's octet counts: first octet of the leaf whose first member is nd.x)
 __global__ void __launch_bounds__(256)
 compact_fill_kernel(const uint2* __restrict__ nodes, int64_t n_nodes, const uint2* __restrict__ members,
-                    const uint32_t* __restrict__ oct_at, float fx_scale, uint2* __restrict__ nodes_c,
-                    uint4* __restrict__ lists) {
+                    const uint32_t* __restrict__ oct_at, float fx_scale, uint32_t n_train,
+                    uint2* __restrict__ nodes_c, uint4* __restrict__ lists) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
     uint2 nd = nodes[i];
@@ -172,15 +176,24 @@ compact_fill_kernel(const uint2* __restrict__ nodes, int64_t n_nodes, const uint
             const uint2* __restrict__ m = members + nd.x;
             const uint32_t s = leaf_count_sum(m, cnt);
             const float sf = static_cast<float>(s);
-            const uint32_t first = oct_at[nd.x];
+            uint32_t first = oct_at[nd.x];
             const uint32_t noct = (cnt + kOctetMembers - 1) / kOctetMembers;
+            const bool is_long = noct > static_cast<uint32_t>(kCompactMaxOctets);
+            const uint32_t word = first | ((is_long ? kCompactLong : noct - 1u) << 28);
+            if (is_long) {                              // info octet, then the member octets
+                lists[2 * static_cast<size_t>(first)] = make_uint4(noct, 0u, 0u, 0u);
+                lists[2 * static_cast<size_t>(first) + 1] = make_uint4(0u, 0u, 0u, 0u);
+                ++first;
+            }
             for (uint32_t j = 0; j < noct; ++j) {
                 uint32_t w[8];
                 w[0] = __float2uint_rn(__fdiv_rn(fx_scale, sf));    // fixed-point weight of one bootstrap count
 #pragma unroll
                 for (int e = 0; e < kOctetMembers; ++e) {
                     const uint32_t k = j * kOctetMembers + e;
-                    w[e + 1] = 0u;
+                    // padding: count 0 (weight zero) and a pseudo-random rank below n_train, so that the slots
+                    // of a warp's 32 octets do not all add their zero to the same histogram bucket
+                    w[e + 1] = static_cast<uint32_t>((static_cast<uint64_t>((first + j) * 7u + e) * 2654435761ull >> 8) % n_train);
                     if (k < cnt) {
                         const uint2 x = m[k];
                         const uint32_t c = static_cast<uint32_t>(rintf(__fmul_rn(__uint_as_float(x.y), sf)));
@@ -190,7 +203,7 @@ compact_fill_kernel(const uint2* __restrict__ nodes, int64_t n_nodes, const uint
                 lists[2 * static_cast<size_t>(first + j)] = make_uint4(w[0], w[1], w[2], w[3]);
                 lists[2 * static_cast<size_t>(first + j) + 1] = make_uint4(w[4], w[5], w[6], w[7]);
             }
-            nd.x = first | ((noct - 1u) << 28);
+            nd.x = word;
         }
     }
     nodes_c[i] = nd;

@@ -507,8 +507,8 @@ int ensure_compact(qf_forest* f) {
     QF_CUDA_TRY(cudaMemcpy(&n_octets, tile_sum + n_tiles, 8, cudaMemcpyDeviceToHost));
     if (h_flags != 0 || n_octets == 0 || n_octets > qf::kCompactOffMask) {               // not compactable
         char why[160];
-        std::snprintf(why, sizeof(why), "compact leaf lists not built: flags %d (1 leaf > 112 members, 2 weights are not "
-                      "count / sum, 4 rank >= 2^24), %llu octets", h_flags, static_cast<unsigned long long>(n_octets));
+        std::snprintf(why, sizeof(why), "compact leaf lists not built: flags %d (2 weights are not count / sum, "
+                      "4 rank >= 2^24), %llu octets", h_flags, static_cast<unsigned long long>(n_octets));
         qf::last_error_slot() = why;                    // informational: the 8-byte kernels take over
         return QF_OK;
     }
@@ -518,7 +518,7 @@ int ensure_compact(qf_forest* f) {
     cudaError_t e = cudaMalloc(&nodes_c, static_cast<size_t>(f->n_nodes) * 8);
     if (e == cudaSuccess) e = cudaMalloc(&lists, static_cast<size_t>(n_octets) * 32);
     if (e == cudaSuccess) {
-        qf::compact_fill_kernel<<<node_blocks, 256>>>(f->d_nodes, f->n_nodes, f->d_members, oct_at, fx_scale, nodes_c, lists);
+        qf::compact_fill_kernel<<<node_blocks, 256>>>(f->d_nodes, f->n_nodes, f->d_members, oct_at, fx_scale, static_cast<uint32_t>(f->N), nodes_c, lists);
         qf::compact_tree_stats_kernel<<<f->T, 256>>>(f->d_nodes, f->d_roots, f->n_nodes, f->T, stats);
         e = cudaGetLastError();
     }

@@ -29,15 +29,15 @@
 //            exceed the segment is read from global memory directly (same code, synchronous loads).
 //   pass 1   the warp waits for ITS OWN copies (wait_group + __syncwarp: no block barrier) and walks
 //            its segment octet by octet, all lanes busy whatever the leaf sizes: seven members -> one
-//            predicated shared-memory RED each into the NB-bucket histogram.
+//            shared-memory RED each into the NB-bucket histogram (padding slots add zero).
 //   scan     4 warps x 16 buckets per thread in registers, one warp scan + 4 partials; the thread
 //            that finds a percentile's crossing bucket bq among its own looks for the nearest
 //            non-empty neighbours bp / bn in its registers or, through a 128-bit map of non-empty
 //            16-bucket groups, in one other group of the (not yet cleared) histogram.  A 16-bit table
 //            says which slot arrays a bucket feeds.
 //   pass 2   second walk over the staged octets: the seven table lookups of an octet are issued
-//            together and tested with one branch; the ~50 members of marked buckets are added at
-//            single-rank resolution to the slot arrays [bp | bq | bn] of their percentile(s).
+//            together; the ~50 members of marked buckets are added at single-rank resolution to the
+//            slot arrays [bp | bq | bn] of their percentile(s).
 //   select   one warp per percentile: crossing entry e in bq's slots, its neighbours inside bq or,
 //            failing that, the largest rank of bp / the smallest rank of bn; lane 0 interpolates.
 //   Histogram and table are double-buffered by row parity, so that clearing them never races with
@@ -193,6 +193,7 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
 #pragma unroll
             for (int i = 0; i < IPT; ++i) {
                 no[i] = (w[i] == kCompactEmpty) ? 0u : ((w[i] >> 28) + 1u);
+                if (no[i] > static_cast<uint32_t>(kCompactMaxOctets)) no[i] = 1u << 20;   // long list: never staged
                 tot += no[i];
             }
             uint32_t incl = tot;
@@ -203,13 +204,17 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
             }
             const uint32_t wtot = __shfl_sync(0xffffffffu, incl, 31);
             if (wtot <= capw) {
-                uint32_t dst = stage0_s + st * stage_bytes + (incl - tot) * 32u;
+                const uint32_t seg_s = stage0_s + st * stage_bytes;
+                uint32_t rel = (incl - tot) * 32u;                         // byte offset of this lane's first octet
 #pragma unroll
                 for (int i = 0; i < IPT; ++i) {
                     const uint4* __restrict__ src = p.lists + 2 * static_cast<size_t>(w[i] & kCompactOffMask);
-                    for (uint32_t k = 0; k < no[i]; ++k, dst += 32u) {
-                        cp_async_16(dst, src + 2 * k);
-                        cp_async_16(dst + 16u, src + 2 * k + 1);
+                    // octet j of the segment keeps its halves swapped when bit 2 of j is set: the 128-bit reads of
+                    // eight consecutive lanes then fall into eight different 16-byte bank groups
+                    for (uint32_t k = 0; k < no[i]; ++k, rel += 32u) {
+                        const uint32_t sw = (rel >> 3) & 16u;              // bit 2 of the octet index
+                        cp_async_16(seg_s + rel + sw, src + 2 * k);
+                        cp_async_16(seg_s + rel + (sw ^ 16u), src + 2 * k + 1);
                     }
                 }
             }
@@ -221,9 +226,10 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
         auto for_each_octet = [&](uint32_t wtot, const uint32_t (&w)[IPT], uint32_t st, auto&& f) {
             if (wtot <= capw) {
                 const uint32_t base = stage0_s + st * stage_bytes;
+                const uint32_t sw = (static_cast<uint32_t>(lane) << 2) & 16u;   // bit 2 of j = bit 2 of the lane
                 for (uint32_t j = lane; j < wtot; j += 32u) {
-                    const uint4 a = ld_shared_v4(base + j * 32u);
-                    const uint4 b = ld_shared_v4(base + j * 32u + 16u);
+                    const uint4 a = ld_shared_v4(base + j * 32u + sw);
+                    const uint4 b = ld_shared_v4(base + j * 32u + (sw ^ 16u));
                     f(a, b);
                 }
             } else {
@@ -231,7 +237,11 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
                 for (int i = 0; i < IPT; ++i) {
                     if (w[i] == kCompactEmpty) continue;
                     const uint4* __restrict__ src = p.lists + 2 * static_cast<size_t>(w[i] & kCompactOffMask);
-                    const uint32_t no = (w[i] >> 28) + 1u;
+                    uint32_t no = (w[i] >> 28) + 1u;
+                    if (no > static_cast<uint32_t>(kCompactMaxOctets)) {   // long list: info octet first
+                        no = __ldg(src).x;
+                        src += 2;
+                    }
                     for (uint32_t k = 0; k < no; ++k) f(__ldg(src + 2 * k), __ldg(src + 2 * k + 1));
                 }
             }
@@ -260,7 +270,8 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
             cp_async_commit();
 
             // pass 1: bucket weights (octet header a.x = fixed-point weight of one bootstrap count).
-            // w == 0 (utils.py:55-57) cannot occur (counts are >= 1); padding slots are predicated off.
+            // w == 0 (utils.py:55-57) cannot occur for a member (counts are >= 1); padding slots carry count 0
+            // and a pseudo-random rank (compact_lists.cuh): they add zero to some bucket, no predicate, no branch.
             cp_async_wait<1>();                         // everything but the group just committed: this row is in
             __syncwarp();
             const uint32_t h_s = h1_s + par * (NB * 4);
@@ -268,7 +279,7 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
                 const uint32_t m[7] = {a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
                 for (int e = 0; e < 7; ++e)
-                    red_add_shared_unless(h_s + (((m[e] >> shift) & bmask) << 2), (m[e] >> 24) * a.x, m[e] == 0u ? 1u : 0u);
+                    red_add_shared(h_s + (((m[e] >> shift) & bmask) << 2), (m[e] >> 24) * a.x);
             });
             bar_sync<kBarWorkers, kSelect3Workers>();   // B1: histogram complete
 
@@ -390,23 +401,20 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
             const uint32_t t_s = tbl_s + par * (NB * 2);
             for_each_octet(wtot, w, par, [&](const uint4& a, const uint4& b) {
                 const uint32_t m[7] = {a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-                uint32_t code[7], any = 0u;
+                uint32_t code[7];
+#pragma unroll
+                for (int e = 0; e < 7; ++e) code[e] = ld_shared_u16(t_s + (((m[e] >> shift) & bmask) << 1));   // issued together
 #pragma unroll
                 for (int e = 0; e < 7; ++e) {
-                    code[e] = ld_shared_u16(t_s + (((m[e] >> shift) & bmask) << 1));
-                    any |= code[e];
-                }
-                if (any) {                              // rare: ~50 members of a row's 3300 (padding: weight 0)
-#pragma unroll
-                    for (int e = 0; e < 7; ++e) {
-                        uint32_t cd = code[e];
+                    uint32_t cd = code[e];
+                    if (cd) {                           // ~50 members of a row's 3300 (a padding slot adds zero)
                         const uint32_t wv = (m[e] >> 24) * a.x;
                         const uint32_t dst = l2_s + (m[e] & slot_mask) * 4u;
-                        while (cd) {
+                        do {
                             const int s = __ffs(cd) - 1;
                             cd &= cd - 1u;
                             red_add_shared(dst + s * SL * 4, wv);
-                        }
+                        } while (cd);
                     }
                 }
             });

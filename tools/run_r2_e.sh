@@ -1,6 +1,6 @@
 #!/bin/bash
-# Round 2, pass D: warp-specialised select3: tests, C3 bench (fast only), ncu of one step.
-tag=${1:-r2_d}
+# Round 2, pass E: warp-specialised select3: tests, C3 bench (fast only), ncu of one step.
+tag=${1:-r2_e}
 out=gpurun_out
 mkdir -p $out
 set -x
