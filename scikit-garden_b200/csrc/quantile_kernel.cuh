@@ -419,8 +419,8 @@ __device__ __forceinline__ void gather_members(const uint2* __restrict__ members
 //
 //   1. gather the (rank, weight) pairs in tree order: rk[pos], wt[pos]; block min / max of
 //      the ranks gives the row's rank window [rmin, rmin + range]
-//   2. counting sort by bucket = (rank - rmin) >> shift with B = 8 * THREADS buckets
-//      (about two members per bucket): integer shared-memory atomics for the histogram
+//   2. counting sort by bucket = (rank - rmin) >> shift with B = 16 * THREADS buckets
+//      (less than one member per bucket on average, a few in the dense centre of the row's rank window): integer shared-memory atomics for the histogram
 //      and for the slots (ATOMS ~16 lanes/clk/SM measured, tools/microbench), one block
 //      scan in between.  An entry is the 32-bit word (low rank bits << POSBITS) | pos.
 //   3. order inside a bucket: every entry counts the smaller entries of its bucket
@@ -439,17 +439,19 @@ __host__ __device__ constexpr int bucket_kernel_capacity(int threads) { return t
 
 __host__ __device__ inline size_t bucket_kernel_smem(int threads, int T) {
     const size_t cap = static_cast<size_t>(bucket_kernel_capacity(threads));
-    return cap * 12 + (cap / 2 + 8) * 4 + static_cast<size_t>(2 * T + 1) * 4 + 16;
+    return cap * 12 + (cap + 8) * 4 + static_cast<size_t>(2 * T + 1) * 4 + 16;
 }
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 256) ? 768 / THREADS : 1)
 quantile_bucket_kernel(const QuantileParams p, const __grid_constant__ QuantileList ql) {
     constexpr int CAP = THREADS * kBucketEPT;
-    constexpr int NB = CAP / 2;                         // buckets
+    // one bucket per capacity slot: the members of a row crowd into a fraction of its rank window
+    // (ncu r2_a: with CAP / 2 buckets the in-bucket ordering of step 3 was 45 % of all instructions)
+    constexpr int NB = CAP;                             // buckets
     constexpr int NW = THREADS / 32;
     constexpr int POSBITS = (THREADS == 64) ? 10 : (THREADS == 128) ? 11 : (THREADS == 256) ? 12 : 13;
-    constexpr int LOG2NB = POSBITS - 1;
+    constexpr int LOG2NB = POSBITS;
     constexpr uint32_t POSMASK = CAP - 1;
     static_assert(THREADS == 64 || THREADS == 128 || THREADS == 256 || THREADS == 512, "unsupported block size");
     static_assert((1 << POSBITS) == CAP, "POSBITS must be log2 of the capacity");
@@ -516,11 +518,16 @@ quantile_bucket_kernel(const QuantileParams p, const __grid_constant__ QuantileL
     // 2a. bucket populations
     for (uint32_t i = tid; i < P; i += THREADS) atomicAdd(&cnt[(rk[i] - rmin) >> shift], 1u);
     __syncthreads();
-    // 2b. exclusive scan of the NB = 8 * THREADS populations (8 consecutive per thread)
+    // 2b. exclusive scan of the NB = 16 * THREADS populations (16 consecutive per thread)
     {
-        uint4 c0 = reinterpret_cast<uint4*>(cnt)[2 * tid];
-        uint4 c1 = reinterpret_cast<uint4*>(cnt)[2 * tid + 1];
-        const uint32_t total = c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w;
+        constexpr int C4 = NB / THREADS / 4;            // 128-bit chunks per thread
+        uint4 c[C4];
+        uint32_t total = 0;
+#pragma unroll
+        for (int k = 0; k < C4; ++k) {
+            c[k] = reinterpret_cast<uint4*>(cnt)[C4 * tid + k];
+            total += c[k].x + c[k].y + c[k].z + c[k].w;
+        }
         uint32_t incl = total;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -533,11 +540,12 @@ quantile_bucket_kernel(const QuantileParams p, const __grid_constant__ QuantileL
 #pragma unroll
         for (int w = 0; w < NW; ++w) before += (w < warp) ? s_red[w] : 0u;
         uint32_t run = before + incl - total;
-        uint4 o0, o1;
-        o0.x = run; run += c0.x; o0.y = run; run += c0.y; o0.z = run; run += c0.z; o0.w = run; run += c0.w;
-        o1.x = run; run += c1.x; o1.y = run; run += c1.y; o1.z = run; run += c1.z; o1.w = run;
-        reinterpret_cast<uint4*>(cnt)[2 * tid] = o0;
-        reinterpret_cast<uint4*>(cnt)[2 * tid + 1] = o1;
+#pragma unroll
+        for (int k = 0; k < C4; ++k) {
+            uint4 o;
+            o.x = run; run += c[k].x; o.y = run; run += c[k].y; o.z = run; run += c[k].z; o.w = run; run += c[k].w;
+            reinterpret_cast<uint4*>(cnt)[C4 * tid + k] = o;
+        }
     }
     __syncthreads();
     // 2c. slots: afterwards cnt[b] is the END of bucket b (= start of bucket b + 1).
