@@ -90,8 +90,9 @@ struct qf_forest {
     int cta_capacity = 0;         // cap on the members per row of the first bucket stage (0 = its capacity)
     int select_bits = qf::kSelectL2Bits;   // log2 refinement slots of the selection kernel (tests lower it)
     int select3_capw = 0;                  // octets per warp segment of the select3 stage (0 = auto; tests shrink it)
-    int select_impl = 0;                   // 0: auto (select3 on compact lists, else select2, else multi-level); 1: always the
-                                           // multi-level kernel; 2: select2 (8-byte members) when the training set allows
+    int select_impl = 0;                   // 0: auto (select2 when the training set allows, else the multi-level kernel);
+                                           // 1: always the multi-level kernel; 3: select3 on compact leaf lists when the forest
+                                           // and the call allow (<= 3 percentiles), else as 0
     int cta2_capacity = 8192;     // same for the 512-thread overflow stage (0 = stage not used)
     int warp_elems = -1;          // warp kernel: keys per lane (2, 4, 8), 0 = never, -1 = auto
     int warp_unit = 1;            // 0: never take the one-member-per-leaf gather of the warp kernel
@@ -551,7 +552,7 @@ struct Select3Geometry {
 
 Select3Geometry select3_geometry(const qf_forest* f, int nq) {
     Select3Geometry g;
-    if (f->select_impl != 0 || f->select_bits != qf::kSelectL2Bits || nq > qf::kSelect2QB) return g;
+    if (f->select_impl != 3 || f->select_bits != qf::kSelectL2Bits || nq > qf::kSelect2QB) return g;
     if (f->T > qf::kSelect3MaxIPT * qf::kSelect3Workers) return g;
     int k = 0;                                          // weights of a row sum to <= bound < 2^k
     const int64_t bound = std::max<int64_t>(f->T, f->row_weight_bound);
@@ -1041,7 +1042,7 @@ int qf_forest_set_option(qf_forest* f, const char* key, int64_t value) {
         if (value != 0 && value != 1) return qf::fail(QF_ERR_INVALID, "warp_unit must be 0 or 1");
         f->warp_unit = static_cast<int>(value);
     } else if (k == "select_impl") {
-        if (value < 0 || value > 2) return qf::fail(QF_ERR_INVALID, "select_impl must be 0 (auto), 1 (multi-level) or 2 (select2)");
+        if (value < 0 || value > 3) return qf::fail(QF_ERR_INVALID, "select_impl must be 0 (auto), 1 (multi-level), 2 (select2) or 3 (select3)");
         f->select_impl = static_cast<int>(value);
     } else if (k == "select_bits") {
         if (value < 1 || value > qf::kSelectL2Bits)

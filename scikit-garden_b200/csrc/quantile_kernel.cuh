@@ -419,8 +419,8 @@ __device__ __forceinline__ void gather_members(const uint2* __restrict__ members
 //
 //   1. gather the (rank, weight) pairs in tree order: rk[pos], wt[pos]; block min / max of
 //      the ranks gives the row's rank window [rmin, rmin + range]
-//   2. counting sort by bucket = (rank - rmin) >> shift with B = 16 * THREADS buckets
-//      (less than one member per bucket on average, a few in the dense centre of the row's rank window): integer shared-memory atomics for the histogram
+//   2. counting sort by bucket = (rank - rmin) >> shift with B = 8 * THREADS buckets
+//      (about two members per bucket): integer shared-memory atomics for the histogram
 //      and for the slots (ATOMS ~16 lanes/clk/SM measured, tools/microbench), one block
 //      scan in between.  An entry is the 32-bit word (low rank bits << POSBITS) | pos.
 //   3. order inside a bucket: every entry counts the smaller entries of its bucket
@@ -439,19 +439,19 @@ __host__ __device__ constexpr int bucket_kernel_capacity(int threads) { return t
 
 __host__ __device__ inline size_t bucket_kernel_smem(int threads, int T) {
     const size_t cap = static_cast<size_t>(bucket_kernel_capacity(threads));
-    return cap * 12 + (cap + 8) * 4 + static_cast<size_t>(2 * T + 1) * 4 + 16;
+    return cap * 12 + (cap / 2 + 8) * 4 + static_cast<size_t>(2 * T + 1) * 4 + 16;
 }
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 256) ? 768 / THREADS : 1)
 quantile_bucket_kernel(const QuantileParams p, const __grid_constant__ QuantileList ql) {
     constexpr int CAP = THREADS * kBucketEPT;
-    // one bucket per capacity slot: the members of a row crowd into a fraction of its rank window
-    // (ncu r2_a: with CAP / 2 buckets the in-bucket ordering of step 3 was 45 % of all instructions)
-    constexpr int NB = CAP;                             // buckets
+    // CAP / 2 buckets.  (One bucket per capacity slot was measured in round 2: the in-bucket ordering of
+    // step 3 gets cheaper, the scan twice as long, config 3 exact 65.3 -> 68.1 ms: not kept.)
+    constexpr int NB = CAP / 2;                         // buckets
     constexpr int NW = THREADS / 32;
     constexpr int POSBITS = (THREADS == 64) ? 10 : (THREADS == 128) ? 11 : (THREADS == 256) ? 12 : 13;
-    constexpr int LOG2NB = POSBITS;
+    constexpr int LOG2NB = POSBITS - 1;
     constexpr uint32_t POSMASK = CAP - 1;
     static_assert(THREADS == 64 || THREADS == 128 || THREADS == 256 || THREADS == 512, "unsupported block size");
     static_assert((1 << POSBITS) == CAP, "POSBITS must be log2 of the capacity");
@@ -518,7 +518,7 @@ quantile_bucket_kernel(const QuantileParams p, const __grid_constant__ QuantileL
     // 2a. bucket populations
     for (uint32_t i = tid; i < P; i += THREADS) atomicAdd(&cnt[(rk[i] - rmin) >> shift], 1u);
     __syncthreads();
-    // 2b. exclusive scan of the NB = 16 * THREADS populations (16 consecutive per thread)
+    // 2b. exclusive scan of the NB = 8 * THREADS populations (8 consecutive per thread)
     {
         constexpr int C4 = NB / THREADS / 4;            // 128-bit chunks per thread
         uint4 c[C4];

@@ -80,3 +80,33 @@ def test_device_builder_refuses_very_long_leaf_lists():
     est.set_params(builder="device")
     with pytest.raises(_native.QFError, match="4096"):
         est.fit(np.tile(X, (4, 1)), np.tile(y, 4))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c1_rfqr_boston", "c1_etqr_boston", "rf_noboot_msl3_ties", "et_msl5", "rf_maxleaf50",
+                                  "et_depth2_large_sets", "rf_pure_leaves"])
+def test_device_builder_reproduces_the_reference_fit_attributes(name):
+    # K4 against the REFERENCE's own outputs (tests/golden, generated from the unmodified reference):
+    # y_train_leaves_ / y_weights_ of ensemble.py:83-101 and the predictions, not just the host flattener
+    pytest.importorskip("torch")
+    import _golden
+    import skgarden_b200 as sg
+    from skgarden_b200.flatten import flatten_forest_device
+    g = _golden.load(name)
+    N = len(g.y_train)
+    trees = [e.tree_ for e in g.estimators]
+    counts = [sg.bootstrap_counts(e.random_state, N) for e in g.estimators] if g.bootstrap else None
+    hi_leaf = max(int(np.bincount(t.apply(g.X_train)).max()) for t in trees)
+    if hi_leaf > 4096:
+        pytest.skip("a leaf of %d members: the device builder hands such forests to the host flattener" % hi_leaf)
+    flat = flatten_forest_device(trees, g.X_train, counts, g.y_train, g.X_train.shape[1], sorter=g.sorter)
+    shell = sg.RandomForestQuantileRegressor()
+    shell._set_flat(flat)
+    assert_array_equal(shell.y_train_leaves_, g.y_train_leaves_)
+    assert_array_equal(shell.y_weights_, g.y_weights_)
+    dev = sg.DeviceForest(flat, device=0)
+    import torch
+    X = torch.from_numpy(np.ascontiguousarray(g.X_test)).cuda()
+    assert_array_equal(dev.apply(X).cpu().numpy(), g.apply)
+    assert_array_equal(dev.predict_quantiles(X, g.q).cpu().numpy().T, g.pred)
+    dev.close()
