@@ -7,6 +7,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -58,7 +59,22 @@ struct HostPipe {
     int64_t x_bytes = 0, out_bytes = 0;     // per slot
     void* ws = nullptr;
     int64_t ws_bytes = 0;
+    // page-locked staging for callers that hand over pageable memory (an ordinary numpy array): a
+    // pageable cudaMemcpyAsync blocks the calling thread until the copy is done, and a pageable D2H
+    // even until the chunk's kernels are, which would serialise copies and kernels
+    float* hx[kPipeSlots] = {};
+    double* hout[kPipeSlots] = {};
+    int64_t hx_bytes = 0, hout_bytes = 0;   // per slot
 };
+
+bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
 
 }  // namespace
 
@@ -90,6 +106,7 @@ struct qf_forest {
     int cta_capacity = 0;         // cap on the members per row of the first bucket stage (0 = its capacity)
     int select_bits = qf::kSelectL2Bits;   // log2 refinement slots of the selection kernel (tests lower it)
     int select3_capw = 0;                  // octets per warp segment of the select3 stage (0 = auto; tests shrink it)
+    int select3_variant = 1;               // 0: 3 select warps, 2 stages, 2 CTAs per SM; 1: 1 select warp, 1 stage, 3 CTAs per SM
     int select_impl = 0;                   // 0: auto (select2 when the training set allows, else the multi-level kernel);
                                            // 1: always the multi-level kernel; 3: select3 on compact leaf lists when the forest
                                            // and the call allow (<= 3 percentiles), else as 0
@@ -545,7 +562,7 @@ int ensure_compact(qf_forest* f) {
 // select2 / the multi-level kernel do).
 struct Select3Geometry {
     bool ok = false;
-    int log2nb = 11, shift1 = 0, ipt = 1, capw = 0;
+    int log2nb = 11, shift1 = 0, ipt = 1, capw = 0, stages = 2, selw = 3;
     float fx_scale = 0.0f;
     size_t smem = 0;
 };
@@ -586,27 +603,38 @@ bool select3_finish_geometry(const qf_forest* f, Select3Geometry& g) {
     if (f->select3_capw > 0) capw = f->select3_capw;
     capw = (capw + 3) & ~3;
     g.capw = capw;
-    g.smem = qf::select3_kernel_smem(g.log2nb, g.shift1, capw);
-    // two CTAs per SM is what the kernel is tuned for; one oversized stage (big leaves) is not worth it
-    g.ok = g.smem <= 112 * 1024;
+    g.stages = f->select3_variant == 0 ? 2 : 1;
+    g.selw = f->select3_variant == 0 ? 3 : 1;
+    g.smem = qf::select3_kernel_smem(g.log2nb, g.shift1, capw, g.stages);
+    // 2 (3) CTAs per SM is what the kernel is tuned for; one oversized stage (big leaves) is not worth it
+    g.ok = g.smem <= static_cast<size_t>(g.stages == 2 ? 112 : 75) * 1024;
     return g.ok;
 }
 
 int launch_select3_kernel(const qf_forest* f, const Select3Geometry& g, const qf::Select3Params& sp,
                           const qf::QuantileList& ql, cudaStream_t st) {
     const int64_t n_groups = (sp.n + qf::kSelect3RowGroup - 1) / qf::kSelect3RowGroup;
-    const unsigned grid = static_cast<unsigned>(std::min<int64_t>(n_groups, int64_t(f->sm_count) * qf::kSelect3CtasPerSm));
+    const unsigned grid = static_cast<unsigned>(
+        std::min<int64_t>(n_groups, int64_t(f->sm_count) * qf::select3_ctas_per_sm(g.stages)));
     auto run = [&](auto kernel) -> int {
         int rc = set_smem(kernel, g.smem);
         if (rc != QF_OK) return rc;
-        kernel<<<grid, qf::kSelect3Threads, g.smem, st>>>(sp, ql);
+        kernel<<<grid, qf::select3_threads(g.selw), g.smem, st>>>(sp, ql);
         return QF_OK;
     };
-    if (g.log2nb == 11)
-        return g.ipt == 1 ? run(qf::quantile_select3_kernel<11, 1>)
-             : g.ipt == 2 ? run(qf::quantile_select3_kernel<11, 2>) : run(qf::quantile_select3_kernel<11, 4>);
-    return g.ipt == 1 ? run(qf::quantile_select3_kernel<12, 1>)
-         : g.ipt == 2 ? run(qf::quantile_select3_kernel<12, 2>) : run(qf::quantile_select3_kernel<12, 4>);
+    auto pick_ipt = [&](auto log2nb_c, auto selw_c, auto stages_c) -> int {
+        constexpr int L = decltype(log2nb_c)::value, W = decltype(selw_c)::value, S = decltype(stages_c)::value;
+        return g.ipt == 1 ? run(qf::quantile_select3_kernel<L, 1, W, S>)
+             : g.ipt == 2 ? run(qf::quantile_select3_kernel<L, 2, W, S>) : run(qf::quantile_select3_kernel<L, 4, W, S>);
+    };
+    using I11 = std::integral_constant<int, 11>;
+    using I12 = std::integral_constant<int, 12>;
+    using I1 = std::integral_constant<int, 1>;
+    using I2 = std::integral_constant<int, 2>;
+    using I3 = std::integral_constant<int, 3>;
+    if (g.stages == 2)
+        return g.log2nb == 11 ? pick_ipt(I11{}, I3{}, I2{}) : pick_ipt(I12{}, I3{}, I2{});
+    return g.log2nb == 11 ? pick_ipt(I11{}, I1{}, I1{}) : pick_ipt(I12{}, I1{}, I1{});
 }
 
 // QF_MODE_FAST adds weights as 32-bit fixed point with 2^(31-k) units per unit of weight
@@ -922,6 +950,8 @@ void qf_forest_destroy(qf_forest* f) {
         for (int s = 0; s < kPipeSlots; ++s) {
             cudaFree(hp.x[s]);
             cudaFree(hp.out[s]);
+            cudaFreeHost(hp.hx[s]);
+            cudaFreeHost(hp.hout[s]);
             if (hp.x_ready[s]) cudaEventDestroy(hp.x_ready[s]);
             if (hp.computed[s]) cudaEventDestroy(hp.computed[s]);
             if (hp.out_free[s]) cudaEventDestroy(hp.out_free[s]);
@@ -972,7 +1002,7 @@ int qf_forest_quantile_kernel_name(qf_forest* f, int64_t n_rows, int32_t nq, int
         int nbits = 0;
         while ((int64_t(1) << nbits) < f->N) ++nbits;
         if (g3.ok)
-            std::snprintf(name, sizeof(name), "quantile_select3_kernel<%d, %d>", g3.log2nb, g3.ipt);
+            std::snprintf(name, sizeof(name), "quantile_select3_kernel<%d, %d, %d, %d>", g3.log2nb, g3.ipt, g3.selw, g3.stages);
         else if (f->select_impl != 1 && f->select_bits == qf::kSelectL2Bits && nbits <= 12 + qf::kSelect2SlotBits &&
                  f->T <= qf::kSelect2MaxIPT * qf::kSelect2Threads)
             std::snprintf(name, sizeof(name), "quantile_select2_kernel<%d>", nbits <= 11 + qf::kSelect2SlotBits ? 11 : 12);
@@ -1048,6 +1078,9 @@ int qf_forest_set_option(qf_forest* f, const char* key, int64_t value) {
         if (value < 1 || value > qf::kSelectL2Bits)
             return qf::fail(QF_ERR_INVALID, "select_bits must be in [1, 10]");
         f->select_bits = static_cast<int>(value);
+    } else if (k == "select3_variant") {
+        if (value != 0 && value != 1) return qf::fail(QF_ERR_INVALID, "select3_variant must be 0 or 1");
+        f->select3_variant = static_cast<int>(value);
     } else if (k == "select3_capw") {
         if (value < 0 || value > 4096) return qf::fail(QF_ERR_INVALID, "select3_capw must be in [0, 4096]");
         f->select3_capw = static_cast<int>(value);
@@ -1235,17 +1268,60 @@ int qf_forest_predict_quantiles_host(qf_forest* f, const float* X_host, int64_t 
     }
     rc = zero_dense_scratch(f, pl, hp.ws, hp.compute);
     if (rc != QF_OK) return rc;
+    // pageable buffers go through page-locked staging slots (several chunks only: one chunk has nothing to overlap)
+    const bool stage_x = n > chunk_rows && is_pageable(X_host);
+    const bool stage_out = n > chunk_rows && is_pageable(out_host);
+    if (stage_x && hp.hx_bytes < x_bytes) {
+        for (int s = 0; s < kPipeSlots; ++s) { cudaFreeHost(hp.hx[s]); hp.hx[s] = nullptr; }
+        hp.hx_bytes = 0;
+        for (int s = 0; s < kPipeSlots; ++s) QF_CUDA_TRY(cudaMallocHost(&hp.hx[s], x_bytes));
+        hp.hx_bytes = x_bytes;
+    }
+    if (stage_out && hp.hout_bytes < out_bytes) {
+        for (int s = 0; s < kPipeSlots; ++s) { cudaFreeHost(hp.hout[s]); hp.hout[s] = nullptr; }
+        hp.hout_bytes = 0;
+        for (int s = 0; s < kPipeSlots; ++s) QF_CUDA_TRY(cudaMallocHost(&hp.hout[s], out_bytes));
+        hp.hout_bytes = out_bytes;
+    }
+    // result of the chunk that used slot s before: wait for its D2H, then hand it to the caller
+    auto drain = [&](int64_t done_chunk) -> int {
+        const int s = static_cast<int>(done_chunk % kPipeSlots);
+        QF_CUDA_TRY(cudaEventSynchronize(hp.out_free[s]));
+        const int64_t q0 = done_chunk * chunk_rows, rows = std::min(chunk_rows, n - q0);
+        std::memcpy(out_host + q0 * nq, hp.hout[s], static_cast<size_t>(rows) * nq * 8);
+        return QF_OK;
+    };
     int64_t chunk = 0;
     for (int64_t r0 = 0; r0 < n; r0 += chunk_rows, ++chunk) {
         const int64_t rows = std::min(chunk_rows, n - r0);
         const int s = static_cast<int>(chunk % kPipeSlots);
+        if (chunk >= kPipeSlots) {
+            if (stage_out) {
+                rc = drain(chunk - kPipeSlots);
+                if (rc != QF_OK) return rc;
+            } else if (stage_x) {                       // the H2D out of hx[s] is long done once that chunk's D2H is
+                QF_CUDA_TRY(cudaEventSynchronize(hp.out_free[s]));
+            }
+        }
+        const float* src = X_host + r0 * ldx;
+        int64_t src_ld = ldx;
+        if (stage_x) {                                  // host-side copy of chunk k runs while the GPU is on chunk k - 1
+            if (ldx == f->F) {
+                std::memcpy(hp.hx[s], src, static_cast<size_t>(rows) * f->F * 4);
+            } else {
+                for (int64_t r = 0; r < rows; ++r)
+                    std::memcpy(hp.hx[s] + r * f->F, src + r * ldx, static_cast<size_t>(f->F) * 4);
+            }
+            src = hp.hx[s];
+            src_ld = f->F;
+        }
         // H2D: the slot's X buffer is free once the kernels of the chunk that used it are done.
         // Rows of X are compacted to F columns on the device (ldx may exceed F on the host).
         if (chunk >= kPipeSlots) QF_CUDA_TRY(cudaStreamWaitEvent(hp.h2d, hp.computed[s], 0));
-        if (ldx == f->F) {
-            QF_CUDA_TRY(cudaMemcpyAsync(hp.x[s], X_host + r0 * ldx, rows * f->F * 4, cudaMemcpyHostToDevice, hp.h2d));
+        if (src_ld == f->F) {
+            QF_CUDA_TRY(cudaMemcpyAsync(hp.x[s], src, rows * f->F * 4, cudaMemcpyHostToDevice, hp.h2d));
         } else {
-            QF_CUDA_TRY(cudaMemcpy2DAsync(hp.x[s], f->F * 4, X_host + r0 * ldx, ldx * 4, f->F * 4, rows,
+            QF_CUDA_TRY(cudaMemcpy2DAsync(hp.x[s], f->F * 4, src, src_ld * 4, f->F * 4, rows,
                                           cudaMemcpyHostToDevice, hp.h2d));
         }
         QF_CUDA_TRY(cudaEventRecord(hp.x_ready[s], hp.h2d));
@@ -1257,8 +1333,15 @@ int qf_forest_predict_quantiles_host(qf_forest* f, const float* X_host, int64_t 
         QF_CUDA_TRY(cudaEventRecord(hp.computed[s], hp.compute));
         // D2H
         QF_CUDA_TRY(cudaStreamWaitEvent(hp.d2h, hp.computed[s], 0));
-        QF_CUDA_TRY(cudaMemcpyAsync(out_host + r0 * nq, hp.out[s], rows * nq * 8, cudaMemcpyDeviceToHost, hp.d2h));
+        QF_CUDA_TRY(cudaMemcpyAsync(stage_out ? hp.hout[s] : out_host + r0 * nq, hp.out[s], rows * nq * 8,
+                                    cudaMemcpyDeviceToHost, hp.d2h));
         QF_CUDA_TRY(cudaEventRecord(hp.out_free[s], hp.d2h));
+    }
+    if (stage_out) {
+        for (int64_t c = std::max<int64_t>(0, chunk - kPipeSlots); c < chunk; ++c) {
+            rc = drain(c);
+            if (rc != QF_OK) return rc;
+        }
     }
     QF_CUDA_TRY(cudaStreamSynchronize(hp.d2h));
     QF_CUDA_TRY(cudaStreamSynchronize(hp.compute));

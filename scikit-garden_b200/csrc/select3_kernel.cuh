@@ -54,8 +54,14 @@ namespace qf {
 
 constexpr int kSelect3Workers = 256;                    // worker threads (8 warps)
 constexpr int kSelect3Warps = kSelect3Workers / 32;
-constexpr int kSelect3Threads = kSelect3Workers + 32 * kSelect2QB;    // + one select warp per percentile
-constexpr int kSelect3CtasPerSm = 2;
+// Two shapes of the CTA (template parameters SELW, STAGES of the kernel):
+//   SELW = 3, STAGES = 2: one select warp per percentile, two stages (the copies of row r + 1 complete under
+//                          row r), 100 KB of shared memory at config 3 -> 2 CTAs (22 warps) per SM
+//   SELW = 1, STAGES = 1: one select warp for all percentiles, one stage (the copies of row r + 1 are issued
+//                          when the warp is done with row r and complete under the other CTAs of the SM),
+//                          71 KB -> 3 CTAs (27 warps) per SM
+__host__ __device__ constexpr int select3_threads(int selw) { return kSelect3Workers + 32 * selw; }
+__host__ __device__ constexpr int select3_ctas_per_sm(int stages) { return stages == 2 ? 2 : 3; }
 constexpr int kSelect3MaxIPT = 4;                       // trees per worker thread: T <= 1024
 constexpr int kSelect3RowGroup = 4;                     // rows per 128-bit load of list words
 constexpr int kSelect3ScanThreads = 128;                // threads that scan the histogram
@@ -77,10 +83,10 @@ struct Select3Params {
 };
 
 // shared memory: 2 histograms | 2 tables | slots | 2 stages
-__host__ __device__ inline size_t select3_kernel_smem(int log2nb, int shift1, int capw) {
+__host__ __device__ inline size_t select3_kernel_smem(int log2nb, int shift1, int capw, int stages) {
     const size_t nb = static_cast<size_t>(1) << log2nb;
     return 2 * nb * 4 + 2 * (nb * 2) + static_cast<size_t>(kSelect2QB) * 3 * select2_slots(shift1) * 4 +
-           2 * static_cast<size_t>(kSelect3Warps) * capw * 32;
+           static_cast<size_t>(stages) * kSelect3Warps * capw * 32;
 }
 
 __device__ __forceinline__ void cp_async_16(uint32_t dst_shared, const void* src_global) {
@@ -129,9 +135,10 @@ struct Select3Rows {
     }
 };
 
-template <int LOG2NB, int IPT>
-__global__ void __launch_bounds__(kSelect3Threads, kSelect3CtasPerSm)
+template <int LOG2NB, int IPT, int SELW, int STAGES>
+__global__ void __launch_bounds__(select3_threads(SELW), select3_ctas_per_sm(STAGES))
 quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileList ql) {
+    constexpr int kSelect3Threads = select3_threads(SELW);
     constexpr int NB = 1 << LOG2NB;
     constexpr int BPT = NB / kSelect3ScanThreads;       // buckets per scan thread: 16 or 32
     constexpr int QB = kSelect2QB;
@@ -254,28 +261,33 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
 #pragma unroll
         for (int i = 0; i < IPT; ++i) w[i] = cur[i].x;
         uint32_t par = 0u;                              // row parity: stage / histogram / table / hand-off in use
-        uint32_t wtot = issue_copies(w, par);
+        uint32_t wtot = issue_copies(w, 0u);
         cp_async_commit();
 
         for (;;) {
-            // the copies of the NEXT row go out first (its stage was released by this warp's pass 2 of the
-            // row before this one); one commit group per row, empty when there is no next row
             uint32_t w2[IPT];
             const bool more = rows.has_next(gridDim.x);
             const bool same = rows.next_in_group();
 #pragma unroll
             for (int i = 0; i < IPT; ++i) w2[i] = same ? pick(cur[i], rows.l + 1) : nxt[i].x;
             uint32_t wtot2 = 0u;
-            if (more) wtot2 = issue_copies(w2, par ^ 1u);          // block-uniform
-            cp_async_commit();
+            const uint32_t st = STAGES == 2 ? par : 0u; // stage of this row
+            if (STAGES == 2) {
+                // the copies of the NEXT row go out first (its stage was released by this warp's pass 2 of the
+                // row before this one); one commit group per row, empty when there is no next row
+                if (more) wtot2 = issue_copies(w2, par ^ 1u);      // block-uniform
+                cp_async_commit();
+                cp_async_wait<1>();                     // everything but the group just committed: this row is in
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncwarp();
 
             // pass 1: bucket weights (octet header a.x = fixed-point weight of one bootstrap count).
             // w == 0 (utils.py:55-57) cannot occur for a member (counts are >= 1); padding slots carry count 0
             // and a pseudo-random rank (compact_lists.cuh): they add zero to some bucket, no predicate, no branch.
-            cp_async_wait<1>();                         // everything but the group just committed: this row is in
-            __syncwarp();
             const uint32_t h_s = h1_s + par * (NB * 4);
-            for_each_octet(wtot, w, par, [&](const uint4& a, const uint4& b) {
+            for_each_octet(wtot, w, st, [&](const uint4& a, const uint4& b) {
                 const uint32_t m[7] = {a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
                 for (int e = 0; e < 7; ++e)
@@ -399,7 +411,7 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
 
             // pass 2: members of marked buckets -> slot arrays at single-rank resolution
             const uint32_t t_s = tbl_s + par * (NB * 2);
-            for_each_octet(wtot, w, par, [&](const uint4& a, const uint4& b) {
+            for_each_octet(wtot, w, st, [&](const uint4& a, const uint4& b) {
                 const uint32_t m[7] = {a.y, a.z, a.w, b.x, b.y, b.z, b.w};
                 uint32_t code[7];
 #pragma unroll
@@ -419,6 +431,10 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
                 }
             });
             __syncwarp();                               // every lane of the warp is done with this stage
+            if (STAGES == 1) {                          // one stage: the next row's copies fly from here on
+                if (more) wtot2 = issue_copies(w2, 0u);
+                cp_async_commit();
+            }
             bar_arrive<kBarSlots, kSelect3Threads>();   // S: this warp's share of the slots is in
             if (!more) break;
             if (same) {
@@ -440,12 +456,12 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
     }
 
     // ========================================= select warps =========================================
-    const int q = warp - kSelect3Warps;                 // this warp's percentile
-    const bool active = q < p.Q;
+    // select warp v takes the percentiles v, v + SELW, ...; lane k keeps what the interpolation of the
+    // warp's k-th percentile needs
+    const int sw_id = warp - kSelect3Warps;
     const int nch = SL >> 2;                            // 128-bit chunks per slot array
     const int CH = (nch + 31) >> 5;                     // chunks per lane: 1, 2 or 4 (consecutive)
     const float inv = __fdiv_rn(1.0f, p.fx_scale);
-    const uint32_t L_s = l2_s + q * 3 * SL * 4;         // [bp | bq | bn]
 
     // lane L's share of a slot array: chunks [L * CH, L * CH + CH) -> v[], bit i of the result = slot i of the share non-empty
     auto load_share = [&](uint32_t arr_s, uint4 (&v)[4]) -> uint32_t {
@@ -467,14 +483,17 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
         const int64_t pos = rows.pos();
         const bool more = rows.has_next(gridDim.x);
         int64_t out_row = pos;
-        if (active && p.order) out_row = static_cast<int64_t>(__ldg(p.order + pos));
+        if (p.order) out_row = static_cast<int64_t>(__ldg(p.order + pos));
         bar_sync<kBarSlots, kSelect3Threads>();         // S: the slot arrays of this row are complete
-        float result = 0.0f;
-        bool have = false;
-        uint32_t re = 0u, rs = NONE, rp = NONE, Ce = 0u, We = 0u, Ws = 0u, Wp = 0u, total = 0u;
-        if (active) {
+        // kept by lane k for the warp's k-th percentile
+        bool k_have = false;
+        uint32_t k_re = 0u, k_rs = NONE, k_rp = NONE, k_Ce = 0u, k_We = 0u, k_Ws = 0u, k_Wp = 0u, k_total = 0u;
+        for (int q = sw_id, kq = 0; q < p.Q; q += SELW, ++kq) {
+            const uint32_t L_s = l2_s + q * 3 * SL * 4; // [bp | bq | bn]
+            uint32_t re = 0u, rs = NONE, rp = NONE, Ce = 0u, We = 0u, Ws = 0u, Wp = 0u;
             const Select3Handoff hd = s_hand[par][q];
-            total = hd.total;
+            const uint32_t total = hd.total;
+            bool have = false;
             if (total != 0u) {
                 const uint32_t tau = hd.tau, bp = hd.bp, bq = hd.bq, bn = hd.bn;
                 uint4 v[4];
@@ -570,14 +589,24 @@ quantile_select3_kernel(const Select3Params p, const __grid_constant__ QuantileL
                     if (bn != NONE) st_shared_u16(t_s + bn * 2u, 0u);
                 }
             }
+            if (lane == kq) {
+                k_have = have; k_total = total;
+                k_re = re; k_rs = rs; k_rp = rp; k_Ce = Ce; k_We = We; k_Ws = Ws; k_Wp = Wp;
+            }
         }
         // the slots are free again: the workers may start pass 2 of the next row
         if (more) bar_arrive<kBarMarks, kSelect3Threads>();
 
-        // ---- utils.py:69-81 on (pred, e, succ), float32
-        if (active && lane == 0) {
+        // ---- utils.py:69-81 on (pred, e, succ), float32: lane k interpolates the warp's k-th percentile
+        // (the y loads of the warp's percentiles overlap)
+        {
+            const int q = sw_id + lane * SELW;
+            const bool have = k_have;
+            const uint32_t re = k_re, rs = k_rs, rp = k_rp, Ce = k_Ce, We = k_We, Ws = k_Ws, Wp = k_Wp, total = k_total;
+            float result = 0.0f;
             double* __restrict__ out = p.out + out_row * p.ldo;
-            if (!have) {
+            if (q >= p.Q) {
+            } else if (!have) {
                 out[q] = __longlong_as_double(0x7ff8000000000000LL);
             } else {
                 const double qv = ql.q[q];

@@ -236,20 +236,42 @@ class DeviceForest:
             return mean.cpu().numpy(), std.cpu().numpy()
 
     def predict_stream(self, chunks, quantiles: Sequence[float], mode: int = _native.QF_MODE_EXACT,
-                       pinned: bool = True):
+                       pinned: bool = True, prepare=None):
         """Streaming front end (BASELINE.json config 5: test rows that do not fit one host
         array): ``chunks`` is any iterable of (m_i, F) float32 arrays; yields one (m_i, Q)
         float64 array per chunk, in order.  See :func:`stream_predict`."""
-        return stream_predict([self], chunks, quantiles, mode=mode, pinned=pinned)
+        return stream_predict([self], chunks, quantiles, mode=mode, pinned=pinned, prepare=prepare)
 
 
-def stream_predict(replicas, chunks, quantiles, mode=_native.QF_MODE_EXACT, pinned=True):
+def assert_all_finite_parallel(X: np.ndarray, workers: int = 8, pool=None) -> None:
+    """The finite check of ``check_array`` (ensemble.py:129 rejects NaN / inf), on row slices in
+    parallel (numpy releases the GIL inside the scan).  Raises scikit-learn's own ValueError."""
+    from sklearn.utils import assert_all_finite
+    n = X.shape[0]
+    if n * max(1, X.shape[1]) < (1 << 20) or workers <= 1:
+        assert_all_finite(X, input_name="X")
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    bounds = np.linspace(0, n, workers + 1).astype(np.int64)
+    jobs = [(int(a), int(b)) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+    own = pool is None
+    pool = pool or ThreadPoolExecutor(len(jobs))
+    try:
+        for f in [pool.submit(assert_all_finite, X[a:b], input_name="X") for a, b in jobs]:
+            f.result()
+    finally:
+        if own:
+            pool.shutdown(wait=True)
+
+
+def stream_predict(replicas, chunks, quantiles, mode=_native.QF_MODE_EXACT, pinned=True, prepare=None):
     """Chunks of test rows through one or several forest replicas, results in order.
 
     Two worker threads per replica: while one chunk is inside the pipelined host-buffer call
     (H2D / kernels / D2H on three streams, csrc/qforest_abi.cu), the next one is being staged
     into the second page-locked buffer, so the GPU never waits for the host copy; chunk k goes
-    to replica k mod G.  ``pinned=False`` hands the caller's arrays to the C call as they are."""
+    to replica k mod G.  ``pinned=False`` hands the caller's arrays to the C call as they are.
+    ``prepare`` (chunk -> float32 C-contiguous array, may raise) runs in the worker threads."""
     import collections
     import threading
     from concurrent.futures import ThreadPoolExecutor
@@ -259,6 +281,8 @@ def stream_predict(replicas, chunks, quantiles, mode=_native.QF_MODE_EXACT, pinn
     tls = threading.local()
 
     def work(dev, X):
+        if prepare is not None:                         # the caller's validation, off the feeding thread
+            X = prepare(X)
         m = X.shape[0]
         if not pinned:
             return dev.predict_quantiles_host(X, q, mode=mode)
@@ -277,10 +301,11 @@ def stream_predict(replicas, chunks, quantiles, mode=_native.QF_MODE_EXACT, pinn
     with ThreadPoolExecutor(depth) as pool:
         k = 0
         for X in chunks:
-            X = np.ascontiguousarray(X, dtype=np.float32)
-            if X.ndim != 2 or X.shape[1] != F:
-                raise ValueError("chunk has shape %r, forest expects (m, %d)" % (X.shape, F))
-            if X.shape[0] == 0:
+            if np.ndim(X) != 2 or np.shape(X)[1] != F:
+                raise ValueError("chunk has shape %r, forest expects (m, %d)" % (np.shape(X), F))
+            if prepare is None:
+                X = np.ascontiguousarray(X, dtype=np.float32)
+            if np.shape(X)[0] == 0:
                 pending.append(None)
             else:
                 pending.append(pool.submit(work, replicas[k % len(replicas)], X))
@@ -365,5 +390,5 @@ class ForestReplicas:
         self._sharded(X_host.shape[0], fn)
         return mean, std
 
-    def predict_stream(self, chunks, quantiles, mode=_native.QF_MODE_EXACT, pinned=True):
-        return stream_predict(self.replicas, chunks, quantiles, mode=mode, pinned=pinned)
+    def predict_stream(self, chunks, quantiles, mode=_native.QF_MODE_EXACT, pinned=True, prepare=None):
+        return stream_predict(self.replicas, chunks, quantiles, mode=mode, pinned=pinned, prepare=prepare)

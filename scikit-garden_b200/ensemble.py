@@ -233,13 +233,22 @@ class _BaseForestQuantileRegressor(RegressorMixin, BaseEstimator):
         return _native.QF_MODE_EXACT if self.mode == "exact" else _native.QF_MODE_FAST
 
     def _validate_X(self, X):
+        """ensemble.py:129 (`check_array(X, dtype=float32)`: casts, rejects NaN / inf and 0 rows) with the
+        finite scan of large inputs split over host threads (it is as long as the GPU work otherwise)."""
         if hasattr(X, "tocsr"):
             raise NotImplementedError("sparse X is not supported on the GPU path")
         self._check_fitted()
-        X = check_array(X, dtype=np.float32, order="C")                  # ensemble.py:129
+        big = np.size(X) >= (1 << 22)
+        try:
+            X = check_array(X, dtype=np.float32, order="C", ensure_all_finite=not big)
+        except TypeError:                                                # scikit-learn < 1.6 spelling
+            X = check_array(X, dtype=np.float32, order="C", force_all_finite=not big)
         if X.shape[1] != self.n_features_:
             raise ValueError("X has %d features, but %s is expecting %d features as input."
                              % (X.shape[1], type(self).__name__, self.n_features_))
+        if big:
+            from .device_forest import assert_all_finite_parallel
+            assert_all_finite_parallel(X, workers=min(16, os.cpu_count() or 1))
         return X
 
     # -- the hot path --------------------------------------------------------------------------
@@ -261,13 +270,19 @@ class _BaseForestQuantileRegressor(RegressorMixin, BaseEstimator):
         qs, scalar = _check_quantiles(quantile)
         dev = self._on_device()
 
-        def validated():
+        def prepare(X):                           # runs in the streaming worker threads
+            if np.shape(X)[0] == 0:
+                return np.empty((0, self.n_features_), dtype=np.float32)        # an empty chunk is fine in a stream
+            return check_array(X, dtype=np.float32, order="C")
+
+        def shaped():
             for X in chunks:
-                if np.ndim(X) == 2 and np.shape(X)[0] == 0 and np.shape(X)[1] == self.n_features_:
-                    yield np.empty((0, self.n_features_), dtype=np.float32)     # an empty chunk is fine in a stream
-                else:
-                    yield self._validate_X(X)
-        for out in dev.predict_stream(validated(), qs, mode=self._mode()):
+                if hasattr(X, "tocsr"):
+                    raise NotImplementedError("sparse X is not supported on the GPU path")
+                if np.ndim(X) != 2 or np.shape(X)[1] != self.n_features_:
+                    self._validate_X(X)           # raises the reference's error for the shape
+                yield X
+        for out in dev.predict_stream(shaped(), qs, mode=self._mode(), prepare=prepare):
             yield out[:, 0] if scalar else out
 
     def apply(self, X):

@@ -34,14 +34,14 @@ FAST = 1
 
 
 @pytest.mark.parametrize("name", _golden.CASES)
-@pytest.mark.parametrize("capw", [0, 4])
-def test_select3_against_reference_outputs(name, capw):
+@pytest.mark.parametrize("capw,variant", [(0, 1), (4, 1), (0, 0), (4, 0)])
+def test_select3_against_reference_outputs(name, capw, variant):
     # every golden forest through the CTA-level fast path with <= 3 percentiles per call (the
     # select3 kernel wherever the forest is compactable); capw = 4 pushes rows out of the
     # shared-memory stage into the direct-from-global path
     g = _golden.load(name)
     flat = _golden.flat_from_golden(g)
-    dev = _dev(flat, warp_elems=0, select3_capw=capw, select_impl=3)
+    dev = _dev(flat, warp_elems=0, select3_capw=capw, select_impl=3, select3_variant=variant)
     X = _cuda(g.X_test)
     scale = np.abs(g.y_train).max()
     names = set()
@@ -119,7 +119,7 @@ def test_select3_more_than_a_million_training_rows():
     est.mode = "fast"
     from skgarden_b200 import _native
     name = dev.quantile_kernel_name(len(Xt), 3, FAST)
-    assert name == "quantile_select3_kernel<12, 1>", (name, _native.last_error())
+    assert name .startswith("quantile_select3_kernel<12, 1,"), (name, _native.last_error())
     fast = est.predict(Xt, quantile=qs)
     assert_allclose(fast, exact, rtol=1e-4, atol=1e-4 * np.abs(ytr).max())
     assert_array_equal(fast[:, [0, -1]], exact[:, [0, -1]])
@@ -180,7 +180,7 @@ def test_c3_shaped_forest_against_oracle():
     assert_allclose(fast2[rows], want, rtol=1e-4, atol=1e-4 * scale)
     assert_allclose(fast2, exact, rtol=1e-4, atol=2e-4 * scale)       # all rows against the exact kernels
     dev.set_option("select_impl", 3)                                   # select3 on the compact leaf lists
-    assert dev.quantile_kernel_name(len(Xt), 3, FAST) == "quantile_select3_kernel<11, 2>"
+    assert dev.quantile_kernel_name(len(Xt), 3, FAST) .startswith("quantile_select3_kernel<11, 2,")
     fast = est.predict(Xt, quantile=qs)
     assert_allclose(fast[rows], want, rtol=1e-4, atol=1e-4 * scale)
     assert_allclose(fast, exact, rtol=1e-4, atol=2e-4 * scale)
