@@ -604,13 +604,13 @@ def parity_sample(wl, dev, out_all, srows, qs, mode, Xs, lo, hi, device):
 
 def estimator_e2e(flat, dev, X, qs, mode, out_all):
     """The drop-in call itself: est.predict(X, quantile=[...]) on a pageable numpy array
-    (check_array + H2D + kernels + D2H), one repetition after one warm-up."""
+    (check_array + H2D + kernels + D2H), one repetition after one warm-up call of the same size."""
     import skgarden_b200 as sg
     est = sg.ExtraTreesQuantileRegressor(mode=mode)
     est._set_flat(flat)
     est._device_forest = dev
     est.n_features_ = est.n_features_in_ = flat.n_features
-    est.predict(X[:4096], quantile=qs)
+    est.predict(X, quantile=qs)                        # warm-up at size: staging buffers, workspaces
     t0 = time.perf_counter()
     got = est.predict(X, quantile=qs)
     dt = time.perf_counter() - t0
