@@ -413,7 +413,8 @@ def run_b200(args, rank, world, local_rank):
     rows = hi - lo
     rows_max = -(-n // world)
     Xh = torch.from_numpy(X_all[lo:hi]).pin_memory()
-    del X_all
+    if rank != 0:
+        del X_all                                          # rank 0 keeps it for the parity sample / estimator call
     Xd = Xh.to(device)
     # the gathered (n, Q) result of all ranks (padded to equal shards for all_gather)
     gathered = torch.empty((world * rows_max, Q), dtype=torch.float64, device=device)
@@ -510,7 +511,7 @@ def run_b200(args, rank, world, local_rank):
         srows = wl["sample_rows"]
         parity = None
         if not args.no_parity:
-            parity = parity_sample(wl, dev, out_all, srows, qs, head, make_test(n, F, seed=0)[srows], lo, hi, device)
+            parity = parity_sample(wl, dev, out_all, srows, qs, head, X_all[srows], lo, hi, device)
         # P_row on the sample (exact, from the leaves hit), scaled to all rows
         P_rows = row_member_counts(flat, wl["sample_leaves"])
         P_mean = float(P_rows.mean())
@@ -566,7 +567,7 @@ def run_b200(args, rank, world, local_rank):
         if cpu_legs is not None:
             line["cpu_baseline"], line["cpu_baseline_1core"], line["cpu_baseline_sparse"] = cpu_legs
         if world == 1 and not args.no_estimator_e2e:
-            line["e2e_estimator"] = estimator_e2e(flat, dev, make_test(n, F, seed=0), qs, head, out_all)
+            line["e2e_estimator"] = estimator_e2e(flat, dev, X_all, qs, head, out_all)
         print(json.dumps(line), flush=True)
         if parity is not None and not parity["ok"]:
             log("[bench] PARITY FAILURE on the timed output: %s" % json.dumps(parity))

@@ -243,8 +243,9 @@ apply_wide_rows_kernel(const ApplyParams p, void* __restrict__ out) {
 // The order inside a bucket is whatever the atomics give; results do not depend on it
 // (every row is computed independently and written to its own output row).
 // ---------------------------------------------------------------------------------------
-constexpr int kKeyBins = 8192;                         // counters in the histogram (8 per scan thread)
-constexpr int kScanThreads = kKeyBins / 8;
+constexpr int kKeyBins = 8192;                         // default number of histogram counters
+constexpr int kKeyBinsMax = 1 << 18;                   // option "key_bins": up to this many (multiples of 8192)
+constexpr int kScanThreads = 1024;
 
 // lane == row; x is read straight from global memory (a row is one or two lines, L1-resident
 // after the first touch), so there is no tile staging and no barrier for a single tree
@@ -270,13 +271,19 @@ locality_key_kernel(const uint2* __restrict__ nodes, uint32_t root, const float*
     atomicAdd(hist + b, 1);
 }
 
+// single CTA: in-place exclusive prefix sum of `nbins` counters (a multiple of 4 * kScanThreads),
+// nbins / kScanThreads consecutive counters per thread
 __global__ void __launch_bounds__(kScanThreads)
-exclusive_scan_kernel(int* __restrict__ hist) {
+exclusive_scan_kernel(int* __restrict__ hist, int nbins) {
     __shared__ int warp_tot[kScanThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int4 a = reinterpret_cast<int4*>(hist)[2 * tid];
-    int4 b = reinterpret_cast<int4*>(hist)[2 * tid + 1];
-    const int sum = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+    const int per = nbins / kScanThreads;               // multiple of 4
+    int4* __restrict__ mine = reinterpret_cast<int4*>(hist + tid * per);
+    int sum = 0;
+    for (int k = 0; k < per / 4; ++k) {
+        const int4 a = mine[k];
+        sum += a.x + a.y + a.z + a.w;
+    }
     int incl = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -297,11 +304,12 @@ exclusive_scan_kernel(int* __restrict__ hist) {
     }
     __syncthreads();
     int run = warp_tot[warp] + incl - sum;
-    int4 oa, ob;
-    oa.x = run; run += a.x; oa.y = run; run += a.y; oa.z = run; run += a.z; oa.w = run; run += a.w;
-    ob.x = run; run += b.x; ob.y = run; run += b.y; ob.z = run; run += b.z; ob.w = run;
-    reinterpret_cast<int4*>(hist)[2 * tid] = oa;
-    reinterpret_cast<int4*>(hist)[2 * tid + 1] = ob;
+    for (int k = 0; k < per / 4; ++k) {
+        const int4 a = mine[k];
+        int4 o;
+        o.x = run; run += a.x; o.y = run; run += a.y; o.z = run; run += a.z; o.w = run; run += a.w;
+        mine[k] = o;
+    }
 }
 
 __global__ void order_scatter_kernel(const int* __restrict__ bucket, int64_t n, int* __restrict__ cursor,

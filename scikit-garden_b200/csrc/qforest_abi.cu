@@ -101,6 +101,7 @@ struct qf_forest {
     int apply_levels = qf::kApplyLevels;   // visits between two warp votes (1, 2, 3, 4; ILP 4 only)
     int sort_rows = -1;           // walk rows in locality order: -1 auto, 0 never, 1 always
     int key_shift = 0, key_bins = 1;   // locality buckets = first member of the leaf in tree 0 >> key_shift
+    int key_hist = qf::kKeyBins;       // histogram counters (>= key_bins; option "key_bins")
     uint32_t root0 = 0;
     int64_t rows_per_chunk = 262144;    // rows per kernel chunk (denser chunks = closer neighbours in the locality order: C3-quarter K1 2.66 -> 2.52 ms against 131072)
     int cta_capacity = 0;         // cap on the members per row of the first bucket stage (0 = its capacity)
@@ -210,6 +211,17 @@ struct Plan {
 
 constexpr int kMaxBucketThreads = 512;
 
+// locality buckets: first member of the leaf reached in tree 0 (members of the first tree start at 0
+// and there are at most n_train of them) >> key_shift, at most `counters` buckets
+void set_key_bins(qf_forest* f, int counters) {
+    const int64_t n0 = f->N;
+    int shift = 0;
+    while (((n0 - 1) >> shift) >= counters) ++shift;
+    f->key_shift = shift;
+    f->key_bins = static_cast<int>(((n0 - 1) >> shift) + 1);
+    f->key_hist = counters;
+}
+
 Plan make_plan(const qf_forest* f, int64_t n_rows, int64_t rows_per_chunk = 0) {
     Plan pl;
     if (rows_per_chunk <= 0) rows_per_chunk = f->rows_per_chunk;
@@ -261,7 +273,7 @@ Plan make_plan(const qf_forest* f, int64_t n_rows, int64_t rows_per_chunk = 0) {
     pl.sort_rows = f->sort_rows > 0 || (f->sort_rows < 0 && n_rows >= 2048);
     pl.off_bucket = o; o += align_up(pl.chunk_rows * 4);
     pl.off_order = o;  o += align_up(pl.chunk_rows * 4);
-    pl.off_hist = o;   o += align_up(qf::kKeyBins * 4);
+    pl.off_hist = o;   o += align_up(static_cast<int64_t>(f->key_hist) * 4);
     pl.off_dense = o;  o += pl.dense_needed ? qf::dense_scratch_bytes(f->N) * pl.dense_ctas : 0;
     pl.total = o;
     return pl;
@@ -357,7 +369,7 @@ int build_locality_order(qf_forest* f, CallStats& cs, const float* X, int64_t n,
     int* bucket = reinterpret_cast<int*>(base + pl.off_bucket);
     int* order = reinterpret_cast<int*>(base + pl.off_order);
     int* hist = reinterpret_cast<int*>(base + pl.off_hist);
-    QF_CUDA_TRY(cudaMemsetAsync(hist, 0, qf::kKeyBins * sizeof(int), st));
+    QF_CUDA_TRY(cudaMemsetAsync(hist, 0, static_cast<size_t>(f->key_hist) * sizeof(int), st));
     {
         SpanTimer span(f, cs, SPAN_OTHER, st);
         qf::locality_key_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(
@@ -366,7 +378,7 @@ int build_locality_order(qf_forest* f, CallStats& cs, const float* X, int64_t n,
     QF_CUDA_TRY(cudaGetLastError());
     {
         SpanTimer span(f, cs, SPAN_OTHER, st);
-        qf::exclusive_scan_kernel<<<1, qf::kScanThreads, 0, st>>>(hist);
+        qf::exclusive_scan_kernel<<<1, qf::kScanThreads, 0, st>>>(hist, f->key_hist);
     }
     QF_CUDA_TRY(cudaGetLastError());
     {
@@ -865,12 +877,8 @@ int qf_forest_create(const qf_forest_desc* d, qf_forest** out) {
                                                           : static_cast<double>(f->max_row_members);
     {   // locality buckets: first member of the leaf reached in tree 0 (members of the first tree
         // start at 0 and there are at most n_train of them), at most kKeyBins buckets
-        const int64_t n0 = d->n_train;
-        int shift = 0;
-        while (((n0 - 1) >> shift) >= qf::kKeyBins) ++shift;
         f->root0 = static_cast<uint32_t>(d->tree_offsets[0]);
-        f->key_shift = shift;
-        f->key_bins = static_cast<int>(((n0 - 1) >> shift) + 1);
+        set_key_bins(f, qf::kKeyBins);
     }
     f->sm_count = prop.multiProcessorCount;
 
@@ -1078,6 +1086,10 @@ int qf_forest_set_option(qf_forest* f, const char* key, int64_t value) {
         if (value < 1 || value > qf::kSelectL2Bits)
             return qf::fail(QF_ERR_INVALID, "select_bits must be in [1, 10]");
         f->select_bits = static_cast<int>(value);
+    } else if (k == "key_bins") {
+        if (value < qf::kKeyBins || value > qf::kKeyBinsMax || value % qf::kKeyBins != 0)
+            return qf::fail(QF_ERR_INVALID, "key_bins must be a multiple of 8192 in [8192, 262144]");
+        set_key_bins(f, static_cast<int>(value));
     } else if (k == "select3_variant") {
         if (value != 0 && value != 1) return qf::fail(QF_ERR_INVALID, "select3_variant must be 0 or 1");
         f->select3_variant = static_cast<int>(value);

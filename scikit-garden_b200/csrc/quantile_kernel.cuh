@@ -682,15 +682,21 @@ quantile_bucket_kernel(const QuantileParams p, const __grid_constant__ QuantileL
     // 5. lane 0: float32 running sum in rank order (utils.py:68), 4 entries per shared access
     float* cum = reinterpret_cast<float*>(srt);
     if (tid == 0) {
+        // the chain of dependent float32 adds is the floor (4 cycles each); the loads run two chunks ahead
+        // of it so that no add ever waits for shared memory (wt is padded: reads past m stay inside it)
         float C = 0.0f;
+        float4 w4 = *reinterpret_cast<const float4*>(wt);
+        float4 n4 = *reinterpret_cast<const float4*>(wt + 4);
         for (int c = 0; c < m; c += 4) {
-            const float4 w4 = *reinterpret_cast<const float4*>(wt + c);
+            const float4 f4 = *reinterpret_cast<const float4*>(wt + min(c + 8, CAP - 4));
             float4 o;
             C = __fadd_rn(C, w4.x); o.x = C;
             C = __fadd_rn(C, w4.y); o.y = C;
             C = __fadd_rn(C, w4.z); o.z = C;
             C = __fadd_rn(C, w4.w); o.w = C;
             *reinterpret_cast<float4*>(cum + c) = o;
+            w4 = n4;
+            n4 = f4;
         }
     }
     __syncthreads();
