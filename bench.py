@@ -245,7 +245,7 @@ def measure_cpu_legs(wl, cfg, qs, budget_s=12.0):
     cpu_reference_setup(wl)
     # (b) all host cores: forked workers on disjoint row chunks
     _, dt = cpu_reference_throughput(q3, 1, workers)              # calibrate: 1 row per worker
-    rows = int(max(1, min(256, budget_s / max(dt, 1e-3))))
+    rows = int(max(1, min(256, np.ceil(budget_s / max(dt, 1e-3)))))
     thr, dt = cpu_reference_throughput(q3, rows, workers)
     what = ("dense O(T*N)-per-row algorithm of ensemble.py:137-142 + utils.py:46-81 (oracle.predict_dense, "
             "pinned bit-identical to the reference; the reference is Python and cannot travel to the GPU box); "
@@ -633,18 +633,20 @@ def run_reference(args, rank, world):
     wl = load_workload(args.config, cfg, use_cache=not args.no_cache)
     workers = max(1, min(host_cores(), 64, _memory_bound_workers(cfg)))
     cpu_reference_setup(wl)
-    _, dt1 = cpu_reference_throughput(qs, 1, workers)
-    # bounded: the whole --steps/--warmup run should end within a few minutes
-    rows = int(max(1, min(64, (120.0 / max(1, args.steps + args.warmup)) / max(dt1, 1e-3))))
-    for _ in range(args.warmup):
-        cpu_reference_throughput(qs, rows, workers)
+    # one step = `rows` rows per worker for ONE of the workload's quantiles (the reference's API takes a scalar
+    # q, ensemble.py:104; the quantile rotates from step to step); bounded so that the whole --steps/--warmup
+    # run ends within a few minutes even at config 3 (2 s per row and quantile)
+    _, dt1 = cpu_reference_throughput(qs[:1], 1, workers)
+    rows = int(max(1, min(64, (90.0 / max(1, args.steps + args.warmup)) / max(dt1, 1e-3))))
+    for k in range(args.warmup):
+        cpu_reference_throughput([qs[k % len(qs)]], rows, workers)
     t_total = 0.0
-    for _ in range(args.steps):
-        _, dt = cpu_reference_throughput(qs, rows, workers)
+    for k in range(args.steps):
+        _, dt = cpu_reference_throughput([qs[k % len(qs)]], rows, workers)
         t_total += dt
-    per_step = rows * workers * len(qs)
+    per_step = rows * workers
     value = per_step * args.steps / t_total
-    sample_txt = ("each step = %d rows x %d quantiles (%d rows per worker, %d forked workers) of the same "
+    sample_txt = ("each step = %d rows x 1 quantile (of %d, rotating; %d rows per worker, %d forked workers) of the same "
                   "workload; dense O(T*N)-per-row algorithm (ensemble.py:137-142 + utils.py:46-81) as "
                   "restated in oracle/qrf_oracle.py (pinned bit-identical to the reference; the reference is "
                   "Python and cannot travel to the GPU box); leaf ids from scikit-learn's own apply"

@@ -17,6 +17,10 @@
  *   - "_dev" pointers are device pointers on the forest's device, "_host" are host
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
  *   - device entry points are asynchronous w.r.t. the host unless stated otherwise
+ *   - a qf_forest handle may be used from several host threads at once (each with its own stream,
+ *     workspace and output): per-call state lives in the call.  qf_forest_predict_quantiles_host calls
+ *     on one handle share its pipeline buffers and run one after the other; the "last call" counters
+ *     report whichever call returned last; qf_forest_set_option is not meant to race with calls
  *   - there is NO CPU fallback: device entry points fail with QF_ERR_CUDA when no
  *     usable sm_100 device is present
  */
@@ -44,7 +48,10 @@ typedef enum qf_status {
 #define QF_MODE_EXACT 0   /* bit-identical to the reference's float32 op order            */
 #define QF_MODE_FAST  1   /* histogram selection on fixed-point weights; <= 1e-4 relative to
                              the reference.  Forests whose leaf weights are too small for 32-bit
-                             fixed point (leaves of hundreds of members) take the exact kernels */
+                             fixed point (leaves of hundreds of members) take the exact kernels.
+                             Option "select_impl" = 3 runs it on compact leaf lists (32-byte octets of
+                             rank | bootstrap count words, built on the device on first use) with
+                             asynchronous copies; the default reads the 8-byte member array */
 
 int qf_abi_version(void);
 const char* qf_last_error(void);
@@ -215,8 +222,9 @@ int qf_forest_predict_mean_std(qf_forest* f, const float* X_dev, int64_t n_rows,
 
 /* End-to-end variant of qf_forest_predict_quantiles on HOST buffers: chunks the rows,
  * copies each chunk host->device, runs the kernels and copies the result back,
- * pipelined over three internal streams (H2D, kernels, D2H) and a ring of chunk buffers.  X_host / out_host should be pinned for
- * full PCIe bandwidth (pageable memory works, slower).  Synchronous: returns when
+ * pipelined over three internal streams (H2D, kernels, D2H) and a ring of chunk buffers.  X_host / out_host
+ * may be pinned (copied from / to directly) or pageable (staged through page-locked slots inside the call, one
+ * host memcpy per chunk that runs while the GPU is on the previous chunk).  Synchronous: returns when
  * out_host is complete.  chunk_rows <= 0 picks a default. */
 int qf_forest_predict_quantiles_host(qf_forest* f, const float* X_host, int64_t n_rows,
                                      int64_t ldx, const double* q_host, int32_t n_quantiles,

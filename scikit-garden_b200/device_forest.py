@@ -267,9 +267,9 @@ def assert_all_finite_parallel(X: np.ndarray, workers: int = 8, pool=None) -> No
 def stream_predict(replicas, chunks, quantiles, mode=_native.QF_MODE_EXACT, pinned=True, prepare=None):
     """Chunks of test rows through one or several forest replicas, results in order.
 
-    Two worker threads per replica: while one chunk is inside the pipelined host-buffer call
-    (H2D / kernels / D2H on three streams, csrc/qforest_abi.cu), the next one is being staged
-    into the second page-locked buffer, so the GPU never waits for the host copy; chunk k goes
+    Three worker threads per replica: while one chunk is inside the pipelined host-buffer call
+    (H2D / kernels / D2H on three streams, csrc/qforest_abi.cu), the next ones are being validated and
+    staged into their own page-locked buffers, so the GPU does not wait for the host copy; chunk k goes
     to replica k mod G.  ``pinned=False`` hands the caller's arrays to the C call as they are.
     ``prepare`` (chunk -> float32 C-contiguous array, may raise) runs in the worker threads."""
     import collections
@@ -297,7 +297,7 @@ def stream_predict(replicas, chunks, quantiles, mode=_native.QF_MODE_EXACT, pinn
         return os_.copy()
 
     pending = collections.deque()
-    depth = 2 * len(replicas)
+    depth = 3 * len(replicas)                           # chunks in flight: one in the GPU call, two being validated / staged
     with ThreadPoolExecutor(depth) as pool:
         k = 0
         for X in chunks:

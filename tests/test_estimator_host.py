@@ -113,3 +113,45 @@ def test_pickle_drops_device_state():
     assert back._device_forest is None
     assert_array_equal(back._flat.nodes, est._flat.nodes)
     est._device_forest = None
+
+
+def test_stream_predict_orders_results_and_rotates_replicas():
+    # host logic of the streaming front end (device_forest.stream_predict) with stand-in replicas:
+    # results come back in chunk order, chunk k goes to replica k mod G, an empty chunk yields an empty
+    # result, the caller's validation runs in the workers and its error reaches the consumer
+    import threading
+    import time
+    from skgarden_b200.device_forest import stream_predict
+
+    class FakeReplica:
+        n_features = 3
+
+        def __init__(self, tag):
+            self.tag, self.seen, self.lock = tag, [], threading.Lock()
+
+        def predict_quantiles_host(self, X, q, out_host=None, mode=0):
+            time.sleep(0.002 * (5 - int(X[0, 0]) % 5))          # later chunks finish earlier
+            with self.lock:
+                self.seen.append(int(X[0, 0]))
+            return np.repeat(X[:, :1].astype(np.float64), len(q), axis=1) + self.tag
+
+    reps = [FakeReplica(0.0), FakeReplica(0.5)]
+    chunks = [np.full((k % 4 + 1, 3), k, dtype=np.float32) for k in range(9)]
+    chunks.insert(4, np.empty((0, 3), dtype=np.float32))
+    out = list(stream_predict(reps, iter(chunks), [10, 90], pinned=False,
+                              prepare=lambda X: np.ascontiguousarray(X, dtype=np.float32)))
+    assert [o.shape for o in out] == [(c.shape[0], 2) for c in chunks]
+    nonempty = [c for c in chunks if c.shape[0]]
+    got = [o for o in out if o.shape[0]]
+    for k, (c, o) in enumerate(zip(nonempty, got)):
+        assert np.all(o == c[0, 0] + (0.5 if k % 2 else 0.0))     # in order, replica k mod 2
+    assert sorted(reps[0].seen) == [0, 2, 4, 6, 8] and sorted(reps[1].seen) == [1, 3, 5, 7]
+
+    def bad(X):
+        if X[0, 0] == 3:
+            raise ValueError("Input X contains NaN.")
+        return X
+    with pytest.raises(ValueError, match="NaN"):
+        list(stream_predict(reps, iter(chunks), [50], pinned=False, prepare=bad))
+    with pytest.raises(ValueError, match="expects"):
+        list(stream_predict(reps, [np.zeros((2, 4), dtype=np.float32)], [50], pinned=False))

@@ -18,7 +18,7 @@ def main():
             if take:
                 lines.append(ln.strip())
             continue
-        if take and re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
+        if take and re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
             lines.append(re.sub(r"\s*/\* 0x[0-9a-f]+ \*/\s*$", "", ln).rstrip())
     if first:
         idx = [i for i, l in enumerate(lines) if first.search(l)]
