@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libqforest_b200.so")
 SOURCES = ["qforest_abi.cu", "pack_forest.cpp"]
-HEADERS = ["apply_kernel.cuh", "quantile_kernel.cuh", "select_kernel.cuh", "select2_kernel.cuh", "select3_kernel.cuh", "compact_lists.cuh", "csr_builder.cuh", "qf_internal.h",
+HEADERS = ["apply_kernel.cuh", "quantile_kernel.cuh", "select_kernel.cuh", "select2_kernel.cuh", "select3_kernel.cuh", "select4_kernel.cuh", "compact_lists.cuh", "csr_builder.cuh", "qf_internal.h",
            os.path.join("..", "..", "include", "qforest_b200.h")]
 
 NVCC_FLAGS = [

@@ -19,6 +19,7 @@
 #include "select2_kernel.cuh"
 #include "compact_lists.cuh"
 #include "select3_kernel.cuh"
+#include "select4_kernel.cuh"
 #include "csr_builder.cuh"
 
 namespace qf {
@@ -106,11 +107,14 @@ struct qf_forest {
     int64_t rows_per_chunk = 262144;    // rows per kernel chunk (denser chunks = closer neighbours in the locality order: C3-quarter K1 2.66 -> 2.52 ms against 131072)
     int cta_capacity = 0;         // cap on the members per row of the first bucket stage (0 = its capacity)
     int select_bits = qf::kSelectL2Bits;   // log2 refinement slots of the selection kernel (tests lower it)
+    int select4_hits = qf::kSelect4Hits;   // hit-list entries a row may use before select4 narrows instead (tests shrink it)
+    int select4_extras = 0;                // entries of select4's extra-octet list (0 = auto; tests shrink it)
     int select3_capw = 0;                  // octets per warp segment of the select3 stage (0 = auto; tests shrink it)
     int select3_variant = 1;               // 0: 3 select warps, 2 stages, 2 CTAs per SM; 1: 1 select warp, 1 stage, 3 CTAs per SM
     int select_impl = 0;                   // 0: auto (select2 when the training set allows, else the multi-level kernel);
-                                           // 1: always the multi-level kernel; 3: select3 on compact leaf lists when the forest
-                                           // and the call allow (<= 3 percentiles), else as 0
+                                           // 1: always the multi-level kernel; 3 / 4: select3 (CTA per row) / select4 (warp per
+                                           // row) on compact leaf lists when the forest and the call allow (<= 3 percentiles),
+                                           // else as 0
     int cta2_capacity = 8192;     // same for the 512-thread overflow stage (0 = stage not used)
     int warp_elems = -1;          // warp kernel: keys per lane (2, 4, 8), 0 = never, -1 = auto
     int warp_unit = 1;            // 0: never take the one-member-per-leaf gather of the warp kernel
@@ -206,7 +210,7 @@ struct Plan {
     bool dense_needed;
     int dense_ctas;
     bool sort_rows;                // rows are walked in locality order (bucket/order/hist in use)
-    int64_t off_seg, off_counts, off_rows[3], off_bucket, off_order, off_hist, off_dense, total;
+    int64_t off_seg, off_segT, off_counts, off_rows[3], off_bucket, off_order, off_hist, off_dense, total;
 };
 
 constexpr int kMaxBucketThreads = 512;
@@ -266,6 +270,8 @@ Plan make_plan(const qf_forest* f, int64_t n_rows, int64_t rows_per_chunk = 0) {
     // K1 output: (start, count) pairs row-major, or one 32-bit list word per (tree, row) tree-major
     // with rows padded to a multiple of four (select3)
     pl.off_seg = o;    o += align_up(std::max<int64_t>(pl.chunk_rows * f->T * 8, ((pl.chunk_rows + 3) & ~int64_t(3)) * f->T * 4));
+    // select4: K1's tree-major list words, transposed into off_seg
+    pl.off_segT = o;   o += f->select_impl == 4 ? align_up(((pl.chunk_rows + 3) & ~int64_t(3)) * f->T * 4) : 0;
     pl.off_counts = o; o += kAlign;                               // one int counter per overflow list
     for (int k = 0; k < 3; ++k) { pl.off_rows[k] = o; o += align_up(pl.chunk_rows * 4); }
     // locality order is worth its three small launches once there are enough rows for
@@ -623,6 +629,66 @@ bool select3_finish_geometry(const qf_forest* f, Select3Geometry& g) {
     return g.ok;
 }
 
+// select4 (warp per row): geometry or ok = false
+struct Select4Geometry {
+    bool ok = false;
+    int shift = 0, lpl = 1, extras_cap = 0;
+    float fx_scale = 0.0f;
+    size_t smem = 0;
+};
+
+Select4Geometry select4_geometry(const qf_forest* f, int nq) {
+    Select4Geometry g;
+    if (f->select_impl != 4 || nq > qf::kSelect2QB || f->T > 32 * qf::kSelect4MaxLPL) return g;
+    int k = 0;
+    const int64_t bound = std::max<int64_t>(f->T, f->row_weight_bound);
+    while ((int64_t(1) << k) < bound + 1) ++k;
+    if (k > 20) return g;
+    int nbits = 0;
+    while ((int64_t(1) << nbits) < f->N) ++nbits;
+    if (nbits > 24) return g;
+    g.fx_scale = static_cast<float>(int64_t(1) << (31 - k));
+    g.shift = std::max(0, nbits - qf::kSelect4LogNB);
+    int lpl = 1;
+    while (32 * lpl < f->T) lpl <<= 1;
+    g.lpl = lpl;
+    return g;
+}
+
+bool select4_finish_geometry(const qf_forest* f, Select4Geometry& g) {
+    if (f->compact_state != 1 || static_cast<int>(f->tree_octets.size()) != f->T) return false;
+    double extras = 0.0;                                // octets beyond the first a row expects
+    for (int t = 0; t < f->T; ++t) extras += std::max(0.0, f->tree_octets[t] - 1.0);
+    int cap = static_cast<int>(extras * 1.3) + 64;
+    if (f->select4_extras > 0) cap = f->select4_extras;
+    cap = std::min((cap + 31) & ~31, 4096);
+    g.extras_cap = cap;
+    g.smem = qf::select4_warp_smem(cap) * qf::kSelect4Warps;
+    g.ok = g.smem <= 200 * 1024;
+    return g.ok;
+}
+
+int launch_select4_kernel(const qf_forest* f, const Select4Geometry& g, const qf::Select4Params& sp,
+                          const qf::QuantileList& ql, cudaStream_t st) {
+    const int64_t want = (sp.n + qf::kSelect4Warps - 1) / qf::kSelect4Warps;
+    const int per_sm = std::max<int>(1, std::min<int>(qf::kSelect4CtasPerSm, static_cast<int>((220 * 1024) / std::max<size_t>(g.smem, 1))));
+    const unsigned grid = static_cast<unsigned>(std::min<int64_t>(want, int64_t(f->sm_count) * per_sm));
+    auto run = [&](auto kernel) -> int {
+        int rc = set_smem(kernel, g.smem);
+        if (rc != QF_OK) return rc;
+        kernel<<<grid, qf::kSelect4Threads, g.smem, st>>>(sp, ql);
+        return QF_OK;
+    };
+    switch (g.lpl) {
+        case 1: return run(qf::quantile_select4_kernel<1>);
+        case 2: return run(qf::quantile_select4_kernel<2>);
+        case 4: return run(qf::quantile_select4_kernel<4>);
+        case 8: return run(qf::quantile_select4_kernel<8>);
+        case 16: return run(qf::quantile_select4_kernel<16>);
+        default: return run(qf::quantile_select4_kernel<32>);
+    }
+}
+
 int launch_select3_kernel(const qf_forest* f, const Select3Geometry& g, const qf::Select3Params& sp,
                           const qf::QuantileList& ql, cudaStream_t st) {
     const int64_t n_groups = (sp.n + qf::kSelect3RowGroup - 1) / qf::kSelect3RowGroup;
@@ -692,12 +758,60 @@ int quantiles_on_stream(qf_forest* f, CallStats& cs, const float* X, int64_t n, 
         }
     }
     const int64_t ld3 = (pl.chunk_rows + 3) & ~int64_t(3);
+    Select4Geometry g4;
+    if (select && pl.warp_elems == 0) {
+        g4 = select4_geometry(f, nq);
+        if (g4.fx_scale > 0.0f) {
+            int rc = ensure_compact(f);
+            if (rc != QF_OK) return rc;
+            select4_finish_geometry(f, g4);
+        }
+    }
+    const int64_t ldT = (f->T + 3) & ~3;
 
     for (int64_t r0 = 0; r0 < n; r0 += pl.chunk_rows) {
         const int64_t rows = std::min(pl.chunk_rows, n - r0);
         const int* order = nullptr;
         int rc = build_locality_order(f, cs, X + r0 * ldx, rows, ldx, pl, base, st, &order);
         if (rc != QF_OK) return rc;
+        if (g4.ok) {                                    // warp per row: K1 tree-major -> transpose -> select4
+            uint32_t* segT = reinterpret_cast<uint32_t*>(base + pl.off_segT);
+            rc = launch_apply<qf::APPLY_EMIT_COMPACT>(f, cs, X + r0 * ldx, rows, ldx, segT, order, 0, f->T, st, ld3);
+            if (rc != QF_OK) return rc;
+            {
+                SpanTimer span(f, cs, SPAN_OTHER, st);
+                const dim3 tgrid(static_cast<unsigned>((rows + 31) / 32), static_cast<unsigned>((ldT + 31) / 32));
+                qf::transpose_words_kernel<<<tgrid, 256, 0, st>>>(segT, ld3, f->T, rows, reinterpret_cast<uint32_t*>(seg), ldT);
+            }
+            QF_CUDA_TRY(cudaGetLastError());
+            ++cs.launches;
+            qf::QuantileList ql;
+            std::memset(&ql, 0, sizeof(ql));
+            for (int i = 0; i < nq; ++i) ql.q[i] = q_host[i];
+            qf::Select4Params sp;
+            sp.seg = reinterpret_cast<const uint32_t*>(seg);
+            sp.ldT = ldT;
+            sp.order = order;
+            sp.lists = f->d_lists;
+            sp.y_sorted = f->d_y_sorted;
+            sp.out = out + r0 * nq;
+            sp.n = rows;
+            sp.ldo = nq;
+            sp.T = f->T;
+            sp.Q = nq;
+            sp.fx_scale = g4.fx_scale;
+            sp.shift = g4.shift;
+            sp.extras_cap = g4.extras_cap;
+            sp.hits_cap = std::min(f->select4_hits, qf::kSelect4Hits);
+            {
+                SpanTimer span(f, cs, SPAN_QUANTILE, st);
+                rc = launch_select4_kernel(f, g4, sp, ql, st);
+            }
+            if (rc != QF_OK) return rc;
+            QF_CUDA_TRY(cudaGetLastError());
+            ++cs.launches;
+            continue;
+        }
         if (g3.ok) {
             rc = launch_apply<qf::APPLY_EMIT_COMPACT>(f, cs, X + r0 * ldx, rows, ldx, seg, order, 0, f->T, st, ld3);
             if (rc != QF_OK) return rc;
@@ -1003,13 +1117,19 @@ int qf_forest_quantile_kernel_name(qf_forest* f, int64_t n_rows, int32_t nq, int
         std::snprintf(name, sizeof(name), "quantile_warp_kernel<%d>", pl.warp_elems);
     } else if (select) {
         Select3Geometry g3 = select3_geometry(f, nq);
-        if (g3.fx_scale > 0.0f) {
+        Select4Geometry g4 = select4_geometry(f, nq);
+        if (g3.fx_scale > 0.0f || g4.fx_scale > 0.0f) {
             DeviceGuard guard(f->device);
-            if (ensure_compact(f) == QF_OK) select3_finish_geometry(f, g3);
+            if (ensure_compact(f) == QF_OK) {
+                if (g3.fx_scale > 0.0f) select3_finish_geometry(f, g3);
+                if (g4.fx_scale > 0.0f) select4_finish_geometry(f, g4);
+            }
         }
         int nbits = 0;
         while ((int64_t(1) << nbits) < f->N) ++nbits;
-        if (g3.ok)
+        if (g4.ok)
+            std::snprintf(name, sizeof(name), "quantile_select4_kernel<%d>", g4.lpl);
+        else if (g3.ok)
             std::snprintf(name, sizeof(name), "quantile_select3_kernel<%d, %d, %d, %d>", g3.log2nb, g3.ipt, g3.selw, g3.stages);
         else if (f->select_impl != 1 && f->select_bits == qf::kSelectL2Bits && nbits <= 12 + qf::kSelect2SlotBits &&
                  f->T <= qf::kSelect2MaxIPT * qf::kSelect2Threads)
@@ -1080,7 +1200,7 @@ int qf_forest_set_option(qf_forest* f, const char* key, int64_t value) {
         if (value != 0 && value != 1) return qf::fail(QF_ERR_INVALID, "warp_unit must be 0 or 1");
         f->warp_unit = static_cast<int>(value);
     } else if (k == "select_impl") {
-        if (value < 0 || value > 3) return qf::fail(QF_ERR_INVALID, "select_impl must be 0 (auto), 1 (multi-level), 2 (select2) or 3 (select3)");
+        if (value < 0 || value > 4) return qf::fail(QF_ERR_INVALID, "select_impl must be 0 (auto), 1 (multi-level), 2 (select2), 3 (select3) or 4 (select4)");
         f->select_impl = static_cast<int>(value);
     } else if (k == "select_bits") {
         if (value < 1 || value > qf::kSelectL2Bits)
@@ -1090,6 +1210,12 @@ int qf_forest_set_option(qf_forest* f, const char* key, int64_t value) {
         if (value < qf::kKeyBins || value > qf::kKeyBinsMax || value % qf::kKeyBins != 0)
             return qf::fail(QF_ERR_INVALID, "key_bins must be a multiple of 8192 in [8192, 262144]");
         set_key_bins(f, static_cast<int>(value));
+    } else if (k == "select4_hits") {
+        if (value < 0 || value > qf::kSelect4Hits) return qf::fail(QF_ERR_INVALID, "select4_hits must be in [0, 256]");
+        f->select4_hits = static_cast<int>(value);
+    } else if (k == "select4_extras") {
+        if (value < 0 || value > 4096) return qf::fail(QF_ERR_INVALID, "select4_extras must be in [0, 4096]");
+        f->select4_extras = static_cast<int>(value);
     } else if (k == "select3_variant") {
         if (value != 0 && value != 1) return qf::fail(QF_ERR_INVALID, "select3_variant must be 0 or 1");
         f->select3_variant = static_cast<int>(value);

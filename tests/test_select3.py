@@ -279,3 +279,51 @@ def test_devices_list_shards_rows_over_replicas():
     m2, s2 = std_many.predict(Xt, return_std=True)
     assert_array_equal(m1, m2)
     assert_array_equal(s1, s2)
+
+
+# ---- select4: the warp-per-row form of the same arithmetic (csrc/select4_kernel.cuh) ---------------
+@pytest.mark.parametrize("name", _golden.CASES)
+@pytest.mark.parametrize("hits,extras", [(256, 0), (0, 0), (256, 32), (3, 32)])
+def test_select4_equals_select3_bit_for_bit(name, hits, extras):
+    # same fixed-point weights and the same definition of the crossing entry and its neighbours: the
+    # sorted-hit-list path (hits=256), the exact narrowing path (hits=0: every row overflows the list;
+    # hits=3: some do) and the leaf-by-leaf second sweep (extras=32 entries only) must return the bits
+    # select3 returns, which tests above pin to the reference's outputs within 1e-4
+    g = _golden.load(name)
+    flat = _golden.flat_from_golden(g)
+    d3 = _dev(flat, warp_elems=0, select_impl=3)
+    d4 = _dev(flat, warp_elems=0, select_impl=4, select4_hits=hits, select4_extras=extras)
+    X = _cuda(g.X_test)
+    scale = np.abs(g.y_train).max()
+    for lo in range(0, len(g.q), 3):
+        qs = g.q[lo:lo + 3]
+        n3 = d3.quantile_kernel_name(len(g.X_test), len(qs), FAST)
+        n4 = d4.quantile_kernel_name(len(g.X_test), len(qs), FAST)
+        got = d4.predict_quantiles(X, qs, mode=FAST).cpu().numpy()
+        if n3.startswith("quantile_select3") and n4.startswith("quantile_select4"):
+            assert_array_equal(got, d3.predict_quantiles(X, qs, mode=FAST).cpu().numpy())
+        assert_allclose(got.T, g.pred[lo:lo + 3], rtol=1e-4, atol=1e-4 * scale)
+    if name in ("c1_rfqr_boston", "et_msl5", "rf_noboot_msl3_ties"):
+        assert d4.quantile_kernel_name(len(g.X_test), 3, FAST).startswith("quantile_select4_kernel")
+    d3.close()
+    d4.close()
+
+
+@pytest.mark.parametrize("T,msl,N", [(1, 8, 6000), (40, 5, 6000), (600, 12, 6000), (1000, 6, 3000)])
+@pytest.mark.parametrize("rows", [1, 33, 500])
+def test_select4_tree_counts_and_row_counts(T, msl, N, rows):
+    import skgarden_b200 as sg
+    Xtr, ytr, Xt = _atsize.make_data(N, 500, 5, seed=T)
+    est = sg.ExtraTreesQuantileRegressor(n_estimators=T, random_state=0, min_samples_leaf=msl, max_depth=9,
+                                         n_jobs=-1, mode="fast").fit(Xtr, ytr)
+    dev = est._on_device()
+    dev.set_option("warp_elems", 0)
+    qs = [5, 50, 95]
+    dev.set_option("select_impl", 3)
+    want = est.predict(Xt[:rows], quantile=qs)
+    dev.set_option("select_impl", 4)
+    if dev.quantile_kernel_name(rows, 3, FAST).startswith("quantile_select4"):
+        assert_array_equal(est.predict(Xt[:rows], quantile=qs), want)
+        dev.set_option("select4_hits", 16)
+        assert_array_equal(est.predict(Xt[:rows], quantile=qs), want)
+        assert_array_equal(est.predict(Xt[:rows], quantile=[50]), want[:, 1:2])
