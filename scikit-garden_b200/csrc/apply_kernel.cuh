@@ -53,15 +53,16 @@ struct ApplyParams {
     int F;
     int fbits;
     int row_warps;                         // warps along rows per CTA (block = 256 threads)
-    int64_t ld_out;                        // APPLY_EMIT_COMPACT: row stride (in words) of the tree-major output
+    int64_t ld_out;                        // APPLY_EMIT_COMPACT: out[tree * ld_out + pos * ld_row] -- tree-major (ld_row = 1,
+    int64_t ld_row;                        //   ld_out >= rows) for the CTA-per-row kernels, row-major (ld_out = 1) for select4
 };
 
 // what a finished walk writes
 //   SEGMENT: uint2 out[pos][T]   (member start, member count), pos = position in the locality order
 //   NODE   : int32 out[row][T]   packed node index of the leaf, row = row of X
-//   COMPACT: uint32 out[T][ld_out]  lo32 of the leaf node (the compact list word when the walk runs on
-//            the compact copy of the nodes, compact_lists.cuh), TREE-major: lane == row, so a warp
-//            writes 128 contiguous bytes per tree instead of 32 scattered sectors
+//   COMPACT: uint32 out[tree * ld_out + pos * ld_row]  lo32 of the leaf node (the compact list word when
+//            the walk runs on the compact copy of the nodes, compact_lists.cuh).  TREE-major (ld_row = 1):
+//            lane == row, so a warp writes 128 contiguous bytes per tree instead of 32 scattered sectors
 enum { APPLY_EMIT_SEGMENT = 0, APPLY_EMIT_NODE = 1, APPLY_EMIT_COMPACT = 2 };
 
 constexpr int kApplyThreads = 256;
@@ -189,7 +190,7 @@ apply_kernel(const ApplyParams p, void* __restrict__ out) {
                         static_cast<uint2*>(out)[out_row * p.T + tree[k]] =
                             make_uint2(nd[k].x, nd[k].y & 0x7fffffffu);
                     else if (EMIT == APPLY_EMIT_COMPACT)
-                        static_cast<uint32_t*>(out)[static_cast<int64_t>(tree[k]) * p.ld_out + out_row] = nd[k].x;
+                        static_cast<uint32_t*>(out)[static_cast<int64_t>(tree[k]) * p.ld_out + out_row * p.ld_row] = nd[k].x;
                     else
                         static_cast<int32_t*>(out)[out_row * p.T + tree[k]] = static_cast<int32_t>(node[k]);
                 }
@@ -229,7 +230,7 @@ apply_wide_rows_kernel(const ApplyParams p, void* __restrict__ out) {
         if (EMIT == APPLY_EMIT_SEGMENT)
             static_cast<uint2*>(out)[pos * p.T + t] = make_uint2(nd.x, nd.y & 0x7fffffffu);
         else if (EMIT == APPLY_EMIT_COMPACT)
-            static_cast<uint32_t*>(out)[static_cast<int64_t>(t) * p.ld_out + pos] = nd.x;
+            static_cast<uint32_t*>(out)[static_cast<int64_t>(t) * p.ld_out + pos * p.ld_row] = nd.x;
         else
             static_cast<int32_t*>(out)[row * p.T + t] = static_cast<int32_t>(node);
     }

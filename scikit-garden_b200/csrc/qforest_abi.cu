@@ -108,6 +108,7 @@ struct qf_forest {
     int cta_capacity = 0;         // cap on the members per row of the first bucket stage (0 = its capacity)
     int select_bits = qf::kSelectL2Bits;   // log2 refinement slots of the selection kernel (tests lower it)
     int select4_hits = qf::kSelect4Hits;   // hit-list entries a row may use before select4 narrows instead (tests shrink it)
+    int select4_ctas = 4;                  // CTAs per SM select4 is compiled and launched for (3 or 4)
     int select4_extras = 0;                // entries of select4's extra-octet list (0 = auto; tests shrink it)
     int select3_capw = 0;                  // octets per warp segment of the select3 stage (0 = auto; tests shrink it)
     int select3_variant = 1;               // 0: 3 select warps, 2 stages, 2 CTAs per SM; 1: 1 select warp, 1 stage, 3 CTAs per SM
@@ -210,7 +211,7 @@ struct Plan {
     bool dense_needed;
     int dense_ctas;
     bool sort_rows;                // rows are walked in locality order (bucket/order/hist in use)
-    int64_t off_seg, off_segT, off_counts, off_rows[3], off_bucket, off_order, off_hist, off_dense, total;
+    int64_t off_seg, off_counts, off_rows[3], off_bucket, off_order, off_hist, off_dense, total;
 };
 
 constexpr int kMaxBucketThreads = 512;
@@ -268,10 +269,8 @@ Plan make_plan(const qf_forest* f, int64_t n_rows, int64_t rows_per_chunk = 0) {
     }
     int64_t o = 0;
     // K1 output: (start, count) pairs row-major, or one 32-bit list word per (tree, row) tree-major
-    // with rows padded to a multiple of four (select3)
+    // with rows padded to a multiple of four (select3), or row-major (select4)
     pl.off_seg = o;    o += align_up(std::max<int64_t>(pl.chunk_rows * f->T * 8, ((pl.chunk_rows + 3) & ~int64_t(3)) * f->T * 4));
-    // select4: K1's tree-major list words, transposed into off_seg
-    pl.off_segT = o;   o += f->select_impl == 4 ? align_up(((pl.chunk_rows + 3) & ~int64_t(3)) * f->T * 4) : 0;
     pl.off_counts = o; o += kAlign;                               // one int counter per overflow list
     for (int k = 0; k < 3; ++k) { pl.off_rows[k] = o; o += align_up(pl.chunk_rows * 4); }
     // locality order is worth its three small launches once there are enough rows for
@@ -308,10 +307,11 @@ int set_smem(Kernel kernel, size_t smem) {
 // nullable) is the locality order of the rows.
 template <int EMIT>
 int launch_apply(qf_forest* f, CallStats& cs, const float* X, int64_t n, int64_t ldx, void* out, const int* order,
-                 int t_begin, int t_end, cudaStream_t st, int64_t ld_out = 0) {
+                 int t_begin, int t_end, cudaStream_t st, int64_t ld_out = 0, int64_t ld_row = 1) {
     qf::ApplyParams ap;
     ap.nodes = EMIT == qf::APPLY_EMIT_COMPACT ? f->d_nodes_c : f->d_nodes;
     ap.ld_out = ld_out;
+    ap.ld_row = ld_row;
     ap.roots = f->d_roots;
     ap.X = X;
     ap.order = order;
@@ -632,14 +632,14 @@ bool select3_finish_geometry(const qf_forest* f, Select3Geometry& g) {
 // select4 (warp per row): geometry or ok = false
 struct Select4Geometry {
     bool ok = false;
-    int shift = 0, lpl = 1, extras_cap = 0;
+    int extras_cap = 0;
     float fx_scale = 0.0f;
     size_t smem = 0;
 };
 
 Select4Geometry select4_geometry(const qf_forest* f, int nq) {
     Select4Geometry g;
-    if (f->select_impl != 4 || nq > qf::kSelect2QB || f->T > 32 * qf::kSelect4MaxLPL) return g;
+    if (f->select_impl != 4 || nq > qf::kSelect2QB || f->T > qf::kSelect4MaxTrees) return g;
     int k = 0;
     const int64_t bound = std::max<int64_t>(f->T, f->row_weight_bound);
     while ((int64_t(1) << k) < bound + 1) ++k;
@@ -648,10 +648,6 @@ Select4Geometry select4_geometry(const qf_forest* f, int nq) {
     while ((int64_t(1) << nbits) < f->N) ++nbits;
     if (nbits > 24) return g;
     g.fx_scale = static_cast<float>(int64_t(1) << (31 - k));
-    g.shift = std::max(0, nbits - qf::kSelect4LogNB);
-    int lpl = 1;
-    while (32 * lpl < f->T) lpl <<= 1;
-    g.lpl = lpl;
     return g;
 }
 
@@ -671,7 +667,8 @@ bool select4_finish_geometry(const qf_forest* f, Select4Geometry& g) {
 int launch_select4_kernel(const qf_forest* f, const Select4Geometry& g, const qf::Select4Params& sp,
                           const qf::QuantileList& ql, cudaStream_t st) {
     const int64_t want = (sp.n + qf::kSelect4Warps - 1) / qf::kSelect4Warps;
-    const int per_sm = std::max<int>(1, std::min<int>(qf::kSelect4CtasPerSm, static_cast<int>((220 * 1024) / std::max<size_t>(g.smem, 1))));
+    const int wanted = f->select4_ctas == 3 ? 3 : qf::kSelect4CtasPerSm;
+    const int per_sm = std::max<int>(1, std::min<int>(wanted, static_cast<int>((220 * 1024) / std::max<size_t>(g.smem, 1))));
     const unsigned grid = static_cast<unsigned>(std::min<int64_t>(want, int64_t(f->sm_count) * per_sm));
     auto run = [&](auto kernel) -> int {
         int rc = set_smem(kernel, g.smem);
@@ -679,14 +676,7 @@ int launch_select4_kernel(const qf_forest* f, const Select4Geometry& g, const qf
         kernel<<<grid, qf::kSelect4Threads, g.smem, st>>>(sp, ql);
         return QF_OK;
     };
-    switch (g.lpl) {
-        case 1: return run(qf::quantile_select4_kernel<1>);
-        case 2: return run(qf::quantile_select4_kernel<2>);
-        case 4: return run(qf::quantile_select4_kernel<4>);
-        case 8: return run(qf::quantile_select4_kernel<8>);
-        case 16: return run(qf::quantile_select4_kernel<16>);
-        default: return run(qf::quantile_select4_kernel<32>);
-    }
+    return wanted == 3 ? run(qf::quantile_select4_kernel<3>) : run(qf::quantile_select4_kernel<4>);
 }
 
 int launch_select3_kernel(const qf_forest* f, const Select3Geometry& g, const qf::Select3Params& sp,
@@ -774,17 +764,9 @@ int quantiles_on_stream(qf_forest* f, CallStats& cs, const float* X, int64_t n, 
         const int* order = nullptr;
         int rc = build_locality_order(f, cs, X + r0 * ldx, rows, ldx, pl, base, st, &order);
         if (rc != QF_OK) return rc;
-        if (g4.ok) {                                    // warp per row: K1 tree-major -> transpose -> select4
-            uint32_t* segT = reinterpret_cast<uint32_t*>(base + pl.off_segT);
-            rc = launch_apply<qf::APPLY_EMIT_COMPACT>(f, cs, X + r0 * ldx, rows, ldx, segT, order, 0, f->T, st, ld3);
+        if (g4.ok) {                                    // warp per row: K1 writes the list words row-major
+            rc = launch_apply<qf::APPLY_EMIT_COMPACT>(f, cs, X + r0 * ldx, rows, ldx, seg, order, 0, f->T, st, 1, ldT);
             if (rc != QF_OK) return rc;
-            {
-                SpanTimer span(f, cs, SPAN_OTHER, st);
-                const dim3 tgrid(static_cast<unsigned>((rows + 31) / 32), static_cast<unsigned>((ldT + 31) / 32));
-                qf::transpose_words_kernel<<<tgrid, 256, 0, st>>>(segT, ld3, f->T, rows, reinterpret_cast<uint32_t*>(seg), ldT);
-            }
-            QF_CUDA_TRY(cudaGetLastError());
-            ++cs.launches;
             qf::QuantileList ql;
             std::memset(&ql, 0, sizeof(ql));
             for (int i = 0; i < nq; ++i) ql.q[i] = q_host[i];
@@ -800,7 +782,7 @@ int quantiles_on_stream(qf_forest* f, CallStats& cs, const float* X, int64_t n, 
             sp.T = f->T;
             sp.Q = nq;
             sp.fx_scale = g4.fx_scale;
-            sp.shift = g4.shift;
+            sp.n_train = static_cast<uint32_t>(f->N);
             sp.extras_cap = g4.extras_cap;
             sp.hits_cap = std::min(f->select4_hits, qf::kSelect4Hits);
             {
@@ -1128,7 +1110,7 @@ int qf_forest_quantile_kernel_name(qf_forest* f, int64_t n_rows, int32_t nq, int
         int nbits = 0;
         while ((int64_t(1) << nbits) < f->N) ++nbits;
         if (g4.ok)
-            std::snprintf(name, sizeof(name), "quantile_select4_kernel<%d>", g4.lpl);
+            std::snprintf(name, sizeof(name), "quantile_select4_kernel");
         else if (g3.ok)
             std::snprintf(name, sizeof(name), "quantile_select3_kernel<%d, %d, %d, %d>", g3.log2nb, g3.ipt, g3.selw, g3.stages);
         else if (f->select_impl != 1 && f->select_bits == qf::kSelectL2Bits && nbits <= 12 + qf::kSelect2SlotBits &&
@@ -1213,6 +1195,9 @@ int qf_forest_set_option(qf_forest* f, const char* key, int64_t value) {
     } else if (k == "select4_hits") {
         if (value < 0 || value > qf::kSelect4Hits) return qf::fail(QF_ERR_INVALID, "select4_hits must be in [0, 256]");
         f->select4_hits = static_cast<int>(value);
+    } else if (k == "select4_ctas") {
+        if (value != 3 && value != 4) return qf::fail(QF_ERR_INVALID, "select4_ctas must be 3 or 4");
+        f->select4_ctas = static_cast<int>(value);
     } else if (k == "select4_extras") {
         if (value < 0 || value > 4096) return qf::fail(QF_ERR_INVALID, "select4_extras must be in [0, 4096]");
         f->select4_extras = static_cast<int>(value);

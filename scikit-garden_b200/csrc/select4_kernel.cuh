@@ -8,20 +8,24 @@
 // 60-100 KB of it per row in flight (2-4 rows and ~25 warps per SM) and 2-3 k shared-memory wavefronts
 // per row -- and by the block barriers between their phases.  Here a row belongs to ONE warp:
 //
-//   state    8 KB of shared memory per row: a 1024-bucket histogram of the rank axis (4 KB), a 256-entry
-//            hit list (2 KB), a list of "extra" octets (<= 2 KB); 24 rows in flight per SM, each on
-//            its own warp, no block barrier anywhere (only __syncwarp).
-//   members  read straight from global memory / L2 (two 128-bit loads per octet, no staging): sweep A
-//            takes the first octet of each of the lane's leaves (perfectly balanced), sweep B the
-//            octets beyond the first of all the warp's leaves, flattened through the small list.  The
-//            second pass re-reads the same octets a few microseconds later: L2 hits.
-//   pass 1   one shared-memory RED per member into the coarse histogram.
-//   scan     lane totals of 32 consecutive buckets (bank-rotated reads), one warp scan; per percentile
-//            the group that holds the crossing is scanned across the lanes: crossing bucket bq, nearest
-//            non-empty neighbours bp / bn from ballots.  The marked buckets live in a 1024-bit map, 32
-//            bits per lane, tested with one SHFL per member -- no table in shared memory.
-//   pass 2   members of marked buckets (~100 of a row's 3300 at config 3) are appended to the hit list
-//            (ballot + popc, no atomics).
+//   state    ~5.5 KB of shared memory per row: a 1024-bucket histogram (4 KB, re-used as the hit list)
+//            and a list of "extra" octets; 32 rows in flight per SM, each on its own warp, no block
+//            barrier anywhere (only __syncwarp).
+//   members  read straight from global memory / L2, one 256-bit load per octet, no staging: sweep A
+//            takes the first octet of each of the lane's leaves (balanced: four leaves per lane at a
+//            time), sweep B the octets beyond the first of all the warp's leaves, flattened through
+//            the small list.  The second pass walks the octets in the REVERSE order of the first, so
+//            that what it re-reads first is what the L2 saw last.
+//   window   the members of a row sit in a narrow band of the rank axis (the conditional distribution
+//            of y).  The first 128 leaves give [lo, hi); the 1024 buckets cover that band only
+//            (bucket = clamp((rank - lo) >> s)), ranks outside fall into the two edge buckets.
+//   pass 1   one shared-memory RED per member into the histogram.
+//   scan     lane totals of 32 consecutive buckets (rotated 128-bit reads), one warp scan; per
+//            percentile the group that holds the crossing is scanned across the lanes: crossing bucket
+//            bq, nearest non-empty neighbours bp / bn from ballots.  The marked buckets live in a
+//            1024-bit map, 32 bits per lane, tested with one SHFL per member.
+//   pass 2   members of marked buckets (a few dozen of a row's 3300 at config 3) are appended to the
+//            hit list (shared-memory counter; their order does not matter, see select).
 //   select   the hits are sorted by rank in registers (bitonic network, 8 keys per lane), weights
 //            prefix-summed in that order, and lane q finds percentile q's crossing entry and its
 //            neighbours by binary search: because every member of bp, bq and bn is in the list, the
@@ -36,22 +40,23 @@
 #include "compact_lists.cuh"
 #include "quantile_kernel.cuh"
 #include "select2_kernel.cuh"
+#include "select3_kernel.cuh"
 
 namespace qf {
 
 constexpr int kSelect4Threads = 256;
 constexpr int kSelect4Warps = kSelect4Threads / 32;     // rows in flight per CTA
-constexpr int kSelect4CtasPerSm = 3;
+constexpr int kSelect4CtasPerSm = 4;
 constexpr int kSelect4LogNB = 10;
-constexpr int kSelect4NB = 1 << kSelect4LogNB;          // coarse buckets of the rank axis
+constexpr int kSelect4NB = 1 << kSelect4LogNB;          // buckets of the row's window of the rank axis
 constexpr int kSelect4Hits = 256;                       // hit list entries per row (8 keys per lane)
-constexpr int kSelect4MaxLPL = 32;                      // leaves per lane: T <= 1024
+constexpr int kSelect4MaxTrees = 4096;
 
 struct Select4Params {
-    const uint32_t* __restrict__ seg;      // [n][ldT] compact list words, ROW-major (transposed from K1's output)
+    const uint32_t* __restrict__ seg;      // [n][ldT] compact list words, ROW-major
     int64_t ldT;
     const int* __restrict__ order;         // [n] locality position -> output row; nullptr = identity
-    const uint4* __restrict__ lists;       // two uint4 per octet
+    const uint4* __restrict__ lists;       // two uint4 per octet (32-byte aligned)
     const float* __restrict__ y_sorted;    // [N]
     double* __restrict__ out;              // [n][ldo], indexed by output row
     int64_t n;
@@ -59,39 +64,23 @@ struct Select4Params {
     int T;
     int Q;                                 // <= kSelect2QB
     float fx_scale;
-    int shift;                             // coarse bucket = rank >> shift
+    uint32_t n_train;
     int extras_cap;                        // entries of the per-warp list of octets beyond a leaf's first
     int hits_cap;                          // <= kSelect4Hits
 };
 
 __host__ __device__ inline size_t select4_warp_smem(int extras_cap) {
-    return static_cast<size_t>(kSelect4NB) * 4 + static_cast<size_t>(kSelect4Hits) * 8 + static_cast<size_t>(extras_cap) * 4;
+    return static_cast<size_t>(kSelect4NB) * 4 + static_cast<size_t>(extras_cap) * 4 + 32;
 }
 
-// K1 writes the list words tree-major ([T][ld], coalesced for its lane = row mapping); a warp that owns a
-// row wants them row-major.  32 x 32 tile transpose through shared memory.
-__global__ void __launch_bounds__(256)
-transpose_words_kernel(const uint32_t* __restrict__ in, int64_t ld_in, int T, int64_t n, uint32_t* __restrict__ out,
-                       int64_t ld_out) {
-    __shared__ uint32_t tile[32][33];
-    const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 32;
-    const int t0 = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int k = ty; k < 32; k += 8) {                  // rows of the tile = trees
-        const int t = t0 + k;
-        const int64_t r = r0 + tx;
-        tile[k][tx] = (t < T && r < n) ? in[static_cast<int64_t>(t) * ld_in + r] : kCompactEmpty;
-    }
-    __syncthreads();
-    for (int k = ty; k < 32; k += 8) {                  // rows of the output = test rows
-        const int64_t r = r0 + k;
-        const int t = t0 + tx;
-        if (r < n && t < ld_out) out[r * ld_out + t] = tile[tx][k];
-    }
+__device__ __forceinline__ void ld_octet(const uint4* __restrict__ lists, uint32_t octet, uint32_t (&o)[8]) {
+    const uint4* src = lists + 2 * static_cast<size_t>(octet);
+    asm("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7])
+        : "l"(src));
 }
-
-template <int LPL>
-__global__ void __launch_bounds__(kSelect4Threads, kSelect4CtasPerSm)
+template <int CTAS_PER_SM>                               // 4: 64 registers (a few spills), 3: 80 registers
+__global__ void __launch_bounds__(kSelect4Threads, CTAS_PER_SM)
 quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileList ql) {
     constexpr int NB = kSelect4NB;
     constexpr uint32_t NONE = 0xffffffffu;
@@ -100,28 +89,25 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
     const int warp = threadIdx.x >> 5;
     const size_t wbytes = select4_warp_smem(p.extras_cap);
     uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + warp * wbytes);   // [NB], zero between rows
-    uint32_t* hit_r = hist + NB;                                              // [256] ranks -> sorted ranks
-    uint32_t* hit_w = hit_r + kSelect4Hits;                                   // [256] weights -> running sums
-    uint32_t* extras = hit_w + kSelect4Hits;                                  // [extras_cap] octet indices
+    uint32_t* hit_r = hist;                                                   // [256] ranks -> sorted ranks   } in the histogram's
+    uint32_t* hit_w = hist + kSelect4Hits;                                    // [256] weights -> running sums } place, after the scan
+    uint32_t* extras = hist + NB;                                             // [extras_cap] octet indices
+    uint32_t* n_hits = extras + p.extras_cap;                                 // hit counter, zero between rows
     const uint32_t hist_s = static_cast<uint32_t>(__cvta_generic_to_shared(hist));
-    const uint32_t shift = static_cast<uint32_t>(p.shift);
-    const uint32_t lt_lane = (1u << lane) - 1u;
     const float inv = __fdiv_rn(1.0f, p.fx_scale);
+    const int n_batches = (p.T + 127) >> 7;             // 4 leaves per lane at a time
+    const int n_slots = (p.T + 31) >> 5;                // leaves per lane
 
     for (int i = lane; i < NB; i += 32) hist[i] = 0u;
+    if (lane == 0) *n_hits = 0u;
     __syncwarp();
 
     const int64_t n_warps = static_cast<int64_t>(gridDim.x) * kSelect4Warps;
     for (int64_t pos = static_cast<int64_t>(blockIdx.x) * kSelect4Warps + warp; pos < p.n; pos += n_warps) {
-        // ---- the row's list words: leaf t = lane + 32 i
-        uint32_t w[LPL];
-#pragma unroll
-        for (int i = 0; i < LPL; ++i) {
-            const int t = lane + 32 * i;
-            w[i] = t < p.T ? __ldg(p.seg + pos * p.ldT + t) : kCompactEmpty;
-        }
-        // first member octet and octet count of leaf i (a long list starts with an info octet)
-        auto leaf = [&](uint32_t word, uint32_t& first, uint32_t& noct) {
+        const uint32_t* __restrict__ words = p.seg + pos * p.ldT;             // leaf t of this row: words[t]
+        // first member octet and octet count of a leaf (a long list starts with an info octet)
+        auto leaf = [&](int t, uint32_t& first, uint32_t& noct) {
+            const uint32_t word = t < p.T ? __ldg(words + t) : kCompactEmpty;
             first = word & kCompactOffMask;
             noct = word == kCompactEmpty ? 0u : (word >> 28) + 1u;
             if (noct > static_cast<uint32_t>(kCompactMaxOctets)) {
@@ -133,10 +119,10 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
         uint32_t n_extra;
         {
             uint32_t mine = 0u;
-#pragma unroll
-            for (int i = 0; i < LPL; ++i) {
+#pragma unroll 1
+            for (int i = 0; i < n_slots; ++i) {
                 uint32_t first, noct;
-                leaf(w[i], first, noct);
+                leaf(i * 32 + lane, first, noct);
                 mine += noct > 1u ? noct - 1u : 0u;
             }
             uint32_t incl = mine;
@@ -146,12 +132,12 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
                 if (lane >= d) incl += u;
             }
             n_extra = __shfl_sync(0xffffffffu, incl, 31);
-            if (n_extra <= static_cast<uint32_t>(p.extras_cap)) {
+            if (n_extra <= static_cast<uint32_t>(p.extras_cap) && mine != 0u) {
                 uint32_t at = incl - mine;
-#pragma unroll
-                for (int i = 0; i < LPL; ++i) {
+#pragma unroll 1
+                for (int i = 0; i < n_slots; ++i) {
                     uint32_t first, noct;
-                    leaf(w[i], first, noct);
+                    leaf(i * 32 + lane, first, noct);
                     for (uint32_t k = 1; k < noct; ++k) extras[at++] = first + k;
                 }
             }
@@ -159,63 +145,101 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
         }
         const bool flat = n_extra <= static_cast<uint32_t>(p.extras_cap);
 
-        // f(ok, a, b) on every octet of the row, all 32 lanes in step (f may vote); ok = false: a lane
-        // without an octet in this step (it sees octet 0 of the lists, to be ignored)
-        auto each_octet = [&](auto&& f) {
+        // f(ok, o) on the first octets of batch b (leaves 128 b + 32 k + lane), all 32 lanes in step;
+        // ok = false: a lane without an octet in this step (it sees octet 0 of the lists, to be ignored)
+        auto batch = [&](int b, auto&& f) {
+            uint32_t o[4][8];
+            bool ok[4];
 #pragma unroll
-            for (int i0 = 0; i0 < LPL; i0 += 4) {       // sweep A: the first octet of four leaves per lane at a time
-                uint4 a[4], b[4];
-                bool ok[4];
+            for (int k = 0; k < 4; ++k) {
+                uint32_t first, noct;
+                leaf(b * 128 + k * 32 + lane, first, noct);
+                ok[k] = noct != 0u;
+                ld_octet(p.lists, ok[k] ? first : 0u, o[k]);
+            }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (i0 + k < LPL) {
-                        uint32_t first, noct;
-                        leaf(w[i0 + k], first, noct);
-                        ok[k] = noct != 0u;
-                        const uint4* __restrict__ src = p.lists + 2 * static_cast<size_t>(ok[k] ? first : 0u);
-                        a[k] = __ldg(src);
-                        b[k] = __ldg(src + 1);
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (i0 + k < LPL) f(ok[k], a[k], b[k]);
+            for (int k = 0; k < 4; ++k) f(ok[k], o[k]);
+        };
+        // f on every octet of the row; `reverse` walks them in the opposite order
+        auto each_octet = [&](bool reverse, auto&& f) {
+            if (!reverse) {
+#pragma unroll 1
+                for (int b = 0; b < n_batches; ++b) batch(b, f);
             }
             if (flat) {                                 // sweep B: the other octets, flat over the lanes
-                for (uint32_t j0 = 0; j0 < n_extra; j0 += 32u) {
-                    const bool ok = j0 + lane < n_extra;
-                    const uint4* __restrict__ src = p.lists + 2 * static_cast<size_t>(ok ? extras[j0 + lane] : 0u);
-                    f(ok, __ldg(src), __ldg(src + 1));
+                const uint32_t steps = (n_extra + 31u) >> 5;
+#pragma unroll 1
+                for (uint32_t si = 0; si < steps; ++si) {
+                    const uint32_t j = ((reverse ? steps - 1u - si : si) << 5) + lane;
+                    const bool ok = j < n_extra;
+                    uint32_t o[8];
+                    ld_octet(p.lists, ok ? extras[j] : 0u, o);
+                    f(ok, o);
                 }
             } else {                                    // list too small for this row: leaf by leaf, lanes in step
 #pragma unroll 1
-                for (int i = 0; i < LPL; ++i) {
+                for (int i = 0; i < n_slots; ++i) {
                     uint32_t first, noct;
-                    leaf(w[i], first, noct);
+                    leaf(i * 32 + lane, first, noct);
                     const uint32_t most = __reduce_max_sync(0xffffffffu, noct);
                     for (uint32_t k = 1; k < most; ++k) {
                         const bool ok = k < noct;
-                        const uint4* __restrict__ src = p.lists + 2 * static_cast<size_t>(ok ? first + k : 0u);
-                        f(ok, __ldg(src), __ldg(src + 1));
+                        uint32_t o[8];
+                        ld_octet(p.lists, ok ? first + k : 0u, o);
+                        f(ok, o);
                     }
                 }
             }
+            if (reverse) {
+#pragma unroll 1
+                for (int b = n_batches - 1; b >= 0; --b) batch(b, f);
+            }
         };
 
-        // ---- pass 1: coarse bucket weights
-        each_octet([&](bool ok, const uint4& a, const uint4& b) {
-            const uint32_t U = ok ? a.x : 0u;
-            const uint32_t m[7] = {a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        // ---- the row's window of the rank axis, from its first 128 leaves (widened by a quarter each side)
+        uint32_t lo = NONE, wsh = 0u;                 // window: first rank, log2(ranks per bucket)
+        {
+            uint32_t hi = 0u;
+            batch(0, [&](bool ok, const uint32_t (&o)[8]) {
 #pragma unroll
-            for (int e = 0; e < 7; ++e)
-                red_add_shared(hist_s + (((m[e] & 0xffffffu) >> shift) << 2), (m[e] >> 24) * U);
+                for (int e = 1; e < 8; ++e) {
+                    const bool real = ok && (o[e] >> 24) != 0u;
+                    lo = min(lo, real ? (o[e] & 0xffffffu) : NONE);
+                    hi = max(hi, real ? (o[e] & 0xffffffu) : 0u);
+                }
+            });
+            lo = __reduce_min_sync(0xffffffffu, lo);
+            hi = __reduce_max_sync(0xffffffffu, hi);
+            if (lo > hi) { lo = 0u; hi = p.n_train - 1u; }          // nothing in the sample
+            const uint32_t margin = (hi - lo) >> 2;
+            lo = lo > margin ? lo - margin : 0u;
+            hi = min(hi + margin, p.n_train - 1u);
+            const int bits = 32 - __clz(hi - lo);                   // hi - lo < 2^bits
+            wsh = static_cast<uint32_t>(max(bits - kSelect4LogNB, 0));
+        }
+        // bucket of a rank: monotone, buckets 0 and NB - 1 also take what lies outside the window
+        auto bucket_of = [&](uint32_t rank) -> uint32_t { return min((max(rank, lo) - lo) >> wsh, static_cast<uint32_t>(NB - 1)); };
+        auto bucket_lo = [&](uint32_t b) -> uint32_t { return b == 0u ? 0u : lo + (b << wsh); };          // first rank
+        auto bucket_hi = [&](uint32_t b) -> uint32_t {                                                  // last rank + 1
+            return b == static_cast<uint32_t>(NB - 1) ? max(p.n_train, lo + (b << wsh) + 1u) : lo + ((b + 1u) << wsh);
+        };
+
+        // ---- pass 1: bucket weights
+        each_octet(false, [&](bool ok, const uint32_t (&o)[8]) {
+            const uint32_t U = ok ? o[0] : 0u;
+#pragma unroll
+            for (int e = 1; e < 8; ++e)
+                red_add_shared(hist_s + (bucket_of(o[e] & 0xffffffu) << 2), (o[e] >> 24) * U);
         });
         __syncwarp();
 
-        // ---- scan: lane l owns buckets [32 l, 32 l + 32); reads rotated by the lane (no bank conflicts)
+        // ---- scan: lane l owns buckets [32 l, 32 l + 32); 128-bit reads rotated by the lane (no bank conflicts)
         uint32_t mine = 0u;
-#pragma unroll 8
-        for (int j = 0; j < 32; ++j) mine += ld_shared_u32(hist_s + (lane * 32 + ((j + lane) & 31)) * 4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint4 v = ld_shared_v4(hist_s + (lane * 32 + ((j + lane) & 7) * 4) * 4);
+            mine += (v.x + v.y) + (v.z + v.w);
+        }
         uint32_t incl = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -241,8 +265,9 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
             const uint32_t m = __ballot_sync(0xffffffffu, y != 0u);
             return static_cast<uint32_t>(G * 32 + (want_last ? 31 - __clz(m) : __ffs(m) - 1));
         };
-        uint32_t k_bq = 0u, k_bp = NONE, k_bn = NONE, k_base = 0u, k_tau = 0u;   // lane q: percentile q
+        uint32_t k_bq = 0u, k_base = 0u, k_tau = 0u;    // lane q: percentile q
         uint32_t marks = 0u;                            // bit j: bucket 32 * lane + j is marked
+#pragma unroll 1
         for (int q = 0; q < p.Q; ++q) {
             const uint32_t tau = __shfl_sync(0xffffffffu, tau_l, q);
             const int G = __ffs(__ballot_sync(0xffffffffu, incl - mine < tau && tau <= incl)) - 1;
@@ -267,37 +292,35 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
             else if (lower) bp = edge_of_group(31 - __clz(lower), true);
             if (above) bn = static_cast<uint32_t>(G * 32 + ln + __ffs(above));
             else if (upper) bn = edge_of_group(G + __ffs(upper), false);
-            if (lane == q) { k_bq = bq; k_bp = bp; k_bn = bn; k_base = base; k_tau = tau; }
+            if (lane == q) { k_bq = bq; k_base = base; k_tau = tau; }
             if (static_cast<int>(bq >> 5) == lane) marks |= 1u << (bq & 31u);
             if (bp != NONE && static_cast<int>(bp >> 5) == lane) marks |= 1u << (bp & 31u);
             if (bn != NONE && static_cast<int>(bn >> 5) == lane) marks |= 1u << (bn & 31u);
         }
         // the histogram goes back to zero
-#pragma unroll 8
-        for (int j = 0; j < 32; ++j) st_shared_u32(hist_s + (lane * 32 + ((j + lane) & 31)) * 4, 0u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) st_shared_v4(hist_s + (lane * 32 + ((j + lane) & 7) * 4) * 4, make_uint4(0u, 0u, 0u, 0u));
         __syncwarp();
 
         // ---- pass 2: members of marked buckets -> hit list (padding slots have count 0: skipped)
-        uint32_t nh = 0u;                               // warp-uniform
-        each_octet([&](bool ok, const uint4& a, const uint4& b) {
-            const uint32_t m[7] = {a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        each_octet(true, [&](bool ok, const uint32_t (&o)[8]) {
 #pragma unroll
-            for (int e = 0; e < 7; ++e) {
-                const uint32_t rank = m[e] & 0xffffffu, bk = rank >> shift;
+            for (int e = 1; e < 8; ++e) {
+                const uint32_t rank = o[e] & 0xffffffu, bk = bucket_of(rank);
                 const uint32_t bit = (__shfl_sync(0xffffffffu, marks, bk >> 5) >> (bk & 31u)) & 1u;
-                const bool hit = ok && bit != 0u && (m[e] >> 24) != 0u;
-                const uint32_t votes = __ballot_sync(0xffffffffu, hit);
-                if (votes) {
-                    const uint32_t at = nh + __popc(votes & lt_lane);
-                    if (hit && at < static_cast<uint32_t>(kSelect4Hits)) {
+                if (ok && bit != 0u && (o[e] >> 24) != 0u) {
+                    const uint32_t at = atomicAdd(n_hits, 1u);
+                    if (at < static_cast<uint32_t>(kSelect4Hits)) {
                         hit_r[at] = rank;
-                        hit_w[at] = (m[e] >> 24) * a.x;
+                        hit_w[at] = (o[e] >> 24) * o[0];
                     }
-                    nh += __popc(votes);
                 }
             }
         });
         __syncwarp();
+        const uint32_t nh = *n_hits;
+        __syncwarp();
+        if (lane == 0) *n_hits = 0u;
 
         // per percentile (lane q): ranks of the crossing entry, its neighbours, and the weights utils.py:72 needs
         uint32_t r_e = 0u, r_s = NONE, r_p = NONE, Ce = 0u, We = 0u, Ws = 0u, Wp = 0u;
@@ -331,11 +354,11 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
             }
             __syncwarp();
             if (lane < p.Q) {                           // scalar work of percentile `lane` on the sorted list
-                const uint32_t lo_rank = k_bq << shift;
-                int s = 0;                              // first slot with rank >= lo_rank
+                const uint32_t lo_rank = bucket_lo(k_bq);
+                int a = 0;                              // first slot with rank >= lo_rank
                 for (int step = kSelect4Hits / 2; step > 0; step >>= 1)
-                    if (s + step <= static_cast<int>(nh) && hit_r[s + step - 1] < lo_rank) s += step;
-                const uint32_t cstart = s ? hit_w[s - 1] : 0u;
+                    if (a + step <= static_cast<int>(nh) && hit_r[a + step - 1] < lo_rank) a += step;
+                const uint32_t cstart = a ? hit_w[a - 1] : 0u;
                 const uint32_t need = k_tau - k_base + cstart;             // first slot whose running sum reaches it
                 int i = 0;
                 for (int step = kSelect4Hits / 2; step > 0; step >>= 1)
@@ -361,22 +384,30 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
                 }
             }
             __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) st_shared_v4(hist_s + (lane * 16 + ((j + lane) & 3) * 4) * 4, make_uint4(0u, 0u, 0u, 0u));   // hit list -> zero
+            __syncwarp();
         } else {
             // ---- too many hits for the list: narrow every percentile exactly, the whole warp on one at a time
+#pragma unroll
+            for (int j = 0; j < 4; ++j) st_shared_v4(hist_s + (lane * 16 + ((j + lane) & 3) * 4) * 4, make_uint4(0u, 0u, 0u, 0u));
+            __syncwarp();
+#pragma unroll 1
             for (int q = 0; q < p.Q; ++q) {
                 const uint32_t tau = __shfl_sync(0xffffffffu, k_tau, q);
-                uint32_t lo = __shfl_sync(0xffffffffu, k_bq, q) << shift;   // ranks [lo, lo + width) hold the crossing
-                uint32_t before = __shfl_sync(0xffffffffu, k_base, q);      // weight of the ranks below lo
-                uint32_t wbits = shift;                                     // width = 2^wbits
+                const uint32_t bq = __shfl_sync(0xffffffffu, k_bq, q);
+                uint32_t rlo = bucket_lo(bq);                               // ranks [rlo, rlo + 2^wbits) hold the crossing
+                uint32_t before = __shfl_sync(0xffffffffu, k_base, q);      // weight of the ranks below rlo
+                uint32_t wbits = static_cast<uint32_t>(32 - __clz(bucket_hi(bq) - rlo - 1u));
+#pragma unroll 1
                 while (wbits > 0u) {
                     const uint32_t sbits = wbits > static_cast<uint32_t>(kSelect4LogNB) ? static_cast<uint32_t>(kSelect4LogNB) : wbits;
-                    const uint32_t sshift = wbits - sbits;                  // sub-bucket = (rank - lo) >> sshift, 2^sbits of them
-                    each_octet([&](bool ok, const uint4& a, const uint4& b) {
-                        const uint32_t m[7] = {a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                    const uint32_t sshift = wbits - sbits;                  // sub-bucket = (rank - rlo) >> sshift, 2^sbits of them
+                    each_octet(false, [&](bool ok, const uint32_t (&o)[8]) {
 #pragma unroll
-                        for (int e = 0; e < 7; ++e) {
-                            const uint32_t d = (m[e] & 0xffffffu) - lo;
-                            if (ok && (d >> wbits) == 0u) red_add_shared(hist_s + ((d >> sshift) << 2), (m[e] >> 24) * a.x);
+                        for (int e = 1; e < 8; ++e) {
+                            const uint32_t d = (o[e] & 0xffffffu) - rlo;
+                            if (ok && (d >> wbits) == 0u) red_add_shared(hist_s + ((d >> sshift) << 2), (o[e] >> 24) * o[0]);
                         }
                     });
                     __syncwarp();
@@ -402,30 +433,28 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
                         run += __shfl_sync(0xffffffffu, in, 31);
                     }
                     __syncwarp();
-                    lo += k_sub << sshift;
+                    rlo += k_sub << sshift;
                     wbits = sshift;
                 }
-                // lo is the crossing rank: its neighbours, then the merged weights of all three
-                uint32_t pr = 0u, sr = NONE, we = 0u;   // pr: rank + 1 of the largest rank below lo (0: none)
-                each_octet([&](bool ok, const uint4& a, const uint4& b) {
-                    const uint32_t m[7] = {a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                // rlo is the crossing rank: its neighbours, then the merged weights of all three
+                uint32_t pr = 0u, sr = NONE, we = 0u;   // pr: rank + 1 of the largest rank below rlo (0: none)
+                each_octet(false, [&](bool ok, const uint32_t (&o)[8]) {
 #pragma unroll
-                    for (int e = 0; e < 7; ++e) {
-                        const uint32_t rank = m[e] & 0xffffffu, c = ok ? (m[e] >> 24) : 0u;
-                        if (c != 0u && rank < lo) pr = max(pr, rank + 1u);
-                        if (c != 0u && rank > lo) sr = min(sr, rank);
-                        if (rank == lo) we += c * a.x;
+                    for (int e = 1; e < 8; ++e) {
+                        const uint32_t rank = o[e] & 0xffffffu, c = ok ? (o[e] >> 24) : 0u;
+                        if (c != 0u && rank < rlo) pr = max(pr, rank + 1u);
+                        if (c != 0u && rank > rlo) sr = min(sr, rank);
+                        if (rank == rlo) we += c * o[0];
                     }
                 });
                 pr = __reduce_max_sync(0xffffffffu, pr);
                 sr = __reduce_min_sync(0xffffffffu, sr);
                 we = __reduce_add_sync(0xffffffffu, we);
                 uint32_t wp = 0u, ws = 0u;
-                each_octet([&](bool ok, const uint4& a, const uint4& b) {
-                    const uint32_t m[7] = {a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                each_octet(false, [&](bool ok, const uint32_t (&o)[8]) {
 #pragma unroll
-                    for (int e = 0; e < 7; ++e) {
-                        const uint32_t rank = m[e] & 0xffffffu, wgt = ok ? (m[e] >> 24) * a.x : 0u;
+                    for (int e = 1; e < 8; ++e) {
+                        const uint32_t rank = o[e] & 0xffffffu, wgt = ok ? (o[e] >> 24) * o[0] : 0u;
                         if (pr != 0u && rank == pr - 1u) wp += wgt;
                         if (rank == sr) ws += wgt;
                     }
@@ -433,7 +462,7 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
                 wp = __reduce_add_sync(0xffffffffu, wp);
                 ws = __reduce_add_sync(0xffffffffu, ws);
                 if (lane == q) {
-                    r_e = lo; r_p = pr ? pr - 1u : NONE; r_s = sr;
+                    r_e = rlo; r_p = pr ? pr - 1u : NONE; r_s = sr;
                     We = we; Ce = before + we; Wp = wp; Ws = ws;
                 }
             }
