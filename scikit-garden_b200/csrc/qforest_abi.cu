@@ -108,7 +108,8 @@ struct qf_forest {
     int cta_capacity = 0;         // cap on the members per row of the first bucket stage (0 = its capacity)
     int select_bits = qf::kSelectL2Bits;   // log2 refinement slots of the selection kernel (tests lower it)
     int select4_hits = qf::kSelect4Hits;   // hit-list entries a row may use before select4 narrows instead (tests shrink it)
-    int select4_ctas = 4;                  // CTAs per SM select4 is compiled and launched for (3 or 4)
+    int select4_ctas = 4;                  // CTAs (of 8 rows) per SM select4 is launched with: 4 = the 64-register build, 1..3 = the 80-register one
+    int select4_hints = 0;                 // 1: L2 eviction hints on select4's octet loads (keep after pass 1, drop after pass 2)
     int select4_extras = 0;                // entries of select4's extra-octet list (0 = auto; tests shrink it)
     int select3_capw = 0;                  // octets per warp segment of the select3 stage (0 = auto; tests shrink it)
     int select3_variant = 1;               // 0: 3 select warps, 2 stages, 2 CTAs per SM; 1: 1 select warp, 1 stage, 3 CTAs per SM
@@ -667,7 +668,7 @@ bool select4_finish_geometry(const qf_forest* f, Select4Geometry& g) {
 int launch_select4_kernel(const qf_forest* f, const Select4Geometry& g, const qf::Select4Params& sp,
                           const qf::QuantileList& ql, cudaStream_t st) {
     const int64_t want = (sp.n + qf::kSelect4Warps - 1) / qf::kSelect4Warps;
-    const int wanted = f->select4_ctas == 3 ? 3 : qf::kSelect4CtasPerSm;
+    const int wanted = std::min(std::max(f->select4_ctas, 1), qf::kSelect4CtasPerSm);
     const int per_sm = std::max<int>(1, std::min<int>(wanted, static_cast<int>((220 * 1024) / std::max<size_t>(g.smem, 1))));
     const unsigned grid = static_cast<unsigned>(std::min<int64_t>(want, int64_t(f->sm_count) * per_sm));
     auto run = [&](auto kernel) -> int {
@@ -676,7 +677,9 @@ int launch_select4_kernel(const qf_forest* f, const Select4Geometry& g, const qf
         kernel<<<grid, qf::kSelect4Threads, g.smem, st>>>(sp, ql);
         return QF_OK;
     };
-    return wanted == 3 ? run(qf::quantile_select4_kernel<3>) : run(qf::quantile_select4_kernel<4>);
+    if (f->select4_hints)
+        return wanted == 4 ? run(qf::quantile_select4_kernel<4, true>) : run(qf::quantile_select4_kernel<3, true>);
+    return wanted == 4 ? run(qf::quantile_select4_kernel<4, false>) : run(qf::quantile_select4_kernel<3, false>);
 }
 
 int launch_select3_kernel(const qf_forest* f, const Select3Geometry& g, const qf::Select3Params& sp,
@@ -1196,8 +1199,11 @@ int qf_forest_set_option(qf_forest* f, const char* key, int64_t value) {
         if (value < 0 || value > qf::kSelect4Hits) return qf::fail(QF_ERR_INVALID, "select4_hits must be in [0, 256]");
         f->select4_hits = static_cast<int>(value);
     } else if (k == "select4_ctas") {
-        if (value != 3 && value != 4) return qf::fail(QF_ERR_INVALID, "select4_ctas must be 3 or 4");
+        if (value < 1 || value > 4) return qf::fail(QF_ERR_INVALID, "select4_ctas must be in [1, 4]");
         f->select4_ctas = static_cast<int>(value);
+    } else if (k == "select4_hints") {
+        if (value != 0 && value != 1) return qf::fail(QF_ERR_INVALID, "select4_hints must be 0 or 1");
+        f->select4_hints = static_cast<int>(value);
     } else if (k == "select4_extras") {
         if (value < 0 || value > 4096) return qf::fail(QF_ERR_INVALID, "select4_extras must be in [0, 4096]");
         f->select4_extras = static_cast<int>(value);

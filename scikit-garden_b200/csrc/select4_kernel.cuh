@@ -73,13 +73,29 @@ __host__ __device__ inline size_t select4_warp_smem(int extras_cap) {
     return static_cast<size_t>(kSelect4NB) * 4 + static_cast<size_t>(extras_cap) * 4 + 32;
 }
 
+// One octet = one 256-bit load.  HINT 1 / 2: bypass L1 and tell the L2 to keep the line (first touch of a row's
+// octets) / to drop it first (last touch) -- the rows in flight hold ~100 MB of octets between their two passes.
+template <int HINT>
 __device__ __forceinline__ void ld_octet(const uint4* __restrict__ lists, uint32_t octet, uint32_t (&o)[8]) {
     const uint4* src = lists + 2 * static_cast<size_t>(octet);
-    asm("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-        : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7])
-        : "l"(src));
+    if (HINT == 1)
+        asm("ld.global.nc.L1::no_allocate.L2::evict_last.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+            : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7])
+            : "l"(src));
+    else if (HINT == 2)
+        asm("ld.global.nc.L1::no_allocate.L2::evict_first.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+            : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7])
+            : "l"(src));
+    else
+        asm("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+            : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7])
+            : "l"(src));
 }
-template <int CTAS_PER_SM>                               // 4: 64 registers (a few spills), 3: 80 registers
+
+template <int H>
+struct Select4Hint { static constexpr int value = H; };
+
+template <int CTAS_PER_SM, bool HINTS>                   // 4: 64 registers (a few spills), 3: 80 registers
 __global__ void __launch_bounds__(kSelect4Threads, CTAS_PER_SM)
 quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileList ql) {
     constexpr int NB = kSelect4NB;
@@ -147,7 +163,8 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
 
         // f(ok, o) on the first octets of batch b (leaves 128 b + 32 k + lane), all 32 lanes in step;
         // ok = false: a lane without an octet in this step (it sees octet 0 of the lists, to be ignored)
-        auto batch = [&](int b, auto&& f) {
+        auto batch = [&](auto hint, int b, auto&& f) {
+            constexpr int H = HINTS ? decltype(hint)::value : 0;
             uint32_t o[4][8];
             bool ok[4];
 #pragma unroll
@@ -155,16 +172,17 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
                 uint32_t first, noct;
                 leaf(b * 128 + k * 32 + lane, first, noct);
                 ok[k] = noct != 0u;
-                ld_octet(p.lists, ok[k] ? first : 0u, o[k]);
+                ld_octet<H>(p.lists, ok[k] ? first : 0u, o[k]);
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) f(ok[k], o[k]);
         };
         // f on every octet of the row; `reverse` walks them in the opposite order
-        auto each_octet = [&](bool reverse, auto&& f) {
+        auto each_octet = [&](auto hint, bool reverse, auto&& f) {
+            constexpr int H = HINTS ? decltype(hint)::value : 0;
             if (!reverse) {
 #pragma unroll 1
-                for (int b = 0; b < n_batches; ++b) batch(b, f);
+                for (int b = 0; b < n_batches; ++b) batch(hint, b, f);
             }
             if (flat) {                                 // sweep B: the other octets, flat over the lanes
                 const uint32_t steps = (n_extra + 31u) >> 5;
@@ -173,7 +191,7 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
                     const uint32_t j = ((reverse ? steps - 1u - si : si) << 5) + lane;
                     const bool ok = j < n_extra;
                     uint32_t o[8];
-                    ld_octet(p.lists, ok ? extras[j] : 0u, o);
+                    ld_octet<H>(p.lists, ok ? extras[j] : 0u, o);
                     f(ok, o);
                 }
             } else {                                    // list too small for this row: leaf by leaf, lanes in step
@@ -185,14 +203,14 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
                     for (uint32_t k = 1; k < most; ++k) {
                         const bool ok = k < noct;
                         uint32_t o[8];
-                        ld_octet(p.lists, ok ? first + k : 0u, o);
+                        ld_octet<H>(p.lists, ok ? first + k : 0u, o);
                         f(ok, o);
                     }
                 }
             }
             if (reverse) {
 #pragma unroll 1
-                for (int b = n_batches - 1; b >= 0; --b) batch(b, f);
+                for (int b = n_batches - 1; b >= 0; --b) batch(hint, b, f);
             }
         };
 
@@ -200,7 +218,7 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
         uint32_t lo = NONE, wsh = 0u;                 // window: first rank, log2(ranks per bucket)
         {
             uint32_t hi = 0u;
-            batch(0, [&](bool ok, const uint32_t (&o)[8]) {
+            batch(Select4Hint<1>{}, 0, [&](bool ok, const uint32_t (&o)[8]) {
 #pragma unroll
                 for (int e = 1; e < 8; ++e) {
                     const bool real = ok && (o[e] >> 24) != 0u;
@@ -225,7 +243,7 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
         };
 
         // ---- pass 1: bucket weights
-        each_octet(false, [&](bool ok, const uint32_t (&o)[8]) {
+        each_octet(Select4Hint<1>{}, false, [&](bool ok, const uint32_t (&o)[8]) {
             const uint32_t U = ok ? o[0] : 0u;
 #pragma unroll
             for (int e = 1; e < 8; ++e)
@@ -303,7 +321,7 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
         __syncwarp();
 
         // ---- pass 2: members of marked buckets -> hit list (padding slots have count 0: skipped)
-        each_octet(true, [&](bool ok, const uint32_t (&o)[8]) {
+        each_octet(Select4Hint<2>{}, true, [&](bool ok, const uint32_t (&o)[8]) {
 #pragma unroll
             for (int e = 1; e < 8; ++e) {
                 const uint32_t rank = o[e] & 0xffffffu, bk = bucket_of(rank);
@@ -403,7 +421,7 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
                 while (wbits > 0u) {
                     const uint32_t sbits = wbits > static_cast<uint32_t>(kSelect4LogNB) ? static_cast<uint32_t>(kSelect4LogNB) : wbits;
                     const uint32_t sshift = wbits - sbits;                  // sub-bucket = (rank - rlo) >> sshift, 2^sbits of them
-                    each_octet(false, [&](bool ok, const uint32_t (&o)[8]) {
+                    each_octet(Select4Hint<0>{}, false, [&](bool ok, const uint32_t (&o)[8]) {
 #pragma unroll
                         for (int e = 1; e < 8; ++e) {
                             const uint32_t d = (o[e] & 0xffffffu) - rlo;
@@ -438,7 +456,7 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
                 }
                 // rlo is the crossing rank: its neighbours, then the merged weights of all three
                 uint32_t pr = 0u, sr = NONE, we = 0u;   // pr: rank + 1 of the largest rank below rlo (0: none)
-                each_octet(false, [&](bool ok, const uint32_t (&o)[8]) {
+                each_octet(Select4Hint<0>{}, false, [&](bool ok, const uint32_t (&o)[8]) {
 #pragma unroll
                     for (int e = 1; e < 8; ++e) {
                         const uint32_t rank = o[e] & 0xffffffu, c = ok ? (o[e] >> 24) : 0u;
@@ -451,7 +469,7 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
                 sr = __reduce_min_sync(0xffffffffu, sr);
                 we = __reduce_add_sync(0xffffffffu, we);
                 uint32_t wp = 0u, ws = 0u;
-                each_octet(false, [&](bool ok, const uint32_t (&o)[8]) {
+                each_octet(Select4Hint<0>{}, false, [&](bool ok, const uint32_t (&o)[8]) {
 #pragma unroll
                     for (int e = 1; e < 8; ++e) {
                         const uint32_t rank = o[e] & 0xffffffu, wgt = ok ? (o[e] >> 24) * o[0] : 0u;

