@@ -108,9 +108,9 @@ struct qf_forest {
     int cta_capacity = 0;         // cap on the members per row of the first bucket stage (0 = its capacity)
     int select_bits = qf::kSelectL2Bits;   // log2 refinement slots of the selection kernel (tests lower it)
     int select4_hits = qf::kSelect4Hits;   // hit-list entries a row may use before select4 narrows instead (tests shrink it)
-    int select4_ctas = 4;                  // CTAs (of 8 rows) per SM select4 is launched with: 4 = the 64-register build, 1..3 = the 80-register one
-    int select4_hints = 0;                 // 1: L2 eviction hints on select4's octet loads (keep after pass 1, drop after pass 2)
-    int select4_extras = 0;                // entries of select4's extra-octet list (0 = auto; tests shrink it)
+    int select4_ctas = 4;                  // CTAs (of 8 rows) per SM select4 is launched with, at most
+    int select4_unroll = 2;                // octets a lane keeps in flight per step of a pass (2 or 4)
+    int select4_list = 0;                  // entries of select4's per-row octet list (0 = auto; tests shrink it)
     int select3_capw = 0;                  // octets per warp segment of the select3 stage (0 = auto; tests shrink it)
     int select3_variant = 1;               // 0: 3 select warps, 2 stages, 2 CTAs per SM; 1: 1 select warp, 1 stage, 3 CTAs per SM
     int select_impl = 0;                   // 0: auto (select2 when the training set allows, else the multi-level kernel);
@@ -633,7 +633,7 @@ bool select3_finish_geometry(const qf_forest* f, Select3Geometry& g) {
 // select4 (warp per row): geometry or ok = false
 struct Select4Geometry {
     bool ok = false;
-    int extras_cap = 0;
+    int list_cap = 0;
     float fx_scale = 0.0f;
     size_t smem = 0;
 };
@@ -654,12 +654,12 @@ Select4Geometry select4_geometry(const qf_forest* f, int nq) {
 
 bool select4_finish_geometry(const qf_forest* f, Select4Geometry& g) {
     if (f->compact_state != 1 || static_cast<int>(f->tree_octets.size()) != f->T) return false;
-    double extras = 0.0;                                // octets beyond the first a row expects
-    for (int t = 0; t < f->T; ++t) extras += std::max(0.0, f->tree_octets[t] - 1.0);
-    int cap = static_cast<int>(extras * 1.3) + 64;
-    if (f->select4_extras > 0) cap = f->select4_extras;
+    double octets = 0.0;                                // octets a row expects
+    for (int t = 0; t < f->T; ++t) octets += f->tree_octets[t];
+    int cap = static_cast<int>(octets * 1.25) + 96;     // rows beyond it walk their leaves one by one (slow, correct)
+    if (f->select4_list > 0) cap = f->select4_list;
     cap = std::min((cap + 31) & ~31, 4096);
-    g.extras_cap = cap;
+    g.list_cap = cap;
     g.smem = qf::select4_warp_smem(cap) * qf::kSelect4Warps;
     g.ok = g.smem <= 200 * 1024;
     return g.ok;
@@ -669,7 +669,7 @@ int launch_select4_kernel(const qf_forest* f, const Select4Geometry& g, const qf
                           const qf::QuantileList& ql, cudaStream_t st) {
     const int64_t want = (sp.n + qf::kSelect4Warps - 1) / qf::kSelect4Warps;
     const int wanted = std::min(std::max(f->select4_ctas, 1), qf::kSelect4CtasPerSm);
-    const int per_sm = std::max<int>(1, std::min<int>(wanted, static_cast<int>((220 * 1024) / std::max<size_t>(g.smem, 1))));
+    const int per_sm = std::max<int>(1, std::min<int>(wanted, static_cast<int>((220 * 1024) / std::max<size_t>(g.smem + 1024, 1))));
     const unsigned grid = static_cast<unsigned>(std::min<int64_t>(want, int64_t(f->sm_count) * per_sm));
     auto run = [&](auto kernel) -> int {
         int rc = set_smem(kernel, g.smem);
@@ -677,9 +677,7 @@ int launch_select4_kernel(const qf_forest* f, const Select4Geometry& g, const qf
         kernel<<<grid, qf::kSelect4Threads, g.smem, st>>>(sp, ql);
         return QF_OK;
     };
-    if (f->select4_hints)
-        return wanted == 4 ? run(qf::quantile_select4_kernel<4, true>) : run(qf::quantile_select4_kernel<3, true>);
-    return wanted == 4 ? run(qf::quantile_select4_kernel<4, false>) : run(qf::quantile_select4_kernel<3, false>);
+    return f->select4_unroll == 4 ? run(qf::quantile_select4_kernel<4>) : run(qf::quantile_select4_kernel<2>);
 }
 
 int launch_select3_kernel(const qf_forest* f, const Select3Geometry& g, const qf::Select3Params& sp,
@@ -786,7 +784,7 @@ int quantiles_on_stream(qf_forest* f, CallStats& cs, const float* X, int64_t n, 
             sp.Q = nq;
             sp.fx_scale = g4.fx_scale;
             sp.n_train = static_cast<uint32_t>(f->N);
-            sp.extras_cap = g4.extras_cap;
+            sp.list_cap = g4.list_cap;
             sp.hits_cap = std::min(f->select4_hits, qf::kSelect4Hits);
             {
                 SpanTimer span(f, cs, SPAN_QUANTILE, st);
@@ -1201,12 +1199,12 @@ int qf_forest_set_option(qf_forest* f, const char* key, int64_t value) {
     } else if (k == "select4_ctas") {
         if (value < 1 || value > 4) return qf::fail(QF_ERR_INVALID, "select4_ctas must be in [1, 4]");
         f->select4_ctas = static_cast<int>(value);
-    } else if (k == "select4_hints") {
-        if (value != 0 && value != 1) return qf::fail(QF_ERR_INVALID, "select4_hints must be 0 or 1");
-        f->select4_hints = static_cast<int>(value);
-    } else if (k == "select4_extras") {
-        if (value < 0 || value > 4096) return qf::fail(QF_ERR_INVALID, "select4_extras must be in [0, 4096]");
-        f->select4_extras = static_cast<int>(value);
+    } else if (k == "select4_unroll") {
+        if (value != 2 && value != 4) return qf::fail(QF_ERR_INVALID, "select4_unroll must be 2 or 4");
+        f->select4_unroll = static_cast<int>(value);
+    } else if (k == "select4_list") {
+        if (value < 0 || value > 4096) return qf::fail(QF_ERR_INVALID, "select4_list must be in [0, 4096]");
+        f->select4_list = static_cast<int>(value);
     } else if (k == "select3_variant") {
         if (value != 0 && value != 1) return qf::fail(QF_ERR_INVALID, "select3_variant must be 0 or 1");
         f->select3_variant = static_cast<int>(value);

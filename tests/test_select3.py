@@ -292,7 +292,7 @@ def test_select4_equals_select3_bit_for_bit(name, hits, extras):
     g = _golden.load(name)
     flat = _golden.flat_from_golden(g)
     d3 = _dev(flat, warp_elems=0, select_impl=3)
-    d4 = _dev(flat, warp_elems=0, select_impl=4, select4_hits=hits, select4_extras=extras)
+    d4 = _dev(flat, warp_elems=0, select_impl=4, select4_hits=hits, select4_list=extras)
     X = _cuda(g.X_test)
     scale = np.abs(g.y_train).max()
     for lo in range(0, len(g.q), 3):
@@ -334,7 +334,7 @@ def test_select4_tree_counts_and_row_counts(T, msl, N, rows):
             assert_allclose(got, ref, rtol=2e-5, atol=2e-5 * scale)
     for ctas, hints in ((4, 0), (3, 1), (1, 1)):
         dev.set_option("select4_ctas", ctas)
-        dev.set_option("select4_hints", hints)
+        dev.set_option("select4_unroll", 4 if hints else 2)
         dev.set_option("select4_hits", 256)
         same(est.predict(Xt[:rows], quantile=qs), want)
         dev.set_option("select4_hits", 16)
