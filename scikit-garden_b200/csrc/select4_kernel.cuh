@@ -22,8 +22,8 @@
 //   pass 1   one shared-memory RED per member into the histogram.
 //   scan     lane totals of 32 consecutive buckets (rotated 128-bit reads), one warp scan; per
 //            percentile the group that holds the crossing is scanned across the lanes: crossing bucket
-//            bq, nearest non-empty neighbours bp / bn from ballots.  The marked buckets live in a
-//            1024-bit map, 32 bits per lane, tested with one SHFL per member.
+//            bq, nearest non-empty neighbours bp / bn from ballots.  The buckets between bp and bn
+//            are empty, so "member of a marked bucket" is one rank interval per percentile.
 //   pass 2   members of marked buckets (a few dozen of a row's 3300 at config 3) are appended to the
 //            hit list (shared-memory counter; their order does not matter, see select).
 //   select   the hits are sorted by rank in registers (bitonic network, 8 keys per lane), weights
@@ -73,12 +73,16 @@ __host__ __device__ inline size_t select4_warp_smem(int list_cap) {
     return static_cast<size_t>(kSelect4NB) * 4 + static_cast<size_t>(list_cap) * 4 + 32;
 }
 
-// One octet = one 256-bit load.
-__device__ __forceinline__ void ld_octet(const uint4* __restrict__ lists, uint32_t octet, uint32_t (&o)[8]) {
+// One octet = one 256-bit load, issued only by the lanes that have an octet (`ok`); the others get zeros, which
+// read as seven padding slots (count 0) under a zero unit weight.
+__device__ __forceinline__ void ld_octet(const uint4* __restrict__ lists, uint32_t octet, bool ok, uint32_t (&o)[8]) {
     const uint4* src = lists + 2 * static_cast<size_t>(octet);
-    asm("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-        : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7])
-        : "l"(src));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = 0u;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %9, 0;\n\t"
+        "@p ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t}"
+        : "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7])
+        : "l"(src), "r"(static_cast<uint32_t>(ok)));
 }
 
 // The hits of a row (hit_r[v] = rank, hit_w[v] = weight, v < nh <= 32 E) sorted by rank, in place: hit_r
@@ -153,15 +157,27 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
                 ++first;
             }
         };
-        // ---- the row's octets -> flat list: every pass is then one balanced loop over it
-        uint32_t n_oct;
-        {
-            uint32_t mine = 0u;
+        // ---- the row's octets -> flat list: every pass is then one balanced loop over it.  Eight leaves per
+        // lane at a time (their words are loaded together), one warp scan per group of 256 leaves.
+        uint32_t n_oct = 0u;
 #pragma unroll 1
-            for (int i = 0; i < n_slots; ++i) {
-                uint32_t first, noct;
-                leaf(i * 32 + lane, first, noct);
-                mine += noct;
+        for (int i0 = 0; i0 < n_slots; i0 += 8) {
+            uint32_t first[8], noct[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int t = (i0 + k) * 32 + lane;
+                const uint32_t word = t < p.T ? __ldg(words + t) : kCompactEmpty;
+                first[k] = word & kCompactOffMask;
+                noct[k] = word == kCompactEmpty ? 0u : (word >> 28) + 1u;
+            }
+            uint32_t mine = 0u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (noct[k] > static_cast<uint32_t>(kCompactMaxOctets)) {       // long list: info octet first
+                    noct[k] = __ldg(p.lists + 2 * static_cast<size_t>(first[k])).x;
+                    ++first[k];
+                }
+                mine += noct[k];
             }
             uint32_t incl = mine;
 #pragma unroll
@@ -169,18 +185,16 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
                 const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
                 if (lane >= d) incl += u;
             }
-            n_oct = __shfl_sync(0xffffffffu, incl, 31);
-            if (n_oct <= static_cast<uint32_t>(p.list_cap)) {
-                uint32_t at = incl - mine;
-#pragma unroll 1
-                for (int i = 0; i < n_slots; ++i) {
-                    uint32_t first, noct;
-                    leaf(i * 32 + lane, first, noct);
-                    for (uint32_t k = 0; k < noct; ++k) olist[at++] = first + k;
-                }
+            const uint32_t group = __shfl_sync(0xffffffffu, incl, 31);
+            if (n_oct + group <= static_cast<uint32_t>(p.list_cap)) {           // (once false it stays false)
+                uint32_t at = n_oct + incl - mine;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    for (uint32_t j = 0; j < noct[k]; ++j) olist[at++] = first[k] + j;
             }
-            __syncwarp();
+            n_oct += group;
         }
+        __syncwarp();
         const bool flat = n_oct <= static_cast<uint32_t>(p.list_cap);
 
         // f(ok, o) on octets [j0, j0 + 32 UNR) of the list, all 32 lanes in step (f may shuffle); ok = false:
@@ -192,7 +206,7 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
             for (int k = 0; k < UNR; ++k) {
                 const uint32_t j = j0 + k * 32 + lane;
                 ok[k] = j < n_oct;
-                ld_octet(p.lists, ok[k] ? olist[j] : 0u, o[k]);
+                ld_octet(p.lists, ok[k] ? olist[j] : 0u, ok[k], o[k]);
             }
 #pragma unroll
             for (int k = 0; k < UNR; ++k) f(ok[k], o[k]);
@@ -213,7 +227,7 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
                     for (uint32_t k = 0; k < most; ++k) {
                         const bool ok = k < noct;
                         uint32_t o[8];
-                        ld_octet(p.lists, ok ? first + k : 0u, o);
+                        ld_octet(p.lists, ok ? first + k : 0u, ok, o);
                         f(ok, o);
                     }
                 }
@@ -227,19 +241,19 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
             auto sample = [&](bool ok, const uint32_t (&o)[8]) {
 #pragma unroll
                 for (int e = 1; e < 8; ++e) {
-                    const bool real = ok && (o[e] >> 24) != 0u;
+                    const bool real = ok && o[0] != 0u && (o[e] >> 24) != 0u;    // (a real octet has a non-zero unit weight)
                     lo = min(lo, real ? (o[e] & 0xffffffu) : NONE);
                     hi = max(hi, real ? (o[e] & 0xffffffu) : 0u);
                 }
             };
             if (flat) {
                 step(0u, sample);
-                if (UNR < 4) step(32u * UNR, sample);
+                if (UNR < 4 && n_oct > 32u * UNR) step(32u * UNR, sample);
             } else {                                    // the first octet of the lane's first leaf
                 uint32_t first, noct;
                 leaf(lane, first, noct);
                 uint32_t o[8];
-                ld_octet(p.lists, noct ? first : 0u, o);
+                ld_octet(p.lists, noct ? first : 0u, noct != 0u, o);
                 sample(noct != 0u, o);
             }
             lo = __reduce_min_sync(0xffffffffu, lo);
@@ -300,7 +314,7 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
             return static_cast<uint32_t>(G * 32 + (want_last ? 31 - __clz(m) : __ffs(m) - 1));
         };
         uint32_t k_bq = 0u, k_base = 0u, k_tau = 0u;    // lane q: percentile q
-        uint32_t marks = 0u;                            // bit j: bucket 32 * lane + j is marked
+        uint32_t k_from = 0u, k_len = 0u;               // lane q: the ranks of bp, bq and bn -- one interval, the buckets between them are empty
 #pragma unroll 1
         for (int q = 0; q < p.Q; ++q) {
             const uint32_t tau = __shfl_sync(0xffffffffu, tau_l, q);
@@ -326,11 +340,15 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
             else if (lower) bp = edge_of_group(31 - __clz(lower), true);
             if (above) bn = static_cast<uint32_t>(G * 32 + ln + __ffs(above));
             else if (upper) bn = edge_of_group(G + __ffs(upper), false);
-            if (lane == q) { k_bq = bq; k_base = base; k_tau = tau; }
-            if (static_cast<int>(bq >> 5) == lane) marks |= 1u << (bq & 31u);
-            if (bp != NONE && static_cast<int>(bp >> 5) == lane) marks |= 1u << (bp & 31u);
-            if (bn != NONE && static_cast<int>(bn >> 5) == lane) marks |= 1u << (bn & 31u);
+            if (lane == q) {
+                k_bq = bq; k_base = base; k_tau = tau;
+                k_from = bucket_lo(bp != NONE ? bp : bq);
+                k_len = bucket_hi(bn != NONE ? bn : bq) - k_from;
+            }
         }
+        const uint32_t from0 = __shfl_sync(0xffffffffu, k_from, 0), len0 = __shfl_sync(0xffffffffu, k_len, 0);
+        const uint32_t from1 = __shfl_sync(0xffffffffu, k_from, 1), len1 = __shfl_sync(0xffffffffu, k_len, 1);
+        const uint32_t from2 = __shfl_sync(0xffffffffu, k_from, 2), len2 = __shfl_sync(0xffffffffu, k_len, 2);   // len 0 beyond Q
         // the histogram goes back to zero
 #pragma unroll
         for (int j = 0; j < 8; ++j) st_shared_v4(hist_s + (lane * 32 + ((j + lane) & 7) * 4) * 4, make_uint4(0u, 0u, 0u, 0u));
@@ -340,9 +358,9 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
         each_octet(true, [&](bool ok, const uint32_t (&o)[8]) {
 #pragma unroll
             for (int e = 1; e < 8; ++e) {
-                const uint32_t rank = o[e] & 0xffffffu, bk = bucket_of(rank);
-                const uint32_t bit = (__shfl_sync(0xffffffffu, marks, bk >> 5) >> (bk & 31u)) & 1u;
-                if (ok && bit != 0u && (o[e] >> 24) != 0u) {
+                const uint32_t rank = o[e] & 0xffffffu;
+                const bool marked = (rank - from0 < len0) | (rank - from1 < len1) | (rank - from2 < len2);
+                if (marked && (o[e] >> 24) != 0u) {                // (lanes without an octet hold zeros: count 0)
                     const uint32_t at = atomicAdd(n_hits, 1u);
                     if (at < static_cast<uint32_t>(kSelect4Hits)) {
                         hit_r[at] = rank;
