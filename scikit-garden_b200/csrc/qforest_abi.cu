@@ -109,6 +109,7 @@ struct qf_forest {
     int select_bits = qf::kSelectL2Bits;   // log2 refinement slots of the selection kernel (tests lower it)
     int select4_hits = qf::kSelect4Hits;   // hit-list entries a row may use before select4 narrows instead (tests shrink it)
     int select4_ctas = 4;                  // CTAs (of 8 rows) per SM select4 is launched with, at most
+    int select4_hints = 0;                 // 1: L2 eviction hints on select4's octet loads (keep after pass 1, drop after pass 2)
     int select4_unroll = 2;                // octets a lane keeps in flight per step of a pass (2 or 4)
     int select4_list = 0;                  // entries of select4's per-row octet list (0 = auto; tests shrink it)
     int select3_capw = 0;                  // octets per warp segment of the select3 stage (0 = auto; tests shrink it)
@@ -677,7 +678,8 @@ int launch_select4_kernel(const qf_forest* f, const Select4Geometry& g, const qf
         kernel<<<grid, qf::kSelect4Threads, g.smem, st>>>(sp, ql);
         return QF_OK;
     };
-    return f->select4_unroll == 4 ? run(qf::quantile_select4_kernel<4>) : run(qf::quantile_select4_kernel<2>);
+    if (f->select4_unroll == 4) return run(qf::quantile_select4_kernel<4, false>);
+    return f->select4_hints ? run(qf::quantile_select4_kernel<2, true>) : run(qf::quantile_select4_kernel<2, false>);
 }
 
 int launch_select3_kernel(const qf_forest* f, const Select3Geometry& g, const qf::Select3Params& sp,
@@ -1199,6 +1201,9 @@ int qf_forest_set_option(qf_forest* f, const char* key, int64_t value) {
     } else if (k == "select4_ctas") {
         if (value < 1 || value > 4) return qf::fail(QF_ERR_INVALID, "select4_ctas must be in [1, 4]");
         f->select4_ctas = static_cast<int>(value);
+    } else if (k == "select4_hints") {
+        if (value != 0 && value != 1) return qf::fail(QF_ERR_INVALID, "select4_hints must be 0 or 1");
+        f->select4_hints = static_cast<int>(value);
     } else if (k == "select4_unroll") {
         if (value != 2 && value != 4) return qf::fail(QF_ERR_INVALID, "select4_unroll must be 2 or 4");
         f->select4_unroll = static_cast<int>(value);

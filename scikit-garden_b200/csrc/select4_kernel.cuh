@@ -74,16 +74,27 @@ __host__ __device__ inline size_t select4_warp_smem(int list_cap) {
 }
 
 // One octet = one 256-bit load, issued only by the lanes that have an octet (`ok`); the others get zeros, which
-// read as seven padding slots (count 0) under a zero unit weight.
+// read as seven padding slots (count 0) under a zero unit weight.  HINT 1 / 2: bypass L1 and tell the L2 to
+// keep the line (first touch of a row's octets) / to drop it first (their last touch): the rows in flight
+// hold 50-100 MB of octets between their two passes.
+#define QF_LD_OCTET(HINTSTR)                                                                                    \
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %9, 0;\n\t"                                                      \
+        "@p ld.global.nc" HINTSTR ".v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t}"                          \
+        : "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7])       \
+        : "l"(src), "r"(static_cast<uint32_t>(ok)))
+template <int HINT>
 __device__ __forceinline__ void ld_octet(const uint4* __restrict__ lists, uint32_t octet, bool ok, uint32_t (&o)[8]) {
     const uint4* src = lists + 2 * static_cast<size_t>(octet);
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = 0u;
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %9, 0;\n\t"
-        "@p ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t}"
-        : "+r"(o[0]), "+r"(o[1]), "+r"(o[2]), "+r"(o[3]), "+r"(o[4]), "+r"(o[5]), "+r"(o[6]), "+r"(o[7])
-        : "l"(src), "r"(static_cast<uint32_t>(ok)));
+    if (HINT == 1) QF_LD_OCTET(".L1::no_allocate.L2::evict_last");
+    else if (HINT == 2) QF_LD_OCTET(".L1::no_allocate.L2::evict_first");
+    else QF_LD_OCTET("");
 }
+#undef QF_LD_OCTET
+
+template <int H>
+struct Select4Hint { static constexpr int value = H; };
 
 // The hits of a row (hit_r[v] = rank, hit_w[v] = weight, v < nh <= 32 E) sorted by rank, in place: hit_r
 // becomes the sorted ranks (0xffffff in the unused slots), hit_w the running sums of the weights in that order.
@@ -122,7 +133,7 @@ __device__ __forceinline__ void select4_sort_hits(uint32_t* hit_r, uint32_t* hit
 // first versions of this kernel (17.8 k and 8.7 k SASS instructions, mostly straight-line) ran at one warp
 // instruction per SM per cycle whatever the occupancy -- 24-32 warps at different places of 50+ KB of hot
 // code live on instruction fetches from the L2 (L0 ~6 KB, L1.5 32 KB).
-template <int UNR>
+template <int UNR, bool HINTS>
 __global__ void __launch_bounds__(kSelect4Threads, kSelect4CtasPerSm)
 quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileList ql) {
     constexpr int NB = kSelect4NB;
@@ -199,24 +210,26 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
 
         // f(ok, o) on octets [j0, j0 + 32 UNR) of the list, all 32 lanes in step (f may shuffle); ok = false:
         // a lane without an octet in this step (it sees octet 0 of the lists, to be ignored)
-        auto step = [&](uint32_t j0, auto&& f) {
+        auto step = [&](auto hint, uint32_t j0, auto&& f) {
+            constexpr int H = HINTS ? decltype(hint)::value : 0;
             uint32_t o[UNR][8];
             bool ok[UNR];
 #pragma unroll
             for (int k = 0; k < UNR; ++k) {
                 const uint32_t j = j0 + k * 32 + lane;
                 ok[k] = j < n_oct;
-                ld_octet(p.lists, ok[k] ? olist[j] : 0u, ok[k], o[k]);
+                ld_octet<H>(p.lists, ok[k] ? olist[j] : 0u, ok[k], o[k]);
             }
 #pragma unroll
             for (int k = 0; k < UNR; ++k) f(ok[k], o[k]);
         };
         // f on every octet of the row; `reverse` walks them in the opposite order
-        auto each_octet = [&](bool reverse, auto&& f) {
+        auto each_octet = [&](auto hint, bool reverse, auto&& f) {
+            constexpr int H = HINTS ? decltype(hint)::value : 0;
             if (flat) {
                 const uint32_t steps = (n_oct + 32u * UNR - 1u) / (32u * UNR);
 #pragma unroll 1
-                for (uint32_t si = 0; si < steps; ++si) step((reverse ? steps - 1u - si : si) * (32u * UNR), f);
+                for (uint32_t si = 0; si < steps; ++si) step(hint, (reverse ? steps - 1u - si : si) * (32u * UNR), f);
             } else {                                    // list too small for this row: leaf by leaf, lanes in step
 #pragma unroll 1
                 for (int i = 0; i < n_slots; ++i) {
@@ -227,7 +240,7 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
                     for (uint32_t k = 0; k < most; ++k) {
                         const bool ok = k < noct;
                         uint32_t o[8];
-                        ld_octet(p.lists, ok ? first + k : 0u, ok, o);
+                        ld_octet<H>(p.lists, ok ? first + k : 0u, ok, o);
                         f(ok, o);
                     }
                 }
@@ -247,13 +260,13 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
                 }
             };
             if (flat) {
-                step(0u, sample);
-                if (UNR < 4 && n_oct > 32u * UNR) step(32u * UNR, sample);
+                step(Select4Hint<1>{}, 0u, sample);
+                if (UNR < 4 && n_oct > 32u * UNR) step(Select4Hint<1>{}, 32u * UNR, sample);
             } else {                                    // the first octet of the lane's first leaf
                 uint32_t first, noct;
                 leaf(lane, first, noct);
                 uint32_t o[8];
-                ld_octet(p.lists, noct ? first : 0u, noct != 0u, o);
+                ld_octet<0>(p.lists, noct ? first : 0u, noct != 0u, o);
                 sample(noct != 0u, o);
             }
             lo = __reduce_min_sync(0xffffffffu, lo);
@@ -273,7 +286,7 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
         };
 
         // ---- pass 1: bucket weights
-        each_octet(false, [&](bool ok, const uint32_t (&o)[8]) {
+        each_octet(Select4Hint<1>{}, false, [&](bool ok, const uint32_t (&o)[8]) {
             const uint32_t U = ok ? o[0] : 0u;
 #pragma unroll
             for (int e = 1; e < 8; ++e)
@@ -355,7 +368,7 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
         __syncwarp();
 
         // ---- pass 2: members of marked buckets -> hit list (padding slots have count 0: skipped)
-        each_octet(true, [&](bool ok, const uint32_t (&o)[8]) {
+        each_octet(Select4Hint<2>{}, true, [&](bool ok, const uint32_t (&o)[8]) {
 #pragma unroll
             for (int e = 1; e < 8; ++e) {
                 const uint32_t rank = o[e] & 0xffffffu;
@@ -435,7 +448,7 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
                 while (wbits > 0u) {
                     const uint32_t sbits = wbits > static_cast<uint32_t>(kSelect4LogNB) ? static_cast<uint32_t>(kSelect4LogNB) : wbits;
                     const uint32_t sshift = wbits - sbits;                  // sub-bucket = (rank - rlo) >> sshift, 2^sbits of them
-                    each_octet(false, [&](bool ok, const uint32_t (&o)[8]) {
+                    each_octet(Select4Hint<0>{}, false, [&](bool ok, const uint32_t (&o)[8]) {
 #pragma unroll
                         for (int e = 1; e < 8; ++e) {
                             const uint32_t d = (o[e] & 0xffffffu) - rlo;
@@ -470,7 +483,7 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
                 }
                 // rlo is the crossing rank: its neighbours, then the merged weights of all three
                 uint32_t pr = 0u, sr = NONE, we = 0u;   // pr: rank + 1 of the largest rank below rlo (0: none)
-                each_octet(false, [&](bool ok, const uint32_t (&o)[8]) {
+                each_octet(Select4Hint<0>{}, false, [&](bool ok, const uint32_t (&o)[8]) {
 #pragma unroll
                     for (int e = 1; e < 8; ++e) {
                         const uint32_t rank = o[e] & 0xffffffu, c = ok ? (o[e] >> 24) : 0u;
@@ -483,7 +496,7 @@ quantile_select4_kernel(const Select4Params p, const __grid_constant__ QuantileL
                 sr = __reduce_min_sync(0xffffffffu, sr);
                 we = __reduce_add_sync(0xffffffffu, we);
                 uint32_t wp = 0u, ws = 0u;
-                each_octet(false, [&](bool ok, const uint32_t (&o)[8]) {
+                each_octet(Select4Hint<0>{}, false, [&](bool ok, const uint32_t (&o)[8]) {
 #pragma unroll
                     for (int e = 1; e < 8; ++e) {
                         const uint32_t rank = o[e] & 0xffffffu, wgt = ok ? (o[e] >> 24) * o[0] : 0u;

@@ -334,7 +334,8 @@ def test_select4_tree_counts_and_row_counts(T, msl, N, rows):
             assert_allclose(got, ref, rtol=2e-5, atol=2e-5 * scale)
     for ctas, hints in ((4, 0), (3, 1), (1, 1)):
         dev.set_option("select4_ctas", ctas)
-        dev.set_option("select4_unroll", 4 if hints else 2)
+        dev.set_option("select4_unroll", 2 if hints else 4)
+        dev.set_option("select4_hints", hints)
         dev.set_option("select4_hits", 256)
         same(est.predict(Xt[:rows], quantile=qs), want)
         dev.set_option("select4_hits", 16)
