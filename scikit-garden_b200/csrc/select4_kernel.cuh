@@ -8,16 +8,16 @@
 // 60-100 KB of it per row in flight (2-4 rows and ~25 warps per SM) and 2-3 k shared-memory wavefronts
 // per row -- and by the block barriers between their phases.  Here a row belongs to ONE warp:
 //
-//   state    ~5.5 KB of shared memory per row: a 1024-bucket histogram (4 KB, re-used as the hit list)
-//            and a list of "extra" octets; 32 rows in flight per SM, each on its own warp, no block
-//            barrier anywhere (only __syncwarp).
-//   members  read straight from global memory / L2, one 256-bit load per octet, no staging: sweep A
-//            takes the first octet of each of the lane's leaves (balanced: four leaves per lane at a
-//            time), sweep B the octets beyond the first of all the warp's leaves, flattened through
-//            the small list.  The second pass walks the octets in the REVERSE order of the first, so
-//            that what it re-reads first is what the L2 saw last.
+//   state    shared memory per row: a 1024-bucket histogram (4 KB, re-used as the hit list) and the
+//            flat list of the row's octets (3.7 KB at config 3); 24 rows in flight per SM, each on its
+//            own warp, no block barrier anywhere (only __syncwarp).
+//   members  read straight from global memory / L2, one 256-bit load per octet (predicated: a lane
+//            without an octet loads nothing), no staging.  The octet list (eight leaf words per lane
+//            loaded together, one warp scan per 256 leaves) makes every pass one balanced loop of
+//            32 * UNR octets per step.  The second pass walks the list in the REVERSE order of the
+//            first, so that what it re-reads first is what the L2 saw last.
 //   window   the members of a row sit in a narrow band of the rank axis (the conditional distribution
-//            of y).  The first 128 leaves give [lo, hi); the 1024 buckets cover that band only
+//            of y).  The first 128 octets of the list give [lo, hi); the 1024 buckets cover that band only
 //            (bucket = clamp((rank - lo) >> s)), ranks outside fall into the two edge buckets.
 //   pass 1   one shared-memory RED per member into the histogram.
 //   scan     lane totals of 32 consecutive buckets (rotated 128-bit reads), one warp scan; per
@@ -26,13 +26,18 @@
 //            are empty, so "member of a marked bucket" is one rank interval per percentile.
 //   pass 2   members of marked buckets (a few dozen of a row's 3300 at config 3) are appended to the
 //            hit list (shared-memory counter; their order does not matter, see select).
-//   select   the hits are sorted by rank in registers (bitonic network, 8 keys per lane), weights
+//   select   the hits are sorted by rank in registers (bitonic network, 4 keys per lane; 8 beyond 128 hits), weights
 //            prefix-summed in that order, and lane q finds percentile q's crossing entry and its
 //            neighbours by binary search: because every member of bp, bq and bn is in the list, the
 //            neighbours of the crossing entry are simply the adjacent rank groups of the sorted list.
 //   overflow a row with more than 256 hits narrows each percentile exactly instead: sub-histograms of
 //            the crossing bucket until it is one rank wide, then two more passes for the neighbours and
 //            the merged weights.  Slow (a dozen passes) and rare; tests force it with `select4_hits`.
+//
+// Measured at config 3 ("select4"): 41 ms per 1M rows for the first, fully unrolled
+// version (instruction fetch bound: 17.8 k SASS instructions), 21 ms for this one -- level with select2 and
+// select3, bound by the random 64-byte DRAM accesses of TWO passes (75 MB of octets in flight between them do
+// not stay in the L2).  Opt-in: `select_impl = 4`.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
