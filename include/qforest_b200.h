@@ -51,7 +51,8 @@ typedef enum qf_status {
                              fixed point (leaves of hundreds of members) take the exact kernels.
                              Option "select_impl" = 3 runs it on compact leaf lists (32-byte octets of
                              rank | bootstrap count words, built on the device on first use) with
-                             asynchronous copies; the default reads the 8-byte member array */
+                             asynchronous copies, "select_impl" = 4 with one warp per row and 256-bit
+                             loads (no staging); the default (0) reads the 8-byte member array */
 
 int qf_abi_version(void);
 const char* qf_last_error(void);
@@ -255,8 +256,10 @@ int qf_forest_last_launches(const qf_forest* f);
 int qf_forest_last_timings(qf_forest* f, double* apply_ms, double* quantile_ms);
 
 /* Tuning knobs (bench / tests): key in {"sort_rows", "apply_row_warps", "apply_ilp",
- * "apply_levels", "rows_per_chunk", "cta_capacity", "cta2_capacity", "warp_elems", "warp_unit", "select_bits", "select_impl", "select3_capw", "select3_variant", "select4_hits", "select4_list", "select4_ctas", "select4_unroll", "select4_hints", "key_bins", "dense_ctas",
- * "profile"}.
+ * "apply_levels", "rows_per_chunk", "cta_capacity", "cta2_capacity", "warp_elems", "warp_unit",
+ * "select_bits", "select_impl" (0 auto, 1 multi-level, 2 select2, 3 select3, 4 select4),
+ * "select3_capw", "select3_variant", "select4_hits", "select4_list", "select4_ctas",
+ * "select4_unroll", "select4_hints", "key_bins", "dense_ctas", "profile"}.
  * Returns QF_ERR_INVALID for unknown keys or values. */
 int qf_forest_set_option(qf_forest* f, const char* key, int64_t value);
 
