@@ -259,7 +259,7 @@ int qf_forest_last_timings(qf_forest* f, double* apply_ms, double* quantile_ms);
  * "apply_levels", "rows_per_chunk", "cta_capacity", "cta2_capacity", "warp_elems", "warp_unit",
  * "select_bits", "select_impl" (0 auto, 1 multi-level, 2 select2, 3 select3, 4 select4),
  * "select3_capw", "select3_variant", "select4_hits", "select4_list", "select4_ctas",
- * "select4_unroll", "select4_hints", "key_bins", "dense_ctas", "profile"}.
+ * "select4_unroll", "select4_hints", "compact_align", "key_bins", "dense_ctas", "profile"}.
  * Returns QF_ERR_INVALID for unknown keys or values. */
 int qf_forest_set_option(qf_forest* f, const char* key, int64_t value);
 

@@ -63,7 +63,7 @@ __device__ inline uint32_t leaf_count_sum(const uint2* __restrict__ m, uint32_t 
 // flags: 2 = weights are not count / sum, 4 = rank >= 2^24
 __global__ void __launch_bounds__(256)
 compact_mark_kernel(const uint2* __restrict__ nodes, int64_t n_nodes, const uint2* __restrict__ members,
-                    uint32_t* __restrict__ noct_at, int* __restrict__ flags) {
+                    uint32_t* __restrict__ noct_at, int* __restrict__ flags, int align2) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
     const uint2 nd = nodes[i];
@@ -73,7 +73,11 @@ compact_mark_kernel(const uint2* __restrict__ nodes, int64_t n_nodes, const uint
     if (leaf_count_sum(members + nd.x, cnt) == 0u) { atomicOr(flags, 2); return; }
     if (members[nd.x + cnt - 1].x >= (1u << 24)) { atomicOr(flags, 4); return; }   // lists are sorted by rank
     const uint32_t noct = (cnt + kOctetMembers - 1) / kOctetMembers;
-    noct_at[nd.x] = noct > static_cast<uint32_t>(kCompactMaxOctets) ? noct + 1u : noct;    // long list: + the info octet
+    uint32_t alloc = noct > static_cast<uint32_t>(kCompactMaxOctets) ? noct + 1u : noct;   // long list: + the info octet
+    // align2: a list of two or more octets starts on an even octet (a 64-byte DRAM burst then holds both octets
+    // of a two-octet leaf instead of half of it and half of a stranger); one spare octet pays for the shift
+    if (align2 && alloc >= 2u) ++alloc;
+    noct_at[nd.x] = alloc;
 }
 
 // in-place exclusive scan of a uint32 array in three launches: tile sums, scan of the tile
@@ -164,7 +168,7 @@ scan_apply_kernel(uint32_t* __restrict__ data, int64_t n, const uint64_t* __rest
 __global__ void __launch_bounds__(256)
 compact_fill_kernel(const uint2* __restrict__ nodes, int64_t n_nodes, const uint2* __restrict__ members,
                     const uint32_t* __restrict__ oct_at, float fx_scale, uint32_t n_train,
-                    uint2* __restrict__ nodes_c, uint4* __restrict__ lists) {
+                    uint2* __restrict__ nodes_c, uint4* __restrict__ lists, int align2) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
     uint2 nd = nodes[i];
@@ -179,6 +183,7 @@ compact_fill_kernel(const uint2* __restrict__ nodes, int64_t n_nodes, const uint
             uint32_t first = oct_at[nd.x];
             const uint32_t noct = (cnt + kOctetMembers - 1) / kOctetMembers;
             const bool is_long = noct > static_cast<uint32_t>(kCompactMaxOctets);
+            if (align2 && noct >= 2u) first += first & 1u;          // (compact_mark_kernel reserved the spare octet)
             const uint32_t word = first | ((is_long ? kCompactLong : noct - 1u) << 28);
             if (is_long) {                              // info octet, then the member octets
                 lists[2 * static_cast<size_t>(first)] = make_uint4(noct, 0u, 0u, 0u);

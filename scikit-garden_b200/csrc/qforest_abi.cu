@@ -109,6 +109,7 @@ struct qf_forest {
     int select_bits = qf::kSelectL2Bits;   // log2 refinement slots of the selection kernel (tests lower it)
     int select4_hits = qf::kSelect4Hits;   // hit-list entries a row may use before select4 narrows instead (tests shrink it)
     int select4_ctas = 4;                  // CTAs (of 8 rows) per SM select4 is launched with, at most
+    int compact_align = 0;                 // 1: compact lists of two or more octets start on an even octet (before the lists are built)
     int select4_hints = 0;                 // 1: L2 eviction hints on select4's octet loads (keep after pass 1, drop after pass 2)
     int select4_unroll = 2;                // octets a lane keeps in flight per step of a pass (2 or 4)
     int select4_list = 0;                  // entries of select4's per-row octet list (0 = auto; tests shrink it)
@@ -535,7 +536,7 @@ int ensure_compact(qf_forest* f) {
     QF_CUDA_TRY(cudaMemset(flags, 0, 16));
     QF_CUDA_TRY(cudaMemset(stats, 0, static_cast<size_t>(f->T) * 16));
     const unsigned node_blocks = static_cast<unsigned>((f->n_nodes + 255) / 256);
-    qf::compact_mark_kernel<<<node_blocks, 256>>>(f->d_nodes, f->n_nodes, f->d_members, oct_at, flags);
+    qf::compact_mark_kernel<<<node_blocks, 256>>>(f->d_nodes, f->n_nodes, f->d_members, oct_at, flags, f->compact_align);
     qf::scan_tile_sums_kernel<<<static_cast<unsigned>(n_tiles), 256>>>(oct_at, f->n_members, tile_sum);
     qf::scan_tile_offsets_kernel<<<1, 1024>>>(tile_sum, n_tiles, tile_sum + n_tiles);
     QF_CUDA_TRY(cudaGetLastError());
@@ -556,7 +557,7 @@ int ensure_compact(qf_forest* f) {
     cudaError_t e = cudaMalloc(&nodes_c, static_cast<size_t>(f->n_nodes) * 8);
     if (e == cudaSuccess) e = cudaMalloc(&lists, static_cast<size_t>(n_octets) * 32);
     if (e == cudaSuccess) {
-        qf::compact_fill_kernel<<<node_blocks, 256>>>(f->d_nodes, f->n_nodes, f->d_members, oct_at, fx_scale, static_cast<uint32_t>(f->N), nodes_c, lists);
+        qf::compact_fill_kernel<<<node_blocks, 256>>>(f->d_nodes, f->n_nodes, f->d_members, oct_at, fx_scale, static_cast<uint32_t>(f->N), nodes_c, lists, f->compact_align);
         qf::compact_tree_stats_kernel<<<f->T, 256>>>(f->d_nodes, f->d_roots, f->n_nodes, f->T, stats);
         e = cudaGetLastError();
     }
@@ -1201,6 +1202,11 @@ int qf_forest_set_option(qf_forest* f, const char* key, int64_t value) {
     } else if (k == "select4_ctas") {
         if (value < 1 || value > 4) return qf::fail(QF_ERR_INVALID, "select4_ctas must be in [1, 4]");
         f->select4_ctas = static_cast<int>(value);
+    } else if (k == "compact_align") {
+        if (value != 0 && value != 1) return qf::fail(QF_ERR_INVALID, "compact_align must be 0 or 1");
+        if (f->compact_state != 0 && value != f->compact_align)
+            return qf::fail(QF_ERR_INVALID, "compact_align must be set before the compact lists are built");
+        f->compact_align = static_cast<int>(value);
     } else if (k == "select4_hints") {
         if (value != 0 && value != 1) return qf::fail(QF_ERR_INVALID, "select4_hints must be 0 or 1");
         f->select4_hints = static_cast<int>(value);

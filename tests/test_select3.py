@@ -341,3 +341,20 @@ def test_select4_tree_counts_and_row_counts(T, msl, N, rows):
         dev.set_option("select4_hits", 16)
         same(est.predict(Xt[:rows], quantile=qs), want)
         same(est.predict(Xt[:rows], quantile=[50]), want[:, 1:2])
+
+
+@pytest.mark.parametrize("name", _golden.CASES)
+@pytest.mark.parametrize("impl", [3, 4])
+def test_compact_lists_aligned_to_64_bytes_same_bits(name, impl):
+    # option compact_align = 1 only moves multi-octet lists to even octets (one spare octet each): same results
+    g = _golden.load(name)
+    flat = _golden.flat_from_golden(g)
+    d0 = _dev(flat, warp_elems=0, select_impl=impl)
+    d1 = _dev(flat, warp_elems=0, select_impl=impl, compact_align=1)
+    X = _cuda(g.X_test)
+    qs = g.q[:3]
+    assert d0.quantile_kernel_name(len(g.X_test), 3, FAST) == d1.quantile_kernel_name(len(g.X_test), 3, FAST)
+    assert_array_equal(d1.predict_quantiles(X, qs, mode=FAST).cpu().numpy(),
+                       d0.predict_quantiles(X, qs, mode=FAST).cpu().numpy())
+    d0.close()
+    d1.close()
